@@ -1,0 +1,205 @@
+/* TEST INFRASTRUCTURE ONLY -- synthetic-input generator + uniform-random players for the oracle.
+ *
+ * NOT reference behaviour: the reference deals with random.shuffle on MT19937 and its bots draw
+ * from the random/numpy global streams (Igra.py:67, Igralec.py:151,156,159,166), none of which is
+ * seeded (main.py:174 is commented out).  Parity is therefore by deal/action injection, and this
+ * file restates -- independently, in scalar C on top of tarok_oracle.c's list-based engine -- the
+ * counter-based Philox4x32-10 input generator that the CUDA path uses (DESIGN.md "Synthetic
+ * inputs"), so whole rollouts can be compared at full size on the GPU box:
+ *
+ *   word(gid, stream, idx)  = philox4x32_10(key = seed, ctr = {gid.lo, gid.hi, stream | attempt<<16, idx>>2})[idx&3]
+ *   draw(gid, stream, idx, n) = Lemire multiply-shift with rejection on word(...) -> uniform in [0,n)
+ *   streams: 0 deal, 1 bids, 2 king, 3 exchange, 4 play, 5 forced contract/declarer
+ *
+ * It doubles as bench.py's CPU baseline ("port": OpenMP over games).
+ */
+#include <string.h>
+#include <stdint.h>
+#include "tarok_oracle.h"
+
+#define PH_M0 0xD2511F53u
+#define PH_M1 0xCD9E8D57u
+#define PH_W0 0x9E3779B9u
+#define PH_W1 0xBB67AE85u
+
+void syn_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)PH_M0 * c[0];
+        uint64_t p1 = (uint64_t)PH_M1 * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += PH_W0; k1 += PH_W1;
+    }
+}
+
+uint32_t syn_draw(uint64_t seed, uint64_t gid, uint32_t stream, uint32_t idx, uint32_t n) {
+    for (uint32_t attempt = 0;; attempt++) {
+        uint32_t c[4] = { (uint32_t)gid, (uint32_t)(gid >> 32), stream | (attempt << 16), idx >> 2 };
+        syn_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint64_t m = (uint64_t)c[idx & 3] * n;
+        uint32_t lo = (uint32_t)m;
+        if (lo >= n) return (uint32_t)(m >> 32);
+        uint32_t t = (0u - n) % n;
+        if (lo >= t) return (uint32_t)(m >> 32);
+    }
+}
+
+enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5 };
+enum { MODE_NAVADNA_MIX = 16, MODE_AUCTION_UNIFORM = 17, MODE_AUCTION_BOT = 18 };
+
+/* Uniform deal: card c = 0..53 goes to a uniformly random free slot among the 54-c left
+   (slots: 12 per seat, then the 6 ordered talon positions).  Exported as the permutation
+   Igra.razdeli would have consumed: seat slices ascending by id, talon in order. */
+void syn_deal(uint64_t seed, uint64_t gid, uint8_t perm[54]) {
+    int cap[4] = { 12, 12, 12, 12 }, fill[4] = { 0, 0, 0, 0 };
+    int talon_free = 0x3F;
+    for (int c = 0; c < 54; c++) {
+        uint32_t r = syn_draw(seed, gid, ST_DEAL, (uint32_t)c, (uint32_t)(54 - c));
+        int s;
+        for (s = 0; s < 4; s++) {
+            if (r < (uint32_t)cap[s]) break;
+            r -= (uint32_t)cap[s];
+        }
+        if (s < 4) { perm[12 * s + fill[s]++] = (uint8_t)c; cap[s]--; }
+        else {
+            int slot = 0;
+            for (;; slot++) if ((talon_free >> slot) & 1) { if (r == 0) break; r--; }
+            talon_free &= ~(1 << slot);
+            perm[48 + slot] = (uint8_t)c;
+        }
+    }
+}
+
+/* Nevronski_igralec.index2igra (Igralec.py:717-745): 0 (Naprej,-), 1-4 (Tri,suit), 5-8 (Dve,suit),
+   9-12 (Ena,suit), 13 Solo_tri, 14 Solo_dve, 15 Solo_ena, 16 Berac, 17 Solo_brez */
+static void index2igra(int idx, int* tip, int* suit) {
+    if (idx == 0) { *tip = ORC_NAPREJ; *suit = ORC_NO_KING; }
+    else if (idx <= 12) { *tip = ORC_TRI + (idx - 1) / 4; *suit = (idx - 1) % 4; }
+    else { static const int t[5] = { ORC_SOLO_TRI, ORC_SOLO_DVE, ORC_SOLO_ENA, ORC_BERAC, ORC_SOLO_BREZ };
+           *tip = t[idx - 13]; *suit = ORC_NO_KING; }
+}
+
+typedef struct { uint64_t seed, gid; int tip[4]; } bid_ctx;
+static int want_uniform(void* p, int seat, int call) { (void)call; return ((bid_ctx*)p)->tip[seat]; }
+static int want_bot(void* p, int seat, int call) {
+    (void)seat;
+    bid_ctx* b = (bid_ctx*)p;     /* np.random.choice([Naprej,Tri,Dve,Ena], p=[.5,1/6,1/6,1/6]), Igralec.py:151 */
+    uint32_t u = syn_draw(b->seed, b->gid, ST_BID, (uint32_t)call, 6);
+    return u < 3 ? ORC_NAPREJ : (int)(ORC_TRI + (u - 3));
+}
+
+static int nth_lowest(uint64_t m, uint32_t r) {
+    for (int c = 0; c < 54; c++) if ((m >> c) & 1) { if (r == 0) return c; r--; }
+    return -1;
+}
+
+/* One whole deal with uniform-random players.  Returns 0, or -1 if the game hit an error state. */
+int syn_rollout(uint64_t seed, uint64_t gid, int mode, orc_game* g, uint8_t perm[54],
+                uint8_t cards[48], uint8_t* group_out, uint64_t* discard_out) {
+    syn_deal(seed, gid, perm);
+    orc_razdeli(g, perm);
+    int contract, declarer = 0, king = ORC_NO_KING;
+    if (mode == MODE_AUCTION_UNIFORM || mode == MODE_AUCTION_BOT) {
+        bid_ctx b; b.seed = seed; b.gid = gid;
+        int suit[4];
+        if (mode == MODE_AUCTION_UNIFORM)
+            for (int s = 0; s < 4; s++) index2igra((int)syn_draw(seed, gid, ST_BID, (uint32_t)s, 18), &b.tip[s], &suit[s]);
+        orc_licitacija(mode == MODE_AUCTION_UNIFORM ? want_uniform : want_bot, &b,
+                       mode == MODE_AUCTION_UNIFORM, &declarer, &contract, 0);
+        if (contract >= ORC_TRI && contract <= ORC_ENA)
+            king = mode == MODE_AUCTION_UNIFORM ? suit[declarer] : (int)syn_draw(seed, gid, ST_KING, 0, 4);
+    } else {
+        contract = mode == MODE_NAVADNA_MIX ? (int)(ORC_TRI + syn_draw(seed, gid, ST_FORCE, 0, 3)) : mode;
+        if (contract != ORC_KLOP) declarer = (int)syn_draw(seed, gid, ST_FORCE, 1, 4);
+        if (contract >= ORC_TRI && contract <= ORC_ENA) king = (int)syn_draw(seed, gid, ST_KING, 0, 4);
+    }
+    orc_zacni_igro(g, contract, declarer, king);
+    *group_out = ORC_NO_GROUP; *discard_out = 0;
+    memset(cards, 0xFF, 48);
+    if (g->phase == 1) {
+        int k = orc_talon_k(contract);
+        int grp = mode == MODE_AUCTION_UNIFORM ? (int)syn_draw(seed, gid, ST_EXCH, 0, g->group_cnt) : 0;
+        /* discardable set after the pick-up: Roka.mozno_zalozit on hand + group (Igralec.py:163-166) */
+        uint64_t avail = 0;
+        orc_game tmp = *g;
+        for (int j = 0; j < tmp.group_sz; j++) {
+            int c = tmp.group[grp][j];
+            int b = orc_iz_id(c).barva;
+            tmp.hand[declarer][b][tmp.hand_n[declarer][b]++] = (uint8_t)c;
+        }
+        uint8_t mz[16];
+        int nm = orc_mozno_zalozit(&tmp, declarer, mz);
+        for (int i = 0; i < nm; i++) avail |= 1ull << mz[i];
+        uint8_t d[3];
+        uint64_t dm = 0;
+        if (nm < k) { g->error = 1; return -1; }
+        for (int j = 0; j < k; j++) {
+            uint32_t r = syn_draw(seed, gid, ST_EXCH, (uint32_t)(1 + j), (uint32_t)__builtin_popcountll(avail));
+            int c = nth_lowest(avail, r);
+            d[j] = (uint8_t)c; avail &= ~(1ull << c); dm |= 1ull << c;
+        }
+        *group_out = (uint8_t)grp; *discard_out = dm;
+        orc_menjaj(g, grp, d, k);
+    }
+    int t = 0;
+    while (!g->error && g->phase == 2) {
+        uint64_t m = orc_mozne_mask(g);
+        uint32_t r = syn_draw(seed, gid, ST_PLAY, (uint32_t)t, (uint32_t)__builtin_popcountll(m));
+        int c = nth_lowest(m, r);
+        cards[t++] = (uint8_t)c;
+        orc_igraj(g, c);
+    }
+    return g->error ? -1 : 0;
+}
+
+/* Batch driver (OpenMP over games).  Any out pointer may be NULL. */
+void syn_rollout_batch(uint64_t seed, uint64_t first_gid, int64_t n, int mode,
+                       int16_t* out_scores, uint8_t* out_plays, uint8_t* out_contract,
+                       uint8_t* out_declarer, uint8_t* out_king, uint8_t* out_err,
+                       uint8_t* out_perm, uint8_t* out_cards, uint8_t* out_group, uint64_t* out_discard,
+                       int64_t* out_stats /* [4 seat sums, 4 player sums, env steps, errors] */) {
+    int64_t st[10] = { 0 };
+#pragma omp parallel
+    {
+        int64_t loc[10] = { 0 };
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; i++) {
+            orc_game g;
+            uint8_t perm[54], cards[48], grp;
+            uint64_t dm;
+            uint64_t gid = first_gid + (uint64_t)i;
+            syn_rollout(seed, gid, mode, &g, perm, cards, &grp, &dm);
+            int fin = g.phase == 3 && !g.error;
+            for (int s = 0; s < 4; s++) {
+                int v = fin ? g.pisejo[s] : 0;
+                if (out_scores) out_scores[4 * i + s] = (int16_t)v;
+                loc[s] += v;
+                loc[4 + ((s + gid) & 3)] += v;        /* seat s of game i is player (s+i)%4, Tarok.py:34 */
+            }
+            loc[8] += g.plays;
+            loc[9] += g.error ? 1 : 0;
+            if (out_plays) out_plays[i] = (uint8_t)g.plays;
+            if (out_contract) out_contract[i] = (uint8_t)g.contract;
+            if (out_declarer) out_declarer[i] = (uint8_t)g.declarer;
+            if (out_king) out_king[i] = (uint8_t)g.king;
+            if (out_err) out_err[i] = (uint8_t)(g.error ? 1 : 0);
+            if (out_perm) memcpy(out_perm + 54 * i, perm, 54);
+            if (out_cards) memcpy(out_cards + 48 * i, cards, 48);
+            if (out_group) out_group[i] = grp;
+            if (out_discard) out_discard[i] = dm;
+        }
+#pragma omp critical
+        for (int j = 0; j < 10; j++) st[j] += loc[j];
+    }
+    if (out_stats) memcpy(out_stats, st, sizeof(st));
+}
+
+void syn_deal_batch(uint64_t seed, uint64_t first_gid, int64_t n, uint8_t* out_perm) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) syn_deal(seed, first_gid + (uint64_t)i, out_perm + 54 * i);
+}
+
+void syn_philox_kat(uint32_t c[4], uint32_t k0, uint32_t k1) { syn_philox4x32_10(c, k0, k1); }
