@@ -1,0 +1,159 @@
+/* tarok_b200 -- C ABI of the B200-native batched Tarok environment (libtarok_b200.so).
+ *
+ * The reference (anzeA/Tarok) is pure Python and has no FFI; its seam is the Python class API
+ * between the engine (Tarok.py / Igra.py / Navadna_igra.py / Klop.py / Berac.py) and the players
+ * (Igralec.py).  Each entry point below names the reference code it replaces ("File.py:N" is a
+ * path into the reference tree).  The reference-side binding a maintainer would add is the ctypes
+ * stub shown in INTEGRATION.md (and shipped as tarok_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - every function returns 0 on success, <0 on error; tarok_last_error() gives the text.
+ *   - "dev" pointers are CUDA device pointers on the handle's device; "host" pointers are host
+ *     memory (pinned memory makes the copies asynchronous).
+ *   - all device work is enqueued on the caller's stream (a cudaStream_t passed as void*;
+ *     NULL = legacy default stream).  No hidden synchronisation unless stated.
+ *   - a handle is not thread-safe; use one handle per GPU per thread.
+ *   - state lives in the handle as structure-of-arrays of 64-bit bitboards (bit i = card id i,
+ *     Karta.v_id, Karta.py:19-23) and is lent out zero-copy as DLPack tensors (tarok_export);
+ *     the 64-bit words are typed int64 in DLPack (bit 63 is never set) because torch lacks uint64 ops.
+ *   - an illegal action does not raise (the reference raises, Navadna_igra.py:125-126): the game's
+ *     error bit is set in `meta`, the game stops, and the error counter in `stats` increments.
+ */
+#ifndef TAROK_B200_H
+#define TAROK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tarok_env tarok_t;
+
+/* ---- DLPack (v0.8 ABI subset; identical layout to dlpack.h) ------------------------------- */
+#ifndef DLPACK_DLPACK_H_
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;       /* kDLCUDA = 2 */
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;  /* kDLInt=0 kDLUInt=1 */
+typedef struct {
+    void* data; DLDevice device; int32_t ndim; DLDataType dtype;
+    int64_t* shape; int64_t* strides; uint64_t byte_offset;
+} DLTensor;
+typedef struct DLManagedTensor {
+    DLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct DLManagedTensor* self);
+} DLManagedTensor;
+#endif
+
+/* ---- constants ----------------------------------------------------------------------------- */
+/* contract code = Tip_igre value / 10 (Tip_igre.py:5-15) */
+enum { TAROK_KLOP = 0, TAROK_TRI = 1, TAROK_DVE = 2, TAROK_ENA = 3, TAROK_SOLO_TRI = 4,
+       TAROK_SOLO_DVE = 5, TAROK_SOLO_ENA = 6, TAROK_BERAC = 7, TAROK_SOLO_BREZ = 8,
+       TAROK_ODPRTI_BERAC = 9 };
+#define TAROK_NO_KING 7
+#define TAROK_NO_GROUP 0xFF
+/* synthetic-input modes (DESIGN.md "Synthetic inputs") */
+#define TAROK_MODE_NAVADNA_MIX 16      /* Tri/Dve/Ena uniform, declarer & king uniform (config 2) */
+#define TAROK_MODE_AUCTION_UNIFORM 17  /* one uniform index2igra intent per seat, random talon group */
+#define TAROK_MODE_AUCTION_BOT 18      /* Bot_igralec bidding distribution, group 0 */
+/* flags for tarok_create */
+#define TAROK_FLAG_HISTORY 1u          /* keep the play history (seat<<6|card per play) for observations */
+/* exportable fields */
+enum { TAROK_F_HANDS = 0,   /* uint64 [4, n_alloc]  hand bitboard of seat s        (Roka, Roka.py:4-13)      */
+       TAROK_F_PILES = 1,   /* uint64 [4, n_alloc]  won-cards pile of seat s       (Igralec.kupcek)          */
+       TAROK_F_TALON = 2,   /* uint64 [n_alloc]     cards still in the talon                                 */
+       TAROK_F_TALON_ORDER = 3, /* uint64 [n_alloc] the 6 talon ids in dealt order, 6 bits each (Igra.py:68) */
+       TAROK_F_META = 4,    /* uint64 [n_alloc]     packed contract / trick state (layout in DESIGN.md)      */
+       TAROK_F_MASK = 5,    /* uint64 [n_alloc]     legal-move mask of the seat to move                      */
+       TAROK_F_SCORES = 6,  /* int16  [n_alloc, 4]  pisejo by seat                                           */
+       TAROK_F_HIST = 7,    /* uint8  [48, n_alloc] play t of game g: seat<<6|card, 0xFF = not played        */
+       TAROK_F_STATS = 8,   /* int64  [32]          accumulated statistics (layout below)                    */
+       TAROK_F_HANDS0 = 9,  /* uint64 [4, n_alloc]  hands as dealt (Nevronski_igralec.zacetna_roka); HISTORY flag */
+       TAROK_F_DISCARD = 10 /* uint64 [n_alloc]     declarer's discards (zalozil); HISTORY flag              */
+};
+/* stats vector: [0..3] score sum by seat, [4..7] score sum by player ((seat+game_id)%4, Tarok.py:34,59-61),
+   [8..17] contract histogram, [18] finished deals, [19] env-steps (card plays), [20] error games */
+#define TAROK_STATS_LEN 32
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, tarok_t** out);
+int tarok_destroy(tarok_t* h);                 /* error if exported tensors are still alive */
+const char* tarok_last_error(const tarok_t* h);/* h may be NULL: last error of a failed tarok_create */
+uint64_t tarok_n_games(const tarok_t* h);
+uint64_t tarok_n_alloc(const tarok_t* h);      /* n_games rounded up to the kernel tile */
+
+/* ---- deal: Igra.razdeli (Igra.py:65-73) ------------------------------------------------------ */
+/* Philox4x32-10 deal, replayable from (seed, global game id); game g of this handle is global
+   game first_global_game_id + g.  Resets piles, meta and the per-game error bits. */
+int tarok_deal(tarok_t* h, uint64_t first_global_game_id, void* stream);
+/* Deal injection: perm_dev is uint8 [n_games, 54]; seat i gets perm[12i:12i+12], talon = perm[48:54]
+   in order -- exactly what a patched Igra.shuffle (Igra.py:10,67) would feed Igra.razdeli. */
+int tarok_set_deals(tarok_t* h, const uint8_t* perm_dev, uint64_t first_global_game_id, void* stream);
+/* The current deal as the permutation Igra.razdeli would have consumed (hand slices ascending by id).
+   Only meaningful before the talon exchange.  out_dev: uint8 [n_games, 54]. */
+int tarok_export_perm(tarok_t* h, uint8_t* out_dev, void* stream);
+
+/* ---- auction + dispatch: Igra.licitacija (Igra.py:75-114), Igralec.licitiram filter
+        (Igralec.py:58-74), Igra.start dispatch (Igra.py:38-58), Navadna_igra.__init__ teams
+        (Navadna_igra.py:20-30) ------------------------------------------------------------------ */
+/* intent_dev: uint8 [n_games, 4]; one bid intent per seat as an index into
+   Nevronski_igralec.index2igra (Igralec.py:717-745): 0 Naprej, 1-12 (Tri|Dve|Ena, king suit),
+   13-15 Solo_tri/dve/ena, 16 Berac, 17 Solo_brez; additionally 18 Odprti_berac, 19 Klop.
+   Fixed-intent semantics of Nevronski_igralec.licitiram (Igralec.py:294-306). */
+int tarok_auction(tarok_t* h, const uint8_t* intent_dev, void* stream);
+int tarok_auction_synth(tarok_t* h, uint32_t mode /* 17 | 18 */, void* stream);
+/* Bypass bidding like the per-contract constructors Klop(...)/Navadna_igra(...)/Berac(...).
+   contract_dev/declarer_dev/king_dev: uint8 [n_games] (king ignored unless Tri/Dve/Ena). */
+int tarok_force_contract(tarok_t* h, const uint8_t* contract_dev, const uint8_t* declarer_dev,
+                         const uint8_t* king_dev, void* stream);
+int tarok_force_contract_synth(tarok_t* h, uint32_t mode /* 0..9 | 16 */, void* stream);
+
+/* ---- talon exchange: Navadna_igra.odpri_talon + start (Navadna_igra.py:36-68),
+        Roka.mozno_zalozit (Roka.py:23-27), player side Igralec.py:161-171 ---------------------- */
+/* group_dev: uint8 [n_games] chosen group; discard_dev: uint64 [n_games] bitboard of the k cards laid
+   down.  Only games waiting for an exchange are touched. */
+int tarok_exchange(tarok_t* h, const uint8_t* group_dev, const uint64_t* discard_dev, void* stream);
+int tarok_exchange_synth(tarok_t* h, uint32_t random_group, void* stream);
+
+/* ---- play: mozne_karte (Navadna_igra.py:158-168, Klop.py:96-133), krog (Navadna_igra.py:115-141,
+        Klop.py:47-79), pobere_stih/primerjaj_karti (Navadna_igra.py:143-156), Berac.start
+        (Berac.py:13-44) --------------------------------------------------------------------------- */
+int tarok_legal_mask(tarok_t* h, uint64_t* out_dev, void* stream);   /* recomputed from the state */
+int tarok_step(tarok_t* h, const uint8_t* card_dev, void* stream);   /* one card per live game */
+int tarok_step_random(tarok_t* h, void* stream);                     /* uniform-random legal card */
+int tarok_steps_random(tarok_t* h, uint32_t count, void* stream);    /* `count` back-to-back random steps */
+
+/* ---- scoring: Roka.prestej (Roka.py:55-98), epilogues Navadna_igra.py:80-113, Klop.py:36-45,
+        Berac.py:33-44; Tarok.rezultati accumulation (Tarok.py:59-61) --------------------------- */
+int tarok_score(tarok_t* h, int16_t* out_dev /* [n_games,4] or NULL */, void* stream);
+int tarok_reset_stats(tarok_t* h, void* stream);
+int tarok_read_stats(tarok_t* h, int64_t* out_host /* [32] */, void* stream); /* synchronises stream */
+
+/* ---- whole deals ----------------------------------------------------------------------------- */
+/* Stepwise pipeline with in-kernel uniform-random players: deal -> contract(mode) -> exchange ->
+   48 x step_random -> score.  Equivalent to Tarok.paralel_start with Bot-like players. */
+int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream);
+/* Same result, one fused kernel with the state in registers (not HBM-bound). */
+int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream);
+/* Host-buffer entry (the end-to-end path): uploads injected deals (uint8 [n,54]) and forced
+   contracts (uint8 [n] each; king may be NULL for non-king games), plays them with uniform-random
+   players, downloads scores (int16 [n,4]) and the stats vector (int64 [32]).  Asynchronous on
+   `stream` when the host buffers are pinned; the caller synchronises. */
+int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host,
+                       const uint8_t* declarer_host, const uint8_t* king_host,
+                       uint64_t first_global_game_id, int fused,
+                       int16_t* scores_host, int64_t* stats_host, void* stream);
+
+/* ---- zero-copy views ------------------------------------------------------------------------- */
+/* Lends a field as a DLPack tensor that aliases the handle's device memory.  The caller (e.g.
+   torch.from_dlpack) must call the deleter; the handle cannot be destroyed before that. */
+int tarok_export(tarok_t* h, int field, DLManagedTensor** out);
+/* Raw device pointer of a field (same memory as tarok_export), for C callers. */
+void* tarok_field_ptr(tarok_t* h, int field);
+
+/* Number of kernels this library has launched on the handle since creation (bench bookkeeping). */
+uint64_t tarok_launch_count(const tarok_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAROK_B200_H */

@@ -50,12 +50,16 @@ uint32_t syn_draw(uint64_t seed, uint64_t gid, uint32_t stream, uint32_t idx, ui
 enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5 };
 enum { MODE_NAVADNA_MIX = 16, MODE_AUCTION_UNIFORM = 17, MODE_AUCTION_BOT = 18 };
 
-/* Uniform deal: card c = 0..53 goes to a uniformly random free slot among the 54-c left
-   (slots: 12 per seat, then the 6 ordered talon positions).  Exported as the permutation
-   Igra.razdeli would have consumed: seat slices ascending by id, talon in order. */
+/* Uniform deal: card c = 0..53 goes to a uniformly random free slot among the 54-c left; slots
+   are exchangeable inside a pile, so this is a walk over the remaining capacities of the piles
+   (seat 0..3: 12 each, then the talon: 6).  The ORDER of the six talon cards (it matters:
+   Navadna_igra.py:44, Klop.py:69) is a uniform permutation decoded from one more draw (idx 54,
+   n = 720, Lehmer code over the talon ids in ascending order).  Exported as the permutation
+   Igra.razdeli would have consumed: seat slices ascending by id, then the ordered talon. */
 void syn_deal(uint64_t seed, uint64_t gid, uint8_t perm[54]) {
     int cap[4] = { 12, 12, 12, 12 }, fill[4] = { 0, 0, 0, 0 };
-    int talon_free = 0x3F;
+    uint8_t tal[6];
+    int nt = 0;
     for (int c = 0; c < 54; c++) {
         uint32_t r = syn_draw(seed, gid, ST_DEAL, (uint32_t)c, (uint32_t)(54 - c));
         int s;
@@ -64,12 +68,17 @@ void syn_deal(uint64_t seed, uint64_t gid, uint8_t perm[54]) {
             r -= (uint32_t)cap[s];
         }
         if (s < 4) { perm[12 * s + fill[s]++] = (uint8_t)c; cap[s]--; }
-        else {
-            int slot = 0;
-            for (;; slot++) if ((talon_free >> slot) & 1) { if (r == 0) break; r--; }
-            talon_free &= ~(1 << slot);
-            perm[48 + slot] = (uint8_t)c;
-        }
+        else tal[nt++] = (uint8_t)c;
+    }
+    uint32_t L = syn_draw(seed, gid, ST_DEAL, 54, 720);
+    static const uint32_t fact[6] = { 120, 24, 6, 2, 1, 1 };
+    int left = 6;
+    for (int i = 0; i < 6; i++) {
+        uint32_t d = L / fact[i];
+        L -= d * fact[i];
+        perm[48 + i] = tal[d];
+        memmove(tal + d, tal + d + 1, (size_t)(left - (int)d - 1));
+        left--;
     }
 }
 

@@ -1,0 +1,456 @@
+// C ABI of libtarok_b200.so (declared in include/tarok_b200.h): handle, device buffers, launches.
+// No torch, no C++ types across the boundary.  Every launch goes to the caller's stream.
+#include "../../include/tarok_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "tarok_kernels.cuh"
+
+using tk::u64;
+using tk::u32;
+
+struct tarok_env {
+    int device;
+    u32 flags;
+    tk::Env e;
+    // staging buffers of the host-buffer entry point
+    uint8_t* st_perm; uint8_t* st_contract; uint8_t* st_declarer; uint8_t* st_king;
+    std::atomic<int> exports;
+    u64 launches;
+    char err[512];
+};
+
+static thread_local char g_create_err[512] = "";
+
+static int fail(tarok_env* h, int code, const char* fmt, ...) {
+    char* dst = h ? h->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define TK_CUDA(h, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(h, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define TK_CHECK_HANDLE(h) do { if (!(h)) return fail(nullptr, -1, "null handle"); } while (0)
+#define TK_LAUNCH_OK(h)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) return fail(h, -3, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+        (h)->launches++;                                                                          \
+    } while (0)
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline unsigned grid1(u64 n_alloc) { return (unsigned)(n_alloc / tk::CTA); }        // one game per lane
+static inline unsigned grid2(u64 n_alloc) { return (unsigned)(n_alloc / tk::TILE); }       // two games per lane
+
+struct DeviceGuard {
+    int prev; bool ok;
+    explicit DeviceGuard(int dev) : prev(0), ok(false) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() { if (ok) cudaSetDevice(prev); }
+};
+
+extern "C" {
+
+int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, tarok_t** out) {
+    if (!out) return fail(nullptr, -1, "out is null");
+    *out = nullptr;
+    if (n_games == 0) return fail(nullptr, -1, "n_games must be > 0");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(nullptr, -2, "no CUDA device: %s (tarok_b200 has no CPU fallback)", cudaGetErrorString(ce));
+    if (device < 0 || device >= count) return fail(nullptr, -1, "device %d out of range (0..%d)", device, count - 1);
+    DeviceGuard dg(device);
+    cudaDeviceProp prop;
+    TK_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, -2, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    tarok_env* h = new (std::nothrow) tarok_env();
+    if (!h) return fail(nullptr, -4, "out of host memory");
+    memset(&h->e, 0, sizeof(h->e));
+    h->device = device; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
+    h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
+    const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
+    h->e.n = n_games; h->e.n_alloc = na; h->e.seed = seed; h->e.first_gid = 0;
+#define TK_ALLOC(ptr, bytes)                                                       \
+    do {                                                                           \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                      \
+        if (_e != cudaSuccess) {                                                   \
+            fail(nullptr, -4, "cudaMalloc(%llu B) failed: %s", (unsigned long long)(bytes), cudaGetErrorString(_e)); \
+            tarok_destroy(h);                                                      \
+            return -4;                                                             \
+        }                                                                          \
+    } while (0)
+    TK_ALLOC(h->e.hands, 4 * na * 8);
+    TK_ALLOC(h->e.piles, 4 * na * 8);
+    TK_ALLOC(h->e.talon, na * 8);
+    TK_ALLOC(h->e.torder, na * 8);
+    TK_ALLOC(h->e.meta, na * 8);
+    TK_ALLOC(h->e.mask, na * 8);
+    TK_ALLOC(h->e.scores, na * 8);
+    TK_ALLOC(h->e.stats, TAROK_STATS_LEN * 8);
+    if (flags & TAROK_FLAG_HISTORY) {
+        TK_ALLOC(h->e.hist, 48 * na);
+        TK_ALLOC(h->e.hands0, 4 * na * 8);
+        TK_ALLOC(h->e.discard, na * 8);
+        cudaMemset(h->e.hist, 0xFF, 48 * na);
+    }
+#undef TK_ALLOC
+    cudaMemset(h->e.stats, 0, TAROK_STATS_LEN * 8);
+    cudaMemset(h->e.scores, 0, na * 8);
+    cudaMemset(h->e.mask, 0, na * 8);
+    // every game starts "finished/padded" until dealt
+    {
+        tk::Env e = h->e; e.n = 0;
+        tk::k_deal<<<grid1(na), tk::CTA>>>(e);
+        cudaError_t _e = cudaDeviceSynchronize();
+        if (_e != cudaSuccess) {
+            fail(nullptr, -3, "initial kernel failed: %s (is libtarok_b200.so built for this GPU?)", cudaGetErrorString(_e));
+            tarok_destroy(h);
+            return -3;
+        }
+    }
+    *out = h;
+    return 0;
+}
+
+int tarok_destroy(tarok_t* h) {
+    if (!h) return 0;
+    if (h->exports.load() != 0) return fail(h, -5, "%d exported tensors still alive", h->exports.load());
+    DeviceGuard dg(h->device);
+    cudaFree(h->e.hands); cudaFree(h->e.piles); cudaFree(h->e.talon); cudaFree(h->e.torder);
+    cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats);
+    cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard);
+    cudaFree(h->st_perm); cudaFree(h->st_contract); cudaFree(h->st_declarer); cudaFree(h->st_king);
+    delete h;
+    return 0;
+}
+
+const char* tarok_last_error(const tarok_t* h) { return h ? h->err : g_create_err; }
+uint64_t tarok_n_games(const tarok_t* h) { return h ? h->e.n : 0; }
+uint64_t tarok_n_alloc(const tarok_t* h) { return h ? h->e.n_alloc : 0; }
+uint64_t tarok_launch_count(const tarok_t* h) { return h ? h->launches : 0; }
+
+// ---- deal ---------------------------------------------------------------------------------------
+
+static void clear_hist(tarok_t* h, void* stream) {
+    if (h->e.hist) cudaMemsetAsync(h->e.hist, 0xFF, 48 * h->e.n_alloc, S(stream));
+}
+
+int tarok_deal(tarok_t* h, uint64_t first_global_game_id, void* stream) {
+    TK_CHECK_HANDLE(h);
+    DeviceGuard dg(h->device);
+    h->e.first_gid = first_global_game_id;
+    clear_hist(h, stream);
+    tk::k_deal<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_set_deals(tarok_t* h, const uint8_t* perm_dev, uint64_t first_global_game_id, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!perm_dev) return fail(h, -1, "perm_dev is null");
+    DeviceGuard dg(h->device);
+    h->e.first_gid = first_global_game_id;
+    clear_hist(h, stream);
+    tk::k_set_deals<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, perm_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_export_perm(tarok_t* h, uint8_t* out_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!out_dev) return fail(h, -1, "out_dev is null");
+    DeviceGuard dg(h->device);
+    tk::k_export_perm<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, out_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+// ---- auction / contract -----------------------------------------------------------------------------
+
+int tarok_auction(tarok_t* h, const uint8_t* intent_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!intent_dev) return fail(h, -1, "intent_dev is null");
+    if (((uintptr_t)intent_dev) & 3u) return fail(h, -1, "intent_dev must be 4-byte aligned");
+    DeviceGuard dg(h->device);
+    tk::k_begin<tk::SRC_INTENTS><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, 0u, intent_dev, nullptr, nullptr);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_auction_synth(tarok_t* h, uint32_t mode, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (mode != TAROK_MODE_AUCTION_UNIFORM && mode != TAROK_MODE_AUCTION_BOT) return fail(h, -1, "bad auction mode %u", mode);
+    DeviceGuard dg(h->device);
+    tk::k_begin<tk::SRC_SYNTH><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_force_contract(tarok_t* h, const uint8_t* contract_dev, const uint8_t* declarer_dev, const uint8_t* king_dev,
+                         void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!contract_dev || !declarer_dev) return fail(h, -1, "contract_dev/declarer_dev is null");
+    DeviceGuard dg(h->device);
+    tk::k_begin<tk::SRC_FORCED><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, 0u, contract_dev, declarer_dev, king_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_force_contract_synth(tarok_t* h, uint32_t mode, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!(mode <= TAROK_ODPRTI_BERAC || mode == TAROK_MODE_NAVADNA_MIX)) return fail(h, -1, "bad contract mode %u", mode);
+    DeviceGuard dg(h->device);
+    tk::k_begin<tk::SRC_SYNTH><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+// ---- exchange ---------------------------------------------------------------------------------------
+
+int tarok_exchange(tarok_t* h, const uint8_t* group_dev, const uint64_t* discard_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!group_dev || !discard_dev) return fail(h, -1, "group_dev/discard_dev is null");
+    DeviceGuard dg(h->device);
+    tk::k_exchange<false><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, 0u, group_dev, (const u64*)discard_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_exchange_synth(tarok_t* h, uint32_t random_group, void* stream) {
+    TK_CHECK_HANDLE(h);
+    DeviceGuard dg(h->device);
+    tk::k_exchange<true><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, random_group, nullptr, nullptr);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+// ---- play -------------------------------------------------------------------------------------------
+
+int tarok_legal_mask(tarok_t* h, uint64_t* out_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!out_dev) return fail(h, -1, "out_dev is null");
+    if (((uintptr_t)out_dev) & 15u) return fail(h, -1, "out_dev must be 16-byte aligned");
+    DeviceGuard dg(h->device);
+    tk::k_legal_mask<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, (u64*)out_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_step(tarok_t* h, const uint8_t* card_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!card_dev) return fail(h, -1, "card_dev is null");
+    if (((uintptr_t)card_dev) & 1u) return fail(h, -1, "card_dev must be 2-byte aligned");
+    DeviceGuard dg(h->device);
+    tk::k_step<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, card_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_step_random(tarok_t* h, void* stream) {
+    TK_CHECK_HANDLE(h);
+    DeviceGuard dg(h->device);
+    tk::k_step<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, nullptr);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_steps_random(tarok_t* h, uint32_t count, void* stream) {
+    TK_CHECK_HANDLE(h);
+    DeviceGuard dg(h->device);
+    for (uint32_t t = 0; t < count; t++) {
+        tk::k_step<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, nullptr);
+        TK_LAUNCH_OK(h);
+    }
+    return 0;
+}
+
+// ---- score / stats ----------------------------------------------------------------------------------
+
+int tarok_score(tarok_t* h, int16_t* out_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (out_dev && (((uintptr_t)out_dev) & 15u)) return fail(h, -1, "out_dev must be 16-byte aligned");
+    DeviceGuard dg(h->device);
+    u64* out = out_dev ? (u64*)out_dev : h->e.scores;
+    u64 out_n = out_dev ? h->e.n : h->e.n_alloc;
+    tk::k_score<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, out, out_n);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_reset_stats(tarok_t* h, void* stream) {
+    TK_CHECK_HANDLE(h);
+    DeviceGuard dg(h->device);
+    TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, S(stream)));
+    return 0;
+}
+
+int tarok_read_stats(tarok_t* h, int64_t* out_host, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!out_host) return fail(h, -1, "out_host is null");
+    DeviceGuard dg(h->device);
+    TK_CUDA(h, cudaMemcpyAsync(out_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, S(stream)));
+    TK_CUDA(h, cudaStreamSynchronize(S(stream)));
+    return 0;
+}
+
+// ---- whole deals --------------------------------------------------------------------------------------
+
+static int play_out_stepwise(tarok_t* h, uint32_t random_group, void* stream) {
+    tk::k_exchange<true><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, random_group, nullptr, nullptr);
+    TK_LAUNCH_OK(h);
+    for (int t = 0; t < 48; t++) {
+        tk::k_step<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, nullptr);
+        TK_LAUNCH_OK(h);
+    }
+    tk::k_score<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream) {
+    TK_CHECK_HANDLE(h);
+    int rc = tarok_deal(h, first_global_game_id, stream);
+    if (rc) return rc;
+    if (mode == TAROK_MODE_AUCTION_UNIFORM || mode == TAROK_MODE_AUCTION_BOT) rc = tarok_auction_synth(h, mode, stream);
+    else rc = tarok_force_contract_synth(h, mode, stream);
+    if (rc) return rc;
+    DeviceGuard dg(h->device);
+    return play_out_stepwise(h, mode == TAROK_MODE_AUCTION_UNIFORM, stream);
+}
+
+int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!(mode <= TAROK_ODPRTI_BERAC || (mode >= TAROK_MODE_NAVADNA_MIX && mode <= TAROK_MODE_AUCTION_BOT)))
+        return fail(h, -1, "bad mode %u", mode);
+    DeviceGuard dg(h->device);
+    h->e.first_gid = first_global_game_id;
+    clear_hist(h, stream);
+    tk::k_rollout_fused<false><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr, nullptr,
+                                                                           h->e.scores, 1);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
+                       const uint8_t* king_host, uint64_t first_global_game_id, int fused, int16_t* scores_host,
+                       int64_t* stats_host, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!perm_host || !contract_host || !declarer_host) return fail(h, -1, "perm/contract/declarer host pointers are required");
+    DeviceGuard dg(h->device);
+    const u64 n = h->e.n;
+    if (!h->st_perm) {
+        TK_CUDA(h, cudaMalloc((void**)&h->st_perm, h->e.n_alloc * 54));
+        TK_CUDA(h, cudaMalloc((void**)&h->st_contract, h->e.n_alloc));
+        TK_CUDA(h, cudaMalloc((void**)&h->st_declarer, h->e.n_alloc));
+        TK_CUDA(h, cudaMalloc((void**)&h->st_king, h->e.n_alloc));
+    }
+    cudaStream_t s = S(stream);
+    TK_CUDA(h, cudaMemcpyAsync(h->st_perm, perm_host, n * 54, cudaMemcpyHostToDevice, s));
+    TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, s));
+    TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, s));
+    if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, s));
+    TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
+    h->e.first_gid = first_global_game_id;
+    if (fused) {
+        tk::k_rollout_fused<true><<<grid1(h->e.n_alloc), tk::CTA, tk::CTA * 54, s>>>(
+            h->e, 0u, h->st_perm, h->st_contract, h->st_declarer, king_host ? h->st_king : nullptr, h->e.scores, 0);
+        TK_LAUNCH_OK(h);
+    } else {
+        clear_hist(h, stream);
+        tk::k_set_deals<<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, h->st_perm);
+        TK_LAUNCH_OK(h);
+        tk::k_begin<tk::SRC_FORCED><<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, 0u, h->st_contract, h->st_declarer,
+                                                                             king_host ? h->st_king : nullptr);
+        TK_LAUNCH_OK(h);
+        int rc = play_out_stepwise(h, 0u, stream);
+        if (rc) return rc;
+    }
+    if (scores_host) TK_CUDA(h, cudaMemcpyAsync(scores_host, h->e.scores, n * 8, cudaMemcpyDeviceToHost, s));
+    if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+// ---- zero-copy views ------------------------------------------------------------------------------------
+
+struct ExportCtx {
+    DLManagedTensor t;
+    int64_t shape[2];
+    tarok_env* owner;
+};
+
+static void export_deleter(DLManagedTensor* self) {
+    if (!self) return;
+    ExportCtx* c = static_cast<ExportCtx*>(self->manager_ctx);
+    c->owner->exports.fetch_sub(1);
+    delete c;
+}
+
+static int field_desc(tarok_env* h, int field, void** ptr, int* ndim, int64_t shape[2], DLDataType* dt) {
+    const int64_t na = (int64_t)h->e.n_alloc;
+    // bitboards are lent as int64 (same bits; torch has no general uint64 support), bit 63 is never set
+    DLDataType u64t = {0, 64, 1}, i16t = {0, 16, 1}, u8t = {1, 8, 1}, i64t = {0, 64, 1};
+    switch (field) {
+        case TAROK_F_HANDS: *ptr = h->e.hands; *ndim = 2; shape[0] = 4; shape[1] = na; *dt = u64t; break;
+        case TAROK_F_PILES: *ptr = h->e.piles; *ndim = 2; shape[0] = 4; shape[1] = na; *dt = u64t; break;
+        case TAROK_F_TALON: *ptr = h->e.talon; *ndim = 1; shape[0] = na; *dt = u64t; break;
+        case TAROK_F_TALON_ORDER: *ptr = h->e.torder; *ndim = 1; shape[0] = na; *dt = u64t; break;
+        case TAROK_F_META: *ptr = h->e.meta; *ndim = 1; shape[0] = na; *dt = u64t; break;
+        case TAROK_F_MASK: *ptr = h->e.mask; *ndim = 1; shape[0] = na; *dt = u64t; break;
+        case TAROK_F_SCORES: *ptr = h->e.scores; *ndim = 2; shape[0] = na; shape[1] = 4; *dt = i16t; break;
+        case TAROK_F_HIST: *ptr = h->e.hist; *ndim = 2; shape[0] = 48; shape[1] = na; *dt = u8t; break;
+        case TAROK_F_STATS: *ptr = h->e.stats; *ndim = 1; shape[0] = TAROK_STATS_LEN; *dt = i64t; break;
+        case TAROK_F_HANDS0: *ptr = h->e.hands0; *ndim = 2; shape[0] = 4; shape[1] = na; *dt = u64t; break;
+        case TAROK_F_DISCARD: *ptr = h->e.discard; *ndim = 1; shape[0] = na; *dt = u64t; break;
+        default: return fail(h, -1, "unknown field %d", field);
+    }
+    if (!*ptr) return fail(h, -1, "field %d needs TAROK_FLAG_HISTORY at tarok_create", field);
+    return 0;
+}
+
+int tarok_export(tarok_t* h, int field, DLManagedTensor** out) {
+    TK_CHECK_HANDLE(h);
+    if (!out) return fail(h, -1, "out is null");
+    ExportCtx* c = new (std::nothrow) ExportCtx();
+    if (!c) return fail(h, -4, "out of host memory");
+    void* ptr; int ndim; DLDataType dt;
+    int rc = field_desc(h, field, &ptr, &ndim, c->shape, &dt);
+    if (rc) { delete c; return rc; }
+    c->owner = h;
+    c->t.dl_tensor.data = ptr;
+    c->t.dl_tensor.device.device_type = 2;   // kDLCUDA
+    c->t.dl_tensor.device.device_id = h->device;
+    c->t.dl_tensor.ndim = ndim;
+    c->t.dl_tensor.dtype = dt;
+    c->t.dl_tensor.shape = c->shape;
+    c->t.dl_tensor.strides = nullptr;        // compact row-major
+    c->t.dl_tensor.byte_offset = 0;
+    c->t.manager_ctx = c;
+    c->t.deleter = export_deleter;
+    h->exports.fetch_add(1);
+    *out = &c->t;
+    return 0;
+}
+
+void* tarok_field_ptr(tarok_t* h, int field) {
+    if (!h) return nullptr;
+    void* ptr = nullptr; int ndim; int64_t shape[2]; DLDataType dt;
+    if (field_desc(h, field, &ptr, &ndim, shape, &dt)) return nullptr;
+    return ptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,571 @@
+// sm_100a kernels of the batched Tarok environment.
+//
+// HBM layout (structure of arrays, one 64-bit word per game per field, n_alloc = n rounded up to
+// the 512-game CTA tile, every array 256-byte aligned):
+//   hands[4][n_alloc]  piles[4][n_alloc]  talon[n_alloc]  torder[n_alloc]  meta[n_alloc]
+//   mask[n_alloc]  scores[n_alloc] (int16 x4)  hist[48][n_alloc] (uint8, optional)
+// The stepwise kernels give each lane TWO consecutive games so that every per-field access is one
+// 128-bit load/store (ld.global.v2.u64): a warp covers a 64-game tile = 512 contiguous bytes per
+// field.  Per-game logic is branch-light integer code (popc / shifts / selects, tarok_rules.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "philox.cuh"
+#include "tarok_rules.cuh"
+
+namespace tk {
+
+constexpr int CTA = 256;
+constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane kernels
+
+struct Env {
+    u64* hands; u64* piles; u64* talon; u64* torder; u64* meta; u64* mask; u64* scores;
+    uint8_t* hist; u64* hands0; u64* discard; long long* stats;
+    u64 n, n_alloc, seed, first_gid;
+};
+
+enum : int { S_SEAT = 0, S_PLAYER = 4, S_CONTRACT = 8, S_FINISHED = 18, S_STEPS = 19, S_ERRORS = 20, S_USED = 21, S_ERR_EVENTS = 21 };
+
+__device__ __forceinline__ ulonglong2 ld2(const u64* p) { return *reinterpret_cast<const ulonglong2*>(p); }
+__device__ __forceinline__ void st2(u64* p, u64 a, u64 b) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b); }
+
+// ------------------------------------------------------------------------------------------------
+// statistics: per-lane fold -> warp REDUX -> shared -> one global atomic per counter per CTA.  All
+// threads of the CTA must call this (converged).  Tarok.rezultati accumulation (Tarok.py:59-61) is
+// the S_PLAYER block: seat s of game i is player (s + i) % 4 (Tarok.py:34).
+// ------------------------------------------------------------------------------------------------
+struct GameStat { bool fin, err; u64 packed; u32 contract, plays; u64 gid; };
+
+template <int NG>
+__device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, const GameStat (&gs)[NG]) {
+    __shared__ long long sh[S_USED];
+    if (threadIdx.x < S_USED) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned full = 0xFFFFFFFFu;
+    int sc[4] = {0, 0, 0, 0}, pl[4] = {0, 0, 0, 0}, steps = 0;
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        int v[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) { v[s] = gs[k].fin ? (int)(int16_t)(gs[k].packed >> (16 * s)) : 0; sc[s] += v[s]; }
+        u32 rot = (u32)gs[k].gid & 3u;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            u32 s = ((u32)p - rot) & 3u;
+            pl[p] += s == 0 ? v[0] : s == 1 ? v[1] : s == 2 ? v[2] : v[3];
+        }
+        steps += (int)gs[k].plays;
+    }
+    int mine = 0;
+    const u32 lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        int a = __reduce_add_sync(full, sc[s]);
+        int b = __reduce_add_sync(full, pl[s]);
+        if (lane == (u32)(S_SEAT + s)) mine = a;
+        if (lane == (u32)(S_PLAYER + s)) mine = b;
+    }
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+        int a = 0;
+#pragma unroll
+        for (int k = 0; k < NG; k++) a += __popc(__ballot_sync(full, gs[k].fin && gs[k].contract == (u32)c));
+        if (lane == (u32)(S_CONTRACT + c)) mine = a;
+    }
+    {
+        int a = 0, e = 0;
+#pragma unroll
+        for (int k = 0; k < NG; k++) { a += __popc(__ballot_sync(full, gs[k].fin)); e += __popc(__ballot_sync(full, gs[k].err)); }
+        int b = __reduce_add_sync(full, steps);
+        if (lane == S_FINISHED) mine = a;
+        if (lane == S_STEPS) mine = b;
+        if (lane == S_ERRORS) mine = e;
+    }
+    if (lane < S_USED && mine != 0) atomicAdd((unsigned long long*)&sh[lane], (unsigned long long)(long long)mine);
+    __syncthreads();
+    if (threadIdx.x < S_USED && sh[threadIdx.x] != 0)
+        atomicAdd((unsigned long long*)&stats[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// deal: Igra.razdeli (Igra.py:65-73) with a counter-based Philox generator.
+// Card c goes to a uniformly random free slot among the 54-c left = a walk over the remaining pile
+// capacities (12,12,12,12,6); the talon ORDER is a uniform permutation decoded from one more draw.
+// 55 bounded draws = 14 Philox blocks per deal: ALU-bound, not HBM-bound.
+// ------------------------------------------------------------------------------------------------
+struct Dealt { u64 h0, h1, h2, h3, talon, order; };
+
+__device__ __forceinline__ u64 order_from_lehmer(u64 talon, u32 L) {
+    u64 rem = 0;                                   // the six talon ids ascending, 6 bits each
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        u32 c = (u32)__ffsll((long long)talon) - 1u;
+        talon &= talon - 1;
+        rem |= (u64)c << (6 * i);
+    }
+    u64 order = 0;
+    const u32 fact[6] = {120, 24, 6, 2, 1, 1};
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        u32 d = L / fact[i];
+        L -= d * fact[i];
+        u32 sh = 6 * d;
+        order |= ((rem >> sh) & 63ull) << (6 * i);
+        u64 low = rem & ((1ull << sh) - 1ull);
+        rem = low | ((rem >> (sh + 6)) << sh);
+    }
+    return order;
+}
+
+__device__ __forceinline__ Dealt deal_philox(u64 seed, u64 gid) {
+    Dealt d = {0, 0, 0, 0, 0, 0};
+    u32 c0 = 12, c1 = 12, c2 = 12, c3 = 12;
+    u32 L = 0;
+#pragma unroll
+    for (int blk = 0; blk < 14; blk++) {
+        Words4 b = philox_block(seed, gid, ST_DEAL, (u32)blk);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = blk * 4 + j;
+            if (c < 54) {
+                u32 r = draw_from_word(b.w[j], seed, gid, ST_DEAL, (u32)c, (u32)(54 - c));
+                u32 a0 = c0, a1 = a0 + c1, a2 = a1 + c2, a3 = a2 + c3;
+                const u64 bit = 1ull << c;
+                bool p0 = r < a0, p1 = !p0 && r < a1, p2 = r >= a1 && r < a2, p3 = r >= a2 && r < a3, p4 = r >= a3;
+                d.h0 |= p0 ? bit : 0ull; c0 -= p0 ? 1u : 0u;
+                d.h1 |= p1 ? bit : 0ull; c1 -= p1 ? 1u : 0u;
+                d.h2 |= p2 ? bit : 0ull; c2 -= p2 ? 1u : 0u;
+                d.h3 |= p3 ? bit : 0ull; c3 -= p3 ? 1u : 0u;
+                d.talon |= p4 ? bit : 0ull;
+            } else if (c == 54) {
+                L = draw_from_word(b.w[j], seed, gid, ST_DEAL, 54u, 720u);
+            }
+        }
+    }
+    d.order = order_from_lehmer(d.talon, L);
+    return d;
+}
+
+__global__ void __launch_bounds__(CTA) k_deal(Env e) {
+    u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
+    if (g >= e.n_alloc) return;
+    const u64 na = e.n_alloc;
+    Dealt d = {0, 0, 0, 0, 0, 0};
+    u64 meta = meta_pad();
+    if (g < e.n) { d = deal_philox(e.seed, e.first_gid + g); meta = meta_fresh(); }
+    e.hands[g] = d.h0; e.hands[na + g] = d.h1; e.hands[2 * na + g] = d.h2; e.hands[3 * na + g] = d.h3;
+    e.piles[g] = 0; e.piles[na + g] = 0; e.piles[2 * na + g] = 0; e.piles[3 * na + g] = 0;
+    e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = 0;
+    if (e.hands0) { e.hands0[g] = d.h0; e.hands0[na + g] = d.h1; e.hands0[2 * na + g] = d.h2; e.hands0[3 * na + g] = d.h3; }
+    if (e.discard) e.discard[g] = 0;
+}
+
+// Deal injection (Igra.shuffle patch, Igra.py:10,67): perm uint8 [n,54].  The CTA stages its
+// 256 x 54 bytes through shared memory with 16-byte loads, then each lane folds its row to bitboards.
+__device__ __forceinline__ Dealt deal_from_perm(const uint8_t* row, bool& ok) {
+    Dealt d = {0, 0, 0, 0, 0, 0};
+    u64 seen = 0;
+#pragma unroll
+    for (int i = 0; i < 54; i++) {
+        u32 c = row[i];
+        u64 bit = c < 54 ? 1ull << c : 0ull;
+        seen |= bit;
+        if (i < 12) d.h0 |= bit; else if (i < 24) d.h1 |= bit; else if (i < 36) d.h2 |= bit;
+        else if (i < 48) d.h3 |= bit; else { d.talon |= bit; d.order |= (u64)(c & 63u) << (6 * (i - 48)); }
+    }
+    ok = seen == ALL54;
+    return d;
+}
+
+__global__ void __launch_bounds__(CTA) k_set_deals(Env e, const uint8_t* __restrict__ perm) {
+    __shared__ __align__(16) uint8_t sh[CTA * 54];
+    const u64 base = (u64)blockIdx.x * CTA;
+    const u64 na = e.n_alloc;
+    {   // CTA * 54 bytes = 864 x 16 B; rows past n are not read
+        const u64 total = e.n * 54ull, off = base * 54ull;
+        const bool vec_ok = (((uintptr_t)perm) & 15u) == 0;
+        for (u32 v = threadIdx.x; v < CTA * 54 / 16; v += CTA) {
+            u64 b = off + (u64)v * 16;
+            if (vec_ok && b + 16 <= total) {
+                *reinterpret_cast<uint4*>(sh + v * 16) = *reinterpret_cast<const uint4*>(perm + b);
+            } else {
+                for (int k = 0; k < 16; k++) sh[v * 16 + k] = (b + k < total) ? perm[b + k] : 0xFF;
+            }
+        }
+    }
+    __syncthreads();
+    u64 g = base + threadIdx.x;
+    if (g >= na) return;
+    Dealt d = {0, 0, 0, 0, 0, 0};
+    u64 meta = meta_pad();
+    if (g < e.n) {
+        bool ok;
+        d = deal_from_perm(sh + threadIdx.x * 54, ok);
+        meta = meta_fresh();
+        if (!ok) { meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR); atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull); }
+    }
+    e.hands[g] = d.h0; e.hands[na + g] = d.h1; e.hands[2 * na + g] = d.h2; e.hands[3 * na + g] = d.h3;
+    e.piles[g] = 0; e.piles[na + g] = 0; e.piles[2 * na + g] = 0; e.piles[3 * na + g] = 0;
+    e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = 0;
+    if (e.hands0) { e.hands0[g] = d.h0; e.hands0[na + g] = d.h1; e.hands0[2 * na + g] = d.h2; e.hands0[3 * na + g] = d.h3; }
+    if (e.discard) e.discard[g] = 0;
+}
+
+// Current deal -> the permutation Igra.razdeli would have consumed (hands ascending, ordered talon).
+__global__ void __launch_bounds__(CTA) k_export_perm(Env e, uint8_t* __restrict__ out) {
+    __shared__ uint8_t sh[CTA * 54];
+    const u64 base = (u64)blockIdx.x * CTA;
+    u64 g = base + threadIdx.x;
+    if (g < e.n) {
+        uint8_t* row = sh + threadIdx.x * 54;
+        const u64 na = e.n_alloc;
+        int k = 0;
+        for (int s = 0; s < 4; s++) {
+            u64 h = e.hands[s * na + g];
+            for (int i = 0; i < 12; i++) {
+                u32 c = h ? (u32)__ffsll((long long)h) - 1u : 0xFFu;
+                h &= h - 1;
+                row[k++] = (uint8_t)c;
+            }
+        }
+        u64 o = e.torder[g];
+        for (int i = 0; i < 6; i++) row[48 + i] = (uint8_t)((o >> (6 * i)) & 63ull);
+    }
+    __syncthreads();
+    const u64 total = e.n * 54ull, off = base * 54ull;
+    for (u32 b = threadIdx.x; b < CTA * 54; b += CTA)
+        if (off + b < total) out[off + b] = sh[b];
+}
+
+// ------------------------------------------------------------------------------------------------
+// contract start: auction (Igra.licitacija) or forced contract, then Igra.start dispatch + teams.
+// ------------------------------------------------------------------------------------------------
+enum : int { SRC_FORCED = 0, SRC_INTENTS = 1, SRC_SYNTH = 2 };
+
+struct WantFixed { int tip[4]; __device__ int operator()(int seat, int) const {
+    return seat == 0 ? tip[0] : seat == 1 ? tip[1] : seat == 2 ? tip[2] : tip[3]; } };
+struct WantBot { u64 seed, gid; __device__ int operator()(int, int call) const {
+    // np.random.choice([Naprej,Tri,Dve,Ena], p=[.5,1/6,1/6,1/6]) at EVERY call (Igralec.py:151)
+    u32 u = draw(seed, gid, ST_BID, (u32)call, 6u);
+    return u < 3u ? (int)C_NAPREJ : (int)(C_TRI + (u - 3u)); } };
+
+// Resolves (contract, declarer, king) for one game from the chosen source.
+template <int SRC>
+__device__ __forceinline__ void resolve_contract(u64 seed, u64 gid, u32 mode, const uint8_t* a, const uint8_t* b,
+                                                 const uint8_t* c, u64 g, u32& contract, u32& declarer, u32& king) {
+    if (SRC == SRC_FORCED) {
+        contract = a[g]; declarer = b[g]; king = c ? c[g] : NO_KING;
+    } else if (SRC == SRC_INTENTS) {
+        uchar4 in = reinterpret_cast<const uchar4*>(a)[g];
+        WantFixed w; u32 su[4];
+        index2igra(in.x, w.tip[0], su[0]); index2igra(in.y, w.tip[1], su[1]);
+        index2igra(in.z, w.tip[2], su[2]); index2igra(in.w, w.tip[3], su[3]);
+        int d, k;
+        licitacija<true>(w, d, k);
+        contract = (u32)k; declarer = (u32)d;
+        // king = the suit attached to the declarer's ORIGINAL intent (Igralec.py:298,308-310)
+        king = d == 0 ? su[0] : d == 1 ? su[1] : d == 2 ? su[2] : su[3];
+    } else {
+        if (mode == 17u) {          // TAROK_MODE_AUCTION_UNIFORM
+            Words4 blk = philox_block(seed, gid, ST_BID, 0u);
+            WantFixed w; u32 su[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) index2igra(draw_from_word(blk.w[s], seed, gid, ST_BID, (u32)s, 18u), w.tip[s], su[s]);
+            int d, k;
+            licitacija<true>(w, d, k);
+            contract = (u32)k; declarer = (u32)d;
+            king = d == 0 ? su[0] : d == 1 ? su[1] : d == 2 ? su[2] : su[3];
+        } else if (mode == 18u) {   // TAROK_MODE_AUCTION_BOT
+            WantBot w{seed, gid};
+            int d, k;
+            licitacija<false>(w, d, k);
+            contract = (u32)k; declarer = (u32)d;
+            king = is_king_game(contract) ? draw(seed, gid, ST_KING, 0u, 4u) : NO_KING;   // Igralec.py:155-156
+        } else {
+            Words4 blk = philox_block(seed, gid, ST_FORCE, 0u);
+            contract = mode == 16u ? C_TRI + draw_from_word(blk.w[0], seed, gid, ST_FORCE, 0u, 3u) : mode;
+            declarer = contract == C_KLOP ? 0u : draw_from_word(blk.w[1], seed, gid, ST_FORCE, 1u, 4u);
+            king = is_king_game(contract) ? draw(seed, gid, ST_KING, 0u, 4u) : NO_KING;
+        }
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(CTA) k_begin(Env e, u32 mode, const uint8_t* __restrict__ a,
+                                               const uint8_t* __restrict__ b, const uint8_t* __restrict__ c) {
+    u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
+    if (g >= e.n) return;
+    u64 meta = e.meta[g];
+    if (mget(meta, M_PHASE, 2) != PH_DEALT || ((meta >> M_ERR) & 1ull)) return;
+    const u64 na = e.n_alloc;
+    u64 h0 = e.hands[g], h1 = e.hands[na + g], h2 = e.hands[2 * na + g], h3 = e.hands[3 * na + g];
+    u32 contract, declarer, king;
+    resolve_contract<SRC>(e.seed, e.first_gid + g, mode, a, b, c, g, contract, declarer, king);
+    meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
+    if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
+    e.meta[g] = meta;
+    e.mask[g] = mask_for_mover(meta, sel4(h0, h1, h2, h3, mover_of(meta)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// talon exchange: Navadna_igra.odpri_talon/start (Navadna_igra.py:36-68); the declarer takes group g
+// and lays k discardable cards (Roka.mozno_zalozit, Roka.py:23-27) into the own pile (Igralec.py:161-171).
+// ------------------------------------------------------------------------------------------------
+// Returns false (error) if the action is invalid or fewer than k cards can be laid down (Q19).
+template <bool SYNTH>
+__device__ __forceinline__ bool exchange_game(u64 seed, u64 gid, u32 random_group, u64& meta, u64& hand, u64& pile,
+                                              u64& talon, u64 order, u32 group, u64 discard, u64& discard_out) {
+    u32 contract = mget(meta, M_CONTRACT, 4);
+    u32 k = talon_k(contract);
+    u32 ngroups = 6u / k;
+    if (SYNTH) {
+        Words4 blk = philox_block(seed, gid, ST_EXCH, 0u);
+        group = random_group ? draw_from_word(blk.w[0], seed, gid, ST_EXCH, 0u, ngroups) : 0u;   // Bot: group 0 (Igralec.py:162)
+        u64 gb = talon_group_bits(order, k, group);
+        u64 avail = (hand | gb) & DISCARDABLE;
+        if ((u32)__popcll(avail) < k) return false;
+        discard = 0;
+        for (u32 j = 0; j < k; j++) {               // uniform k-subset = random.sample (Igralec.py:166)
+            u32 wj = j == 0 ? blk.w[1] : j == 1 ? blk.w[2] : blk.w[3];
+            u32 r = draw_from_word(wj, seed, gid, ST_EXCH, 1u + j, (u32)__popcll(avail));
+            u64 bit = 1ull << nth_set_bit(avail, r);
+            avail ^= bit; discard |= bit;
+        }
+    }
+    if (group >= ngroups) return false;
+    u64 gb = talon_group_bits(order, k, group);
+    u64 full = hand | gb;
+    if ((u32)__popcll(discard) != k || (discard & ~(full & DISCARDABLE))) return false;
+    hand = full & ~discard;
+    pile |= discard;
+    talon &= ~gb;
+    discard_out = discard;
+    meta = mset(meta, M_GROUP, 3, group);
+    meta = mset(meta, M_PHASE, 2, PH_PLAY);
+    return true;
+}
+
+template <bool SYNTH>
+__global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const uint8_t* __restrict__ group,
+                                                  const u64* __restrict__ discard) {
+    u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
+    if (g >= e.n) return;
+    u64 meta = e.meta[g];
+    if (mget(meta, M_PHASE, 2) != PH_EXCHANGE) return;
+    const u64 na = e.n_alloc;
+    u32 decl = mget(meta, M_DECL, 2);
+    u64 h0 = e.hands[g], h1 = e.hands[na + g], h2 = e.hands[2 * na + g], h3 = e.hands[3 * na + g];
+    u64 hand = sel4(h0, h1, h2, h3, decl);
+    u64 pile = e.piles[decl * na + g];
+    u64 talon = e.talon[g], order = e.torder[g], dout = 0;
+    bool ok = exchange_game<SYNTH>(e.seed, e.first_gid + g, random_group, meta, hand, pile, talon, order,
+                                   SYNTH ? 0u : (u32)group[g], SYNTH ? 0ull : discard[g], dout);
+    if (!ok) {
+        meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
+        atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
+        e.meta[g] = meta;
+        e.mask[g] = 0;
+        return;
+    }
+    e.hands[decl * na + g] = hand;
+    e.piles[decl * na + g] = pile;
+    e.talon[g] = talon;
+    e.meta[g] = meta;
+    if (e.discard) e.discard[g] = dout;
+    u32 mv = mover_of(meta);
+    e.mask[g] = mask_for_mover(meta, mv == decl ? hand : sel4(h0, h1, h2, h3, mv));
+}
+
+// ------------------------------------------------------------------------------------------------
+// play_step: one card per live game per launch -- THE hot kernel (48 launches per deal).
+// Algorithmic traffic per env-step: R meta 8 + hands 16 + action 1, W hand 8 + meta 8
+// + mask 8, per trick /4: pile RW 16 (+ Klop talon) = 64 B.
+// ------------------------------------------------------------------------------------------------
+template <bool RANDOM>
+__device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, u64 h0, u64 h1, u64 h2, u64 h3, u32 card,
+                                          u64& next_mask) {
+    const u64 na = e.n_alloc;
+    u32 mover = mover_of(meta);
+    u64 hand = sel4(h0, h1, h2, h3, mover);
+    u32 contract = mget(meta, M_CONTRACT, 4);
+    u32 plays = mget(meta, M_PLAYS, 6);
+    u64 talon = 0, order = 0;
+    bool klop_talon = contract == C_KLOP && mget(meta, M_POS, 2) == 3 && mget(meta, M_TRICKS, 4) < 6;
+    if (klop_talon) { talon = e.talon[g]; order = e.torder[g]; }
+    if (RANDOM) {
+        u64 legal = legal_moves(hand, mget(meta, M_POS, 2) != 0, mget(meta, M_TRICK, 6), klop_rules(contract));
+        u32 n = (u32)__popcll(legal);
+        card = n ? nth_set_bit(legal, draw(e.seed, e.first_gid + g, ST_PLAY, plays, n)) : 63u;
+    }
+    PlayResult pr;
+    meta = play_card(meta, hand, card, talon, order, pr);
+    next_mask = 0;
+    if ((meta >> M_ERR) & 1ull) {
+        atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
+        return;
+    }
+    e.hands[mover * na + g] = hand;
+    if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
+    if (pr.trick_done) {
+        u64* pp = e.piles + pr.winner * na + g;
+        *pp |= pr.pile_bits;
+        if (pr.talon_clear) e.talon[g] = talon & ~pr.talon_clear;
+    }
+    u32 nx = mover_of(meta);
+    next_mask = mask_for_mover(meta, nx == mover ? hand : sel4(h0, h1, h2, h3, nx));
+}
+
+template <bool RANDOM>
+__global__ void __launch_bounds__(CTA) k_step(Env e, const uint8_t* __restrict__ action) {
+    u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
+    if (g >= e.n_alloc) return;
+    ulonglong2 m = ld2(e.meta + g);
+    bool a0 = mget(m.x, M_PHASE, 2) == PH_PLAY, a1 = mget(m.y, M_PHASE, 2) == PH_PLAY;
+    if (!a0 && !a1) return;
+    const u64 na = e.n_alloc;
+    ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + na + g), h2 = ld2(e.hands + 2 * na + g),
+               h3 = ld2(e.hands + 3 * na + g);
+    u32 act = 0;
+    if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
+    u64 k0 = 0, k1 = 0;
+    if (a0) step_game<RANDOM>(e, g, m.x, h0.x, h1.x, h2.x, h3.x, act & 0xFFu, k0);
+    if (a1) step_game<RANDOM>(e, g + 1, m.y, h0.y, h1.y, h2.y, h3.y, act >> 8, k1);
+    st2(e.meta + g, m.x, m.y);
+    st2(e.mask + g, k0, k1);
+}
+
+// Standalone legal mask, recomputed from hands + meta (24 B/env-step algorithmic).
+__global__ void __launch_bounds__(CTA) k_legal_mask(Env e, u64* __restrict__ out) {
+    u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
+    if (g >= e.n_alloc) return;
+    const u64 na = e.n_alloc;
+    ulonglong2 m = ld2(e.meta + g);
+    ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + na + g), h2 = ld2(e.hands + 2 * na + g),
+               h3 = ld2(e.hands + 3 * na + g);
+    u64 k0 = mask_for_mover(m.x, sel4(h0.x, h1.x, h2.x, h3.x, mover_of(m.x)));
+    u64 k1 = mask_for_mover(m.y, sel4(h0.y, h1.y, h2.y, h3.y, mover_of(m.y)));
+    if (g + 1 < e.n) st2(out + g, k0, k1);
+    else if (g < e.n) out[g] = k0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// score: Roka.prestej + the three start() epilogues; accumulates the statistics vector.
+// 56 B/deal algorithmic: R 4 piles 32 + talon 8 + meta 8, W int16[4] 8.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64 out_n) {
+    u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
+    const u64 na = e.n_alloc;
+    u64 s0 = 0, s1 = 0;
+    bool f0 = false, f1 = false, e0 = false, e1 = false;
+    u32 c0 = 0, c1 = 0, pl0 = 0, pl1 = 0;
+    if (g < na) {
+        ulonglong2 m = ld2(e.meta + g);
+        ulonglong2 p0 = ld2(e.piles + g), p1 = ld2(e.piles + na + g), p2 = ld2(e.piles + 2 * na + g),
+                   p3 = ld2(e.piles + 3 * na + g);
+        ulonglong2 t = ld2(e.talon + g);
+        e0 = ((m.x >> M_ERR) & 1ull) && g < e.n;
+        e1 = ((m.y >> M_ERR) & 1ull) && g + 1 < e.n;
+        f0 = mget(m.x, M_PHASE, 2) == PH_DONE && !((m.x >> M_ERR) & 1ull) && g < e.n;
+        f1 = mget(m.y, M_PHASE, 2) == PH_DONE && !((m.y >> M_ERR) & 1ull) && g + 1 < e.n;
+        c0 = mget(m.x, M_CONTRACT, 4); c1 = mget(m.y, M_CONTRACT, 4);
+        pl0 = g < e.n ? mget(m.x, M_PLAYS, 6) : 0u; pl1 = g + 1 < e.n ? mget(m.y, M_PLAYS, 6) : 0u;
+        if (f0) s0 = score_game(m.x, p0.x, p1.x, p2.x, p3.x, t.x);
+        if (f1) s1 = score_game(m.y, p0.y, p1.y, p2.y, p3.y, t.y);
+        if (g + 1 < out_n) st2(out + g, s0, s1);
+        else if (g < out_n) out[g] = s0;
+    }
+    // two games per lane: folded per lane before the warp reductions
+    GameStat gs[2] = {{f0, e0, s0, c0, pl0, e.first_gid + g}, {f1, e1, s1, c1, pl1, e.first_gid + g + 1}};
+    accumulate_stats<2>(e.stats, gs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused rollout: deal -> contract -> exchange -> up to 48 random plays -> score with the whole game in
+// registers (one lane = one game).  Same device functions, same Philox draws, hence bit-identical to
+// the stepwise pipeline.  Not HBM-bound: 8 B/deal written.
+// ------------------------------------------------------------------------------------------------
+template <bool FROM_PERM>
+__global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const uint8_t* __restrict__ perm,
+                                                       const uint8_t* __restrict__ fc, const uint8_t* __restrict__ fd,
+                                                       const uint8_t* __restrict__ fk, u64* __restrict__ out, int write_state) {
+    extern __shared__ __align__(16) uint8_t shp[];
+    const u64 base = (u64)blockIdx.x * CTA;
+    u64 g = base + threadIdx.x;
+    const u64 na = e.n_alloc;
+    const u64 gid = e.first_gid + g;
+    if (FROM_PERM) {
+        const u64 total = e.n * 54ull, off = base * 54ull;
+        const bool vec_ok = (((uintptr_t)perm) & 15u) == 0;
+        for (u32 v = threadIdx.x; v < CTA * 54 / 16; v += CTA) {
+            u64 b = off + (u64)v * 16;
+            if (vec_ok && b + 16 <= total) *reinterpret_cast<uint4*>(shp + v * 16) = *reinterpret_cast<const uint4*>(perm + b);
+            else for (int k = 0; k < 16; k++) shp[v * 16 + k] = (b + k < total) ? perm[b + k] : 0xFF;
+        }
+        __syncthreads();
+    }
+    bool live = g < e.n, err = false;
+    u64 meta = meta_pad(), packed = 0;
+    u64 h0 = 0, h1 = 0, h2 = 0, h3 = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0, talon = 0, order = 0;
+    if (live) {
+        Dealt d;
+        bool ok = true;
+        if (FROM_PERM) d = deal_from_perm(shp + threadIdx.x * 54, ok);
+        else d = deal_philox(e.seed, gid);
+        h0 = d.h0; h1 = d.h1; h2 = d.h2; h3 = d.h3; talon = d.talon; order = d.order;
+        meta = meta_fresh();
+        if (!ok) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
+        else {
+            u32 contract, declarer, king;
+            if (fc) resolve_contract<SRC_FORCED>(e.seed, gid, mode, fc, fd, fk, g, contract, declarer, king);
+            else resolve_contract<SRC_SYNTH>(e.seed, gid, mode, nullptr, nullptr, nullptr, g, contract, declarer, king);
+            meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
+        }
+        if (mget(meta, M_PHASE, 2) == PH_EXCHANGE) {
+            u32 decl = mget(meta, M_DECL, 2);
+            u64 hand = sel4(h0, h1, h2, h3, decl), pile = 0, dout;
+            bool ok2 = exchange_game<true>(e.seed, gid, mode == 17u, meta, hand, pile, talon, order, 0u, 0ull, dout);
+            if (!ok2) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
+            else {
+                h0 = decl == 0 ? hand : h0; h1 = decl == 1 ? hand : h1; h2 = decl == 2 ? hand : h2; h3 = decl == 3 ? hand : h3;
+                p0 = decl == 0 ? pile : p0; p1 = decl == 1 ? pile : p1; p2 = decl == 2 ? pile : p2; p3 = decl == 3 ? pile : p3;
+            }
+        }
+        const u32 contract = mget(meta, M_CONTRACT, 4);
+        const bool klop = klop_rules(contract);
+        for (u32 trick = 0; trick < 12 && mget(meta, M_PHASE, 2) == PH_PLAY; trick++) {
+            Words4 blk = philox_block(e.seed, gid, ST_PLAY, trick);     // 4 plays = one Philox block
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                u32 mover = mover_of(meta);
+                u64 hand = sel4(h0, h1, h2, h3, mover);
+                u64 legal = legal_moves(hand, j != 0, mget(meta, M_TRICK, 6), klop);
+                u32 n = (u32)__popcll(legal);
+                u32 card = nth_set_bit(legal, draw_from_word(blk.w[j], e.seed, gid, ST_PLAY, trick * 4 + j, n));
+                PlayResult pr;
+                meta = play_card(meta, hand, card, talon, order, pr);
+                if (e.hist && write_state) e.hist[(u64)(trick * 4 + j) * na + g] = (uint8_t)((mover << 6) | card);
+                h0 = mover == 0 ? hand : h0; h1 = mover == 1 ? hand : h1; h2 = mover == 2 ? hand : h2; h3 = mover == 3 ? hand : h3;
+                if (pr.trick_done) {
+                    u64 b = pr.pile_bits;
+                    p0 |= pr.winner == 0 ? b : 0ull; p1 |= pr.winner == 1 ? b : 0ull;
+                    p2 |= pr.winner == 2 ? b : 0ull; p3 |= pr.winner == 3 ? b : 0ull;
+                    talon &= ~pr.talon_clear;
+                }
+            }
+        }
+        err = (meta >> M_ERR) & 1ull;
+        if (!err && mget(meta, M_PHASE, 2) == PH_DONE) packed = score_game(meta, p0, p1, p2, p3, talon);
+        if (out) out[g] = packed;
+    }
+    if (write_state && g < na) {
+        e.hands[g] = h0; e.hands[na + g] = h1; e.hands[2 * na + g] = h2; e.hands[3 * na + g] = h3;
+        e.piles[g] = p0; e.piles[na + g] = p1; e.piles[2 * na + g] = p2; e.piles[3 * na + g] = p3;
+        e.talon[g] = talon; e.torder[g] = order; e.meta[g] = meta; e.mask[g] = 0;
+    }
+    GameStat gs[1] = {{live && !err && mget(meta, M_PHASE, 2) == PH_DONE, live && err, packed,
+                       mget(meta, M_CONTRACT, 4), live ? mget(meta, M_PLAYS, 6) : 0u, gid}};
+    accumulate_stats<1>(e.stats, gs);
+}
+
+}  // namespace tk

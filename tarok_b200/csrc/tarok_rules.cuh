@@ -1,0 +1,348 @@
+// Device-side Tarok rules on 64-bit card bitboards (bit i = card id i, Karta.v_id, Karta.py:19-23).
+// Everything here is register arithmetic: popc / shifts / selects, no memory traffic.
+// Reference behaviour incl. its quirks is cited per function.
+#pragma once
+#include <cstdint>
+
+namespace tk {
+
+using u64 = unsigned long long;
+using u32 = unsigned int;
+
+// ---- card constants --------------------------------------------------------
+// id 0..7 KARA (1,2,3,4,J,C,Q,K), 8..15 SRCE, 16..23 PIK, 24..31 KRIZ, 32..53 TAROK I..XXII
+constexpr u64 ALL54 = (1ull << 54) - 1;
+constexpr u64 TAROKS = 0x3FFFFFull << 32;
+constexpr u64 PAGAT = 1ull << 32;
+constexpr u64 KINGS = (1ull << 7) | (1ull << 15) | (1ull << 23) | (1ull << 31);
+constexpr u64 QUEENS = KINGS >> 1;
+constexpr u64 CAVALS = KINGS >> 2;
+constexpr u64 JACKS = KINGS >> 3;
+constexpr u64 TRULA = (1ull << 32) | (1ull << 52) | (1ull << 53);
+// Roka.mozno_zalozit (Roka.py:23-27) with the buggy Karta.vrednost (Karta.py:10-16):
+// suit ranks 1..7 and taroks II..VII may be laid down (Q8).
+constexpr u64 DISCARDABLE = 0x7F7F7F7Full | (0x3Full << 33);
+
+// ---- contract codes = Tip_igre value / 10 (Tip_igre.py:5-15) ---------------------------------
+enum : int { C_NAPREJ = -1, C_KLOP = 0, C_TRI, C_DVE, C_ENA, C_SOLO_TRI, C_SOLO_DVE, C_SOLO_ENA,
+             C_BERAC, C_SOLO_BREZ, C_ODPRTI_BERAC, C_NONE = 15 };
+constexpr u32 NO_KING = 7;
+constexpr u32 NO_GROUP = 7;
+
+__device__ __forceinline__ bool is_navadna(u32 c) { return (c >= C_TRI && c <= C_SOLO_ENA) || c == C_SOLO_BREZ; }
+__device__ __forceinline__ bool is_king_game(u32 c) { return c >= C_TRI && c <= C_ENA; }
+__device__ __forceinline__ bool is_berac(u32 c) { return c == C_BERAC || c == C_ODPRTI_BERAC; }
+// Klop.mozne_karte is inherited by Berac (Berac.py:4)
+__device__ __forceinline__ bool klop_rules(u32 c) { return c == C_KLOP || is_berac(c); }
+// st_kart_za_menjat / korak (Navadna_igra.py:36-58); 0 = no exchange
+__device__ __forceinline__ u32 talon_k(u32 c) {
+    return (c == C_TRI || c == C_SOLO_TRI) ? 3u : (c == C_DVE || c == C_SOLO_DVE) ? 2u
+         : (c == C_ENA || c == C_SOLO_ENA) ? 1u : 0u;
+}
+
+// ---- meta word layout -----------------------------------------------------------------------
+//  0-3  contract code (15 = none)     4-5  declarer          6-8  king suit (7 = none)
+//  9-12 ekipa (team) seat mask        13-14 leader (zacne)   15-16 pos = cards in current trick
+//  17-20 tricks completed             21-44 trick cards, 6 bits each, play order
+//  45-46 phase 0 dealt 1 await-exchange 2 playing 3 finished     47 error
+//  48-50 chosen talon group (7 none)  51-52 last trick winner    53 trick-just-completed
+//  54-59 plays made (0..48)           60 scored
+constexpr int M_CONTRACT = 0, M_DECL = 4, M_KING = 6, M_TEAM = 9, M_LEADER = 13, M_POS = 15,
+              M_TRICKS = 17, M_TRICK = 21, M_PHASE = 45, M_ERR = 47, M_GROUP = 48, M_WINNER = 51,
+              M_TRICKDONE = 53, M_PLAYS = 54, M_SCORED = 60;
+enum : u32 { PH_DEALT = 0, PH_EXCHANGE = 1, PH_PLAY = 2, PH_DONE = 3 };
+
+__device__ __forceinline__ u32 mget(u64 m, int sh, u32 bits) { return (u32)(m >> sh) & ((1u << bits) - 1u); }
+__device__ __forceinline__ u64 mset(u64 m, int sh, u32 bits, u32 v) {
+    return (m & ~((u64)((1u << bits) - 1u) << sh)) | ((u64)v << sh);
+}
+__device__ __forceinline__ u64 meta_fresh() {
+    return ((u64)C_NONE << M_CONTRACT) | ((u64)NO_KING << M_KING) | ((u64)NO_GROUP << M_GROUP);
+}
+__device__ __forceinline__ u64 meta_pad() { return meta_fresh() | ((u64)PH_DONE << M_PHASE) | (1ull << M_SCORED); }
+
+// ---- small helpers --------------------------------------------------------------------------
+__device__ __forceinline__ u64 sel4(u64 a, u64 b, u64 c, u64 d, u32 i) {
+    u64 lo = (i & 1) ? b : a, hi = (i & 1) ? d : c;
+    return (i & 2) ? hi : lo;
+}
+// r-th (0-based) lowest set bit of m; r < popc(m)
+__device__ __forceinline__ u32 nth_set_bit(u64 m, u32 r) {
+    u32 lo = (u32)m, hi = (u32)(m >> 32);
+    u32 cl = __popc(lo);
+    u32 w = lo, base = 0;
+    if (r >= cl) { r -= cl; w = hi; base = 32; }
+    // binary descent inside the 32-bit word
+    u32 pos = 0, c;
+    c = __popc(w & 0xFFFFu);            if (r >= c) { r -= c; pos = 16; }
+    c = __popc((w >> pos) & 0xFFu);     if (r >= c) { r -= c; pos += 8; }
+    c = __popc((w >> pos) & 0xFu);      if (r >= c) { r -= c; pos += 4; }
+    c = __popc((w >> pos) & 0x3u);      if (r >= c) { r -= c; pos += 2; }
+    c = (w >> pos) & 1u;                if (r >= c) { pos += 1; }
+    return base + pos;
+}
+__device__ __forceinline__ u64 suit_mask_of(u32 card) {
+    return card >= 32 ? TAROKS : (0xFFull << (card & 24u));
+}
+
+// ---- legal moves ----------------------------------------------------------------------------
+// Navadna_igra.mozne_karte (Navadna_igra.py:158-168): follow suit, else must trump, else anything.
+// Klop.mozne_karte (Klop.py:96-133), *effective* behaviour (Q1): the overtake filter is computed and
+// dropped (Klop.py:104), leaving the same set minus the pagat whenever more than one card is legal.
+__device__ __forceinline__ u64 legal_moves(u64 hand, bool has_lead, u32 lead, bool klop) {
+    u64 m = hand;
+    if (has_lead) {
+        u64 f = hand & suit_mask_of(lead);
+        u64 t = hand & TAROKS;
+        m = f ? f : (t ? t : hand);
+    }
+    if (klop && (m & (m - 1))) m &= ~PAGAT;
+    return m;
+}
+
+// pobere_stih / primerjaj_karti (Navadna_igra.py:143-156, Klop.py:81-94): scan cards 1..3 against the
+// current best: same suit and higher rank, or a tarok over a non-tarok.  No trula/pagat rule (Q3).
+__device__ __forceinline__ u32 trick_winner(u32 t24) {
+    u32 best = t24 & 63u, w = 0;
+#pragma unroll
+    for (int i = 1; i < 4; i++) {
+        u32 c = (t24 >> (6 * i)) & 63u;
+        u32 sb = best >= 32 ? 4u : (best >> 3), sc = c >= 32 ? 4u : (c >> 3);
+        bool beats = (sb == sc) ? (c > best) : (sc == 4u);
+        if (beats) { best = c; w = i; }
+    }
+    return w;
+}
+
+// Roka.prestej (Roka.py:55-98): groups of three, sum-2; a remainder of one or two cards, sum-1 (Q10).
+// Order independent: sum(points) - 2*floor(n/3) - [n%3 != 0].
+__device__ __forceinline__ int prestej(u64 s) {
+    int n = __popcll(s);
+    int pts = n + __popcll(s & JACKS) + 2 * __popcll(s & CAVALS) + 3 * __popcll(s & QUEENS)
+            + 4 * __popcll(s & (KINGS | TRULA));
+    return pts - 2 * (n / 3) - ((n % 3) != 0);
+}
+// value of one trick for per-trick rewards: Roka.vrednost_stiha on 4 or 5 cards = sum - 2 (Roka.py:92-95)
+__device__ __forceinline__ int vrednost_stiha_bits(u64 s) {
+    int n = __popcll(s);
+    int pts = n + __popcll(s & JACKS) + 2 * __popcll(s & CAVALS) + 3 * __popcll(s & QUEENS)
+            + 4 * __popcll(s & (KINGS | TRULA));
+    return pts - ((n == 1 || n == 2) ? 1 : 2);
+}
+
+// ---- auction ----------------------------------------------------------------------------------
+// Igralec.licitiram filter (Igralec.py:58-74).  obv < -1 encodes "obvezno is None".
+constexpr int OBV_NONE = -2;
+__device__ __forceinline__ int bid_filter(int want, int min_igra, int obv, bool pred) {
+    bool ok = pred ? (want >= min_igra) : (want > min_igra);
+    return ok ? want : (obv == OBV_NONE ? (int)C_NAPREJ : obv);
+}
+
+// Igra.licitacija (Igra.py:75-114) as a state machine over a bidder functor
+//   int Want::operator()(int seat, int call_index)   -> the Tip code the seat wants at this call.
+// FIXED = Nevronski_igralec semantics: the first answer is kept and overwritten by every returned
+// value (Igralec.py:295-304); otherwise (Bot_igralec, Igralec.py:151) every call asks afresh.
+template <bool FIXED, class Want>
+__device__ __forceinline__ void licitacija(Want& want, int& declarer, int& contract) {
+    int intent[4] = {C_NONE, C_NONE, C_NONE, C_NONE};
+    int calls = 0;
+    auto call = [&](int seat, int mn, int obv, bool pred) -> int {
+        int w;
+        if (FIXED) {
+            if (intent[seat] == C_NONE) intent[seat] = want(seat, calls);
+            w = intent[seat];
+        } else {
+            w = want(seat, calls);
+        }
+        calls++;
+        int r = bid_filter(w, mn, obv, pred);
+        if (FIXED) intent[seat] = r;
+        return r;
+    };
+    u32 lic = 0;
+    int mx = C_TRI;
+#pragma unroll
+    for (int s = 1; s < 4; s++) {
+        int r = call(s, mx, OBV_NONE, false);
+        if (r != C_NAPREJ) lic |= 1u << s;
+        mx = max(mx, r);
+    }
+    if (mx == C_TRI) {                                   // nobody bid: forehand plays own game or Klop
+        declarer = 0;
+        contract = call(0, C_NAPREJ, C_KLOP, false);
+        return;
+    }
+    {
+        int r = call(0, mx, OBV_NONE, true);             // forehand has priority (prednost)
+        if (r != C_NAPREJ) lic |= 1u;
+        mx = max(mx, r);
+    }
+    int holder = __ffs(lic) - 1;                         // min(lic)
+    for (int guard = 0; __popc(lic) != 1 && guard < 32; guard++) {
+        u32 nl = 0;
+#pragma unroll
+        for (int j = 1; j <= 4; j++) {                   // sorted keys with seat 0 moved last
+            int k = j & 3;
+            if (!((lic >> k) & 1u)) continue;
+            int r = (k == holder) ? call(k, mx, mx, false) : call(k, mx, OBV_NONE, false);
+            if (r != C_NAPREJ) { nl |= 1u << k; holder = k; mx = r; }
+        }
+        lic = nl;
+    }
+    declarer = holder;
+    contract = mx;
+}
+
+// Nevronski_igralec.index2igra (Igralec.py:717-745) + two raw extras (18 Odprti_berac, 19 Klop)
+__device__ __forceinline__ void index2igra(u32 idx, int& tip, u32& suit) {
+    suit = NO_KING;
+    if (idx == 0) tip = C_NAPREJ;
+    else if (idx <= 12) { tip = C_TRI + (int)((idx - 1) >> 2); suit = (idx - 1) & 3u; }
+    else if (idx <= 15) tip = C_SOLO_TRI + (int)(idx - 13);
+    else if (idx == 16) tip = C_BERAC;
+    else if (idx == 17) tip = C_SOLO_BREZ;
+    else if (idx == 18) tip = C_ODPRTI_BERAC;
+    else tip = C_KLOP;
+}
+
+// ---- contract start ---------------------------------------------------------------------------
+// Igra.start dispatch (Igra.py:38-58) + constructors: Navadna_igra.__init__ teams from the
+// pre-exchange hands (Navadna_igra.py:20-30, Q9), leader 0 (Navadna_igra.py:70, Klop.py:26) or the
+// declarer for Berac (Berac.py:15, Q11).  Returns the new meta word.
+__device__ __forceinline__ u64 begin_contract(u64 meta, u32 contract, u32 declarer, u32 king,
+                                              u64 h0, u64 h1, u64 h2, u64 h3) {
+    bool bad = contract > C_ODPRTI_BERAC || declarer > 3;
+    if (contract == C_KLOP) declarer = 0;
+    u32 team = 0, leader = 0, phase = PH_PLAY;
+    if (!bad && is_king_game(contract)) {
+        if (king > 3) bad = true;                        // assert barva_kralja != TAROK (Navadna_igra.py:21)
+        u64 kb = 1ull << ((king & 3u) * 8 + 7);
+        team = (1u << declarer) | ((h0 & kb) ? 1u : 0u) | ((h1 & kb) ? 2u : 0u) | ((h2 & kb) ? 4u : 0u)
+             | ((h3 & kb) ? 8u : 0u);
+    } else {
+        king = NO_KING;
+        if (!bad && is_navadna(contract)) team = 1u << declarer;
+    }
+    if (!bad) {
+        if (is_berac(contract)) leader = declarer;
+        if (talon_k(contract) != 0) phase = PH_EXCHANGE;
+    }
+    meta = mset(meta, M_CONTRACT, 4, bad ? (u32)C_NONE : contract);
+    meta = mset(meta, M_DECL, 2, declarer & 3u);
+    meta = mset(meta, M_KING, 3, king);
+    meta = mset(meta, M_TEAM, 4, team);
+    meta = mset(meta, M_LEADER, 2, leader);
+    meta = mset(meta, M_PHASE, 2, bad ? (u32)PH_DONE : phase);
+    if (bad) meta |= 1ull << M_ERR;
+    return meta;
+}
+
+// ---- talon exchange -----------------------------------------------------------------------------
+// Group g of Navadna_igra.odpri_talon (Navadna_igra.py:36-44): consecutive slices of the ordered talon.
+__device__ __forceinline__ u64 talon_group_bits(u64 order, u32 k, u32 g) {
+    u64 b = 0;
+    for (u32 j = 0; j < k; j++) b |= 1ull << ((order >> (6 * (g * k + j))) & 63ull);
+    return b;
+}
+
+// ---- one card play ------------------------------------------------------------------------------
+// krog body (Navadna_igra.py:115-141 / Klop.py:47-79) for the seat to move.  `hand` is the mover's
+// hand.  On trick completion reports the winner seat and the bitboard that goes to its pile; Klop adds
+// the talon card popped from the END of the ordered talon in tricks 1..6 (Klop.py:67-71, Q4), which
+// never competes for the trick (Klop.py:81-86).  Berac stops when the declarer takes a trick
+// (Berac.py:33-39, Q12).
+struct PlayResult {
+    bool trick_done;
+    u32 winner;       // absolute seat
+    u64 pile_bits;    // cards the winner collects
+    u64 talon_clear;  // Klop: talon bit consumed
+};
+
+__device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talon, u64 talon_order,
+                                         PlayResult& out) {
+    out.trick_done = false; out.winner = 0; out.pile_bits = 0; out.talon_clear = 0;
+    u32 contract = mget(meta, M_CONTRACT, 4);
+    u32 pos = mget(meta, M_POS, 2);
+    u32 leader = mget(meta, M_LEADER, 2);
+    u32 lead = mget(meta, M_TRICK, 6);
+    u64 legal = legal_moves(hand, pos != 0, lead, klop_rules(contract));
+    u64 bit = card < 54 ? (1ull << card) : 0ull;
+    if (!(legal & bit)) {                                 // 'Karte ne mores igarti' (Navadna_igra.py:125-126)
+        meta |= 1ull << M_ERR;
+        return mset(meta, M_PHASE, 2, PH_DONE);
+    }
+    hand ^= bit;
+    meta &= ~(1ull << M_TRICKDONE);
+    meta += 1ull << M_PLAYS;
+    u64 tr = (pos == 0 ? 0ull : (meta >> M_TRICK) & 0xFFFFFFull) | ((u64)card << (6 * pos));
+    if (pos < 3) {
+        meta = (meta & ~(0xFFFFFFull << M_TRICK)) | (tr << M_TRICK);
+        return mset(meta, M_POS, 2, pos + 1);
+    }
+    // trick complete
+    u32 tricks = mget(meta, M_TRICKS, 4);
+    u32 t24 = (u32)tr;
+    u32 w = (leader + trick_winner(t24)) & 3u;
+    u64 bits = (1ull << (t24 & 63u)) | (1ull << ((t24 >> 6) & 63u)) | (1ull << ((t24 >> 12) & 63u))
+             | (1ull << ((t24 >> 18) & 63u));
+    if (contract == C_KLOP && tricks < 6) {
+        u64 tc = 1ull << ((talon_order >> (6 * (5 - tricks))) & 63ull);
+        out.talon_clear = tc & talon;
+        bits |= out.talon_clear;
+    }
+    out.trick_done = true; out.winner = w; out.pile_bits = bits;
+    tricks += 1;
+    meta = (meta & ~(0xFFFFFFull << M_TRICK)) | (tr << M_TRICK);   // keep the finished trick visible
+    meta = mset(meta, M_POS, 2, 0);
+    meta = mset(meta, M_LEADER, 2, w);
+    meta = mset(meta, M_WINNER, 2, w);
+    meta = mset(meta, M_TRICKS, 4, tricks);
+    meta |= 1ull << M_TRICKDONE;
+    bool fin = tricks == 12 || (is_berac(contract) && w == mget(meta, M_DECL, 2));
+    if (fin) meta = mset(meta, M_PHASE, 2, PH_DONE);
+    return meta;
+}
+
+// Legal mask of the seat to move given the (already updated) meta and that seat's hand.
+__device__ __forceinline__ u64 mask_for_mover(u64 meta, u64 hand) {
+    if (mget(meta, M_PHASE, 2) != PH_PLAY) return 0ull;
+    u32 pos = mget(meta, M_POS, 2);
+    return legal_moves(hand, pos != 0, mget(meta, M_TRICK, 6), klop_rules(mget(meta, M_CONTRACT, 4)));
+}
+__device__ __forceinline__ u32 mover_of(u64 meta) { return (mget(meta, M_LEADER, 2) + mget(meta, M_POS, 2)) & 3u; }
+
+// ---- scoring --------------------------------------------------------------------------------------
+// Epilogues: Navadna_igra.start (Navadna_igra.py:80-113, Q6/Q7), Klop.start (Klop.py:36-45, Q5),
+// Berac.start (Berac.py:33-44).  Returns the four scores packed as int16 x4 (seat 0 in the low half).
+__device__ __forceinline__ u64 score_game(u64 meta, u64 p0, u64 p1, u64 p2, u64 p3, u64 talon) {
+    u32 contract = mget(meta, M_CONTRACT, 4);
+    u32 decl = mget(meta, M_DECL, 2);
+    int s[4] = {0, 0, 0, 0};
+    if (is_navadna(contract)) {
+        u32 team = mget(meta, M_TEAM, 4);
+        u32 king = mget(meta, M_KING, 3);
+        u64 tp = ((team & 1u) ? p0 : 0) | ((team & 2u) ? p1 : 0) | ((team & 4u) ? p2 : 0) | ((team & 8u) ? p3 : 0);
+        u64 pd = sel4(p0, p1, p2, p3, decl);
+        bool to_team = contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING
+                    && (pd & (1ull << ((king & 3u) * 8 + 7)));
+        if (to_team) tp |= talon;
+        int v = prestej(tp);
+        int r = v - 35 + 2;                               // 5*round((v-35)/5): no ties for integers
+        int q = (r >= 0 ? r / 5 : -((-r + 4) / 5)) * 5;   // floor division
+        int val = (v > 35 ? 10 * (int)contract : -10 * (int)contract) + q;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[i] = ((team >> i) & 1u) ? val : 0;
+    } else if (contract == C_KLOP) {
+        int a = prestej(p0), b = prestej(p1), c = prestej(p2), d = prestej(p3);
+        bool any = a > 35 || b > 35 || c > 35 || d > 35;  // then everybody writes 0 (Klop.py:38-42, Q5)
+        s[0] = any ? 0 : -a; s[1] = any ? 0 : -b; s[2] = any ? 0 : -c; s[3] = any ? 0 : -d;
+    } else if (is_berac(contract)) {
+        int v = contract == C_ODPRTI_BERAC ? 90 : 70;
+        u64 pd = sel4(p0, p1, p2, p3, decl);              // no exchange in Berac: pile != 0 <=> took a trick
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[i] = ((u32)i == decl) ? (pd ? -v : v) : 0;
+    }
+    return (u64)(uint16_t)s[0] | ((u64)(uint16_t)s[1] << 16) | ((u64)(uint16_t)s[2] << 32) | ((u64)(uint16_t)s[3] << 48);
+}
+
+}  // namespace tk

@@ -1,0 +1,245 @@
+"""Batched Tarok environment: the host-side object over the C ABI (include/tarok_b200.h).
+
+One ``TarokEnv`` owns ``n_games`` concurrent deals on one GPU.  The whole rule engine of the
+reference -- ``Igra.razdeli`` (Igra.py:65-73), ``Igra.licitacija`` (Igra.py:75-114), the talon
+exchange of ``Navadna_igra.start`` (Navadna_igra.py:36-68), ``mozne_karte`` / ``krog`` /
+``pobere_stih`` (Navadna_igra.py:115-168, Klop.py:47-133, Berac.py:13-44) and the scoring
+epilogues -- runs in hand-written sm_100a kernels; this class only passes pointers and streams.
+PyTorch is used for device memory, streams and DLPack views, nothing else.
+
+All state fields are zero-copy ``torch`` views of the library's HBM arrays (structure of arrays,
+one int64 bitboard per game, bit i = card id i).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from torch.utils import dlpack as _dlpack
+
+from . import _lib
+
+DEFAULT_SEED = 0x5EED7A20C0001
+NO_KING = 7
+MODE_NAVADNA_MIX = 16
+MODE_AUCTION_UNIFORM = 17
+MODE_AUCTION_BOT = 18
+FLAG_HISTORY = 1
+
+(F_HANDS, F_PILES, F_TALON, F_TALON_ORDER, F_META, F_MASK, F_SCORES, F_HIST, F_STATS, F_HANDS0,
+ F_DISCARD) = range(11)
+
+# stats vector layout (include/tarok_b200.h)
+S_SEAT, S_PLAYER, S_CONTRACT, S_FINISHED, S_STEPS, S_ERRORS, S_ERR_EVENTS = 0, 4, 8, 18, 19, 20, 21
+
+# meta word layout (tarok_b200/csrc/tarok_rules.cuh)
+M_CONTRACT, M_DECL, M_KING, M_TEAM, M_LEADER, M_POS, M_TRICKS, M_TRICK = 0, 4, 6, 9, 13, 15, 17, 21
+M_PHASE, M_ERR, M_GROUP, M_WINNER, M_TRICKDONE, M_PLAYS = 45, 47, 48, 51, 53, 54
+PH_DEALT, PH_EXCHANGE, PH_PLAY, PH_DONE = 0, 1, 2, 3
+
+_DLTENSOR = b"dltensor"
+C.pythonapi.PyCapsule_New.restype = C.py_object
+C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+
+
+def meta_field(meta, shift, bits):
+    """Extract a bit field from the packed meta words (torch tensor or numpy array)."""
+    return (meta >> shift) & ((1 << bits) - 1)
+
+
+class TarokEnv:
+    def __init__(self, n_games: int, seed: int = DEFAULT_SEED, device: int = 0, history: bool = False):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.device = int(device)
+        self.n = int(n_games)
+        self.seed = int(seed)
+        rc = self._lib.tarok_create(self.device, self.n, self.seed & (2 ** 64 - 1),
+                                    FLAG_HISTORY if history else 0, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            _lib.check(None, rc)
+        self.n_alloc = int(self._lib.tarok_n_alloc(self._h))
+        self.history = bool(history)
+        self._views = {}
+        self.torch_device = torch.device("cuda", self.device)
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._views.clear()
+            rc = self._lib.tarok_destroy(self._h)
+            if rc == 0:
+                self._h = C.c_void_p()
+            else:
+                _lib.check(self._h, rc)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.torch_device).cuda_stream)
+
+    def _check(self, rc):
+        _lib.check(self._h, rc)
+
+    def _dev_u8(self, x, shape):
+        """Accept a CUDA uint8 tensor or anything numpy can read; returns a contiguous CUDA tensor."""
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.uint8)).to(self.torch_device, non_blocking=True)
+        if x.dtype != torch.uint8 or x.device != self.torch_device:
+            x = x.to(device=self.torch_device, dtype=torch.uint8)
+        x = x.contiguous()
+        if tuple(x.shape) != tuple(shape):
+            raise ValueError("expected shape %s, got %s" % (tuple(shape), tuple(x.shape)))
+        return x
+
+    def view(self, field: int) -> torch.Tensor:
+        """Zero-copy torch view of a state field (DLPack, aliases the library's HBM array)."""
+        t = self._views.get(field)
+        if t is None:
+            out = C.c_void_p()
+            self._check(self._lib.tarok_export(self._h, field, C.byref(out)))
+            cap = C.pythonapi.PyCapsule_New(out, _DLTENSOR, None)
+            t = _dlpack.from_dlpack(cap)
+            self._views[field] = t
+        return t
+
+    # zero-copy state
+    hands = property(lambda self: self.view(F_HANDS))            # int64 [4, n_alloc]
+    piles = property(lambda self: self.view(F_PILES))            # int64 [4, n_alloc]
+    talon = property(lambda self: self.view(F_TALON))            # int64 [n_alloc]
+    talon_order = property(lambda self: self.view(F_TALON_ORDER))
+    meta = property(lambda self: self.view(F_META))
+    mask = property(lambda self: self.view(F_MASK))              # legal moves of the seat to move
+    scores = property(lambda self: self.view(F_SCORES))          # int16 [n_alloc, 4]
+    hist = property(lambda self: self.view(F_HIST))              # uint8 [48, n_alloc]
+    stats_dev = property(lambda self: self.view(F_STATS))        # int64 [32]
+    hands0 = property(lambda self: self.view(F_HANDS0))
+    discard = property(lambda self: self.view(F_DISCARD))
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.tarok_launch_count(self._h))
+
+    # ------------------------------------------------------------------ deal (Igra.razdeli)
+    def deal(self, first_game_id: int = 0):
+        self._check(self._lib.tarok_deal(self._h, int(first_game_id), self._stream()))
+
+    def set_deals(self, perm, first_game_id: int = 0):
+        """Inject deals: uint8 [n,54] permutations, as a patched ``Igra.shuffle`` would."""
+        p = self._dev_u8(perm, (self.n, 54))
+        self._check(self._lib.tarok_set_deals(self._h, C.c_void_p(p.data_ptr()), int(first_game_id), self._stream()))
+
+    def export_perm(self) -> torch.Tensor:
+        out = torch.empty((self.n, 54), dtype=torch.uint8, device=self.torch_device)
+        self._check(self._lib.tarok_export_perm(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ auction / dispatch
+    def auction(self, intents):
+        """intents: uint8 [n,4] indices into ``Nevronski_igralec.index2igra`` (Igralec.py:717-745)."""
+        x = self._dev_u8(intents, (self.n, 4))
+        self._check(self._lib.tarok_auction(self._h, C.c_void_p(x.data_ptr()), self._stream()))
+
+    def auction_synth(self, mode: int):
+        self._check(self._lib.tarok_auction_synth(self._h, int(mode), self._stream()))
+
+    def force_contract(self, contract, declarer, king=None):
+        c = self._dev_u8(contract, (self.n,))
+        d = self._dev_u8(declarer, (self.n,))
+        k = None if king is None else self._dev_u8(king, (self.n,))
+        self._check(self._lib.tarok_force_contract(
+            self._h, C.c_void_p(c.data_ptr()), C.c_void_p(d.data_ptr()),
+            C.c_void_p(k.data_ptr()) if k is not None else None, self._stream()))
+
+    def force_contract_synth(self, mode: int):
+        self._check(self._lib.tarok_force_contract_synth(self._h, int(mode), self._stream()))
+
+    # ------------------------------------------------------------------ talon exchange
+    def exchange(self, group, discard):
+        g = self._dev_u8(group, (self.n,))
+        if not isinstance(discard, torch.Tensor):
+            discard = torch.from_numpy(np.ascontiguousarray(discard).astype(np.uint64).view(np.int64))
+        d = discard.to(device=self.torch_device, dtype=torch.int64).contiguous()
+        if tuple(d.shape) != (self.n,):
+            raise ValueError("discard must have shape (n,)")
+        self._check(self._lib.tarok_exchange(self._h, C.c_void_p(g.data_ptr()), C.c_void_p(d.data_ptr()), self._stream()))
+
+    def exchange_synth(self, random_group: bool = False):
+        self._check(self._lib.tarok_exchange_synth(self._h, 1 if random_group else 0, self._stream()))
+
+    # ------------------------------------------------------------------ play
+    def legal_mask(self) -> torch.Tensor:
+        """Recompute the legal-move masks from hands+meta (``mozne_karte``); int64 [n]."""
+        out = torch.empty(self.n_alloc, dtype=torch.int64, device=self.torch_device)
+        self._check(self._lib.tarok_legal_mask(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out[: self.n]
+
+    def step(self, cards):
+        """One card per live game (``igraj_karto``); cards: uint8 [n] card ids."""
+        x = self._dev_u8(cards, (self.n,))
+        if self.n_alloc != self.n:   # kernel reads two actions per lane
+            pad = torch.zeros(self.n_alloc, dtype=torch.uint8, device=self.torch_device)
+            pad[: self.n] = x
+            x = pad
+        self._check(self._lib.tarok_step(self._h, C.c_void_p(x.data_ptr()), self._stream()))
+
+    def step_random(self, count: int = 1):
+        """``count`` back-to-back steps with in-kernel uniform-random legal cards (Bot_igralec, Igralec.py:158-159)."""
+        if count == 1:
+            self._check(self._lib.tarok_step_random(self._h, self._stream()))
+        else:
+            self._check(self._lib.tarok_steps_random(self._h, int(count), self._stream()))
+
+    # ------------------------------------------------------------------ scoring / stats
+    def score(self) -> torch.Tensor:
+        """Scores by seat, int16 [n,4] (``pisejo``); also accumulates the statistics vector."""
+        self._check(self._lib.tarok_score(self._h, None, self._stream()))
+        return self.scores[: self.n]
+
+    def reset_stats(self):
+        self._check(self._lib.tarok_reset_stats(self._h, self._stream()))
+
+    def stats(self) -> np.ndarray:
+        out = np.zeros(32, np.int64)
+        self._check(self._lib.tarok_read_stats(self._h, out.ctypes.data_as(C.c_void_p), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ whole deals
+    def rollout(self, mode: int, first_game_id: int = 0, fused: bool = False):
+        """deal -> contract(mode) -> exchange -> random play -> score, all on the device."""
+        fn = self._lib.tarok_rollout_fused if fused else self._lib.tarok_rollout_stepwise
+        self._check(fn(self._h, int(mode), int(first_game_id), self._stream()))
+
+    def rollout_host(self, perm, contract, declarer, king, scores_out, stats_out, first_game_id: int = 0,
+                     fused: bool = False):
+        """End-to-end entry with HOST buffers (numpy arrays or pinned CPU torch tensors).
+
+        Uploads the injected deals + forced contracts, plays them with uniform-random players and
+        downloads ``scores_out`` (int16 [n,4]) and ``stats_out`` (int64 [32]).  Asynchronous on the
+        current stream when the buffers are pinned; the caller synchronises."""
+        def hp(a):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                assert a.device.type == "cpu" and a.is_contiguous()
+                return C.c_void_p(a.data_ptr())
+            assert a.flags["C_CONTIGUOUS"]
+            return a.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.tarok_rollout_host(
+            self._h, hp(perm), hp(contract), hp(declarer), hp(king), int(first_game_id), 1 if fused else 0,
+            hp(scores_out), hp(stats_out), self._stream()))
+
+    # ------------------------------------------------------------------ helpers
+    def errors(self) -> int:
+        """Number of games whose error bit is set (illegal action / invalid exchange / bad deal)."""
+        return int(((self.meta[: self.n] >> M_ERR) & 1).sum().item())
+
+    def live(self) -> torch.Tensor:
+        """bool [n]: games still waiting for a card."""
+        return meta_field(self.meta[: self.n], M_PHASE, 2) == PH_PLAY

@@ -1,0 +1,47 @@
+"""CPU: the C-ABI library loads (no GPU needed) and exports every symbol include/tarok_b200.h declares."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "tarok_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tarok_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_is_built_and_exports_every_declared_symbol():
+    import __graft_entry__ as G
+    G.build()
+    from tarok_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 25
+    for nm in names:
+        assert hasattr(lib, nm), "libtarok_b200.so does not export %s" % nm
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+
+
+def test_no_gpu_fails_loudly_not_silently():
+    """Without a CUDA device tarok_create must return an error (there is no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tarok_b200 import _lib
+    from tarok_b200.env import TarokEnv
+    with pytest.raises(_lib.TarokLibraryError) as ei:
+        TarokEnv(16)
+    assert "no CUDA device" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tarok_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("oracle's", "") or f == "README.md", \
+                    "%s mentions the oracle" % f

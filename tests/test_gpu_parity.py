@@ -1,0 +1,289 @@
+"""GPU parity: the CUDA path, called through the C ABI (tarok_b200.env.TarokEnv -> libtarok_b200.so),
+against (a) vectors frozen from the real reference (tests/golden) and (b) the C oracle on the same
+seeded inputs.  Bar: bit-exact (all arithmetic on this path is integer)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+ALL54 = (1 << 54) - 1
+
+
+def u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def _env(n, **kw):
+    from tarok_b200.env import TarokEnv
+    return TarokEnv(n, **kw)
+
+
+def _meta(env):
+    import tarok_b200.env as E
+    m = u64(env.meta[: env.n])
+    f = lambda sh, b: ((m >> np.uint64(sh)) & np.uint64((1 << b) - 1)).astype(np.int64)
+    return dict(contract=f(E.M_CONTRACT, 4), declarer=f(E.M_DECL, 2), king=f(E.M_KING, 3), team=f(E.M_TEAM, 4),
+                leader=f(E.M_LEADER, 2), pos=f(E.M_POS, 2), tricks=f(E.M_TRICKS, 4), phase=f(E.M_PHASE, 2),
+                err=f(E.M_ERR, 1), group=f(E.M_GROUP, 3), winner=f(E.M_WINNER, 2), trickdone=f(E.M_TRICKDONE, 1),
+                plays=f(E.M_PLAYS, 6))
+
+
+def _replay_on_gpu(g, use_auction=False):
+    """Teacher-forces a golden trace set through the stepwise kernels, checking every exposed value."""
+    n = len(g["perm"])
+    env = _env(n, history=True)
+    env.set_deals(g["perm"])
+    hands0 = u64(env.hands[:, :n]).T
+    if "hands0" in g.files and g["hands0"].any():
+        assert (hands0 == g["hands0"]).all()
+    if use_auction:
+        env.auction(g["intent"])
+    else:
+        env.force_contract(g["contract"], g["declarer"], g["king"])
+    m = _meta(env)
+    assert (m["contract"] == g["contract"]).all()
+    nk = g["contract"] != 0
+    assert (m["declarer"][nk] == g["declarer"][nk]).all()
+    assert (m["king"] == g["king"]).all()
+    env.exchange(g["group"], g["discard_mask"])
+    assert env.errors() == 0
+    live = np.ones(n, bool)
+    for t in range(48):
+        m = _meta(env)
+        live = m["phase"] == 2
+        assert (live == (g["plays"] > t)).all(), t
+        mover = (m["leader"] + m["pos"]) & 3
+        assert (mover[live] == g["seat"][live, t]).all(), t
+        assert (u64(env.mask[:n])[live] == g["mask"][live, t]).all(), t
+        assert (u64(env.legal_mask())[live] == g["mask"][live, t]).all(), t
+        env.step(g["card"][:, t])
+        if t % 4 == 3:
+            m2 = _meta(env)
+            assert (m2["trickdone"][live] == 1).all()
+            assert (m2["winner"][live] == g["winner"][live, t // 4]).all(), t
+    assert env.errors() == 0
+    m = _meta(env)
+    assert (m["phase"] == 3).all() and (m["plays"] == g["plays"]).all()
+    sc = env.score().cpu().numpy()
+    assert (sc == g["scores"]).all()
+    assert (u64(env.hands[:, :n]).T == g["hands"]).all()
+    assert (u64(env.piles[:, :n]).T == g["piles"]).all()
+    # conservation: hands, piles and talon partition the deck
+    tot = np.bitwise_or.reduce(u64(env.hands[:, :n]), axis=0) | np.bitwise_or.reduce(u64(env.piles[:, :n]), axis=0) \
+        | u64(env.talon[:n])
+    assert (tot == np.uint64(ALL54)).all()
+    hist = env.hist[:, :n].cpu().numpy().T
+    played = g["card"] != 0xFF
+    assert ((hist & 63)[played] == g["card"][played]).all()
+    assert ((hist >> 6)[played] == g["seat"][played]).all()
+    assert (hist[~played] == 0xFF).all()
+    st = env.stats()
+    assert st[18] == n and st[19] == g["plays"].astype(np.int64).sum() and st[20] == 0
+    assert (st[0:4] == g["scores"].astype(np.int64).sum(axis=0)).all()
+    assert (st[8:18] == np.bincount(g["contract"], minlength=10)).all()
+    env.close()
+
+
+def test_golden_traces_forced(golden):
+    _replay_on_gpu(golden("traces_forced.npz"))
+
+
+def test_golden_traces_full_auction(golden):
+    _replay_on_gpu(golden("traces_full.npz"), use_auction=True)
+
+
+def test_kat_table_scores_and_history_hash():
+    rows = json.load(open(os.path.join(GOLDEN, "kat.json")))
+    n = len(rows)
+    env = _env(n, history=True)
+    perm = np.array([r["perm"] for r in rows], np.uint8)
+    env.set_deals(perm)
+    env.force_contract([r["contract"] for r in rows], [r["declarer"] for r in rows], [r["king"] for r in rows])
+    env.exchange([r["group"] for r in rows], np.array([r["discard_mask"] for r in rows], np.uint64))
+    cards = np.full((n, 48), 0xFF, np.uint8)
+    for i, r in enumerate(rows):
+        cards[i, :len(r["cards"])] = r["cards"]
+    for t in range(48):
+        env.step(cards[:, t])
+    sc = env.score().cpu().numpy()
+    hist = env.hist[:, :n].cpu().numpy().T
+    for i, r in enumerate(rows):
+        assert sc[i].tolist() == r["scores"], r
+        b = bytearray()
+        for t in range(r["plays"]):
+            b += bytes((hist[i, t] >> 6, hist[i, t] & 63))
+            if r["contract"] == 0 and t % 4 == 3 and t // 4 < 6:      # Klop talon card, seat 9
+                b += bytes((9, perm[i, 53 - t // 4]))
+        assert hashlib.sha256(bytes(b)).hexdigest()[:16] == r["hash"], r
+    env.close()
+
+
+TIP_TO_INDEX = {-1: 0, 0: 19, 1: 1, 2: 5, 3: 9, 4: 13, 5: 14, 6: 15, 7: 16, 8: 17, 9: 18}
+
+
+def test_auction_fixed_exhaustive(golden):
+    a = golden("auction_fixed.npz")
+    n = len(a["intents"])
+    env = _env(n)
+    env.deal()
+    idx = np.vectorize(TIP_TO_INDEX.get)(a["intents"]).astype(np.uint8)
+    env.auction(idx)
+    m = _meta(env)
+    assert (m["contract"] == a["contract"]).all()
+    nk = a["contract"] != 0
+    assert (m["declarer"][nk] == a["declarer"][nk]).all()
+    env.close()
+
+
+def test_deal_matches_oracle_and_is_shard_invariant(oracle):
+    n = 30001
+    env = _env(n, seed=1234)
+    env.deal(first_game_id=0)
+    p = env.export_perm().cpu().numpy()
+    assert (p == oracle.deal(1234, 0, n)).all()
+    env.deal(first_game_id=777)
+    assert (env.export_perm().cpu().numpy() == oracle.deal(1234, 777, n)).all()
+    # round trip: injecting the exported deal reproduces the state
+    h = u64(env.hands).copy(); t = u64(env.talon).copy(); o = u64(env.talon_order).copy()
+    env.set_deals(env.export_perm())
+    assert (u64(env.hands) == h).all() and (u64(env.talon) == t).all() and (u64(env.talon_order) == o).all()
+    env.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 18])
+def test_rollout_matches_oracle(oracle, mode):
+    """Whole deals with the Philox players: stepwise kernels == fused kernel == C oracle."""
+    n, seed, gid0 = 20011, 4242, 123456789
+    ref = oracle.rollout(seed, gid0, n, mode)
+    env = _env(n, seed=seed, history=True)
+    env.rollout(mode, first_game_id=gid0, fused=False)
+    m = _meta(env)
+    ok = ref["err"] == 0
+    assert (m["err"] == ref["err"]).all()
+    assert (m["contract"][ok] == ref["contract"][ok]).all()
+    nk = ok & (ref["contract"] != 0)
+    assert (m["declarer"][nk] == ref["declarer"][nk]).all()
+    assert (m["king"][ok] == ref["king"][ok]).all()
+    assert (m["plays"] == ref["plays"]).all()
+    hist = env.hist[:, :n].cpu().numpy().T
+    played = ref["cards"] != 0xFF
+    assert ((hist & 63)[played] == ref["cards"][played]).all()
+    assert (hist[~played] == 0xFF).all()
+    sc = env.scores[:n].cpu().numpy()
+    assert (sc == ref["scores"]).all()
+    st = env.stats()
+    assert (st[0:4] == ref["stats"][0:4]).all() and (st[4:8] == ref["stats"][4:8]).all()
+    assert st[19] == ref["stats"][8] and st[20] == ref["stats"][9] and st[18] == ok.sum()
+    assert (st[8:18] == np.bincount(ref["contract"][ok], minlength=10)).all()
+    state = {k: u64(getattr(env, k)).copy() for k in ("hands", "piles", "talon", "talon_order", "meta")}
+    # fused kernel: identical state, scores and statistics
+    env.reset_stats()
+    env.rollout(mode, first_game_id=gid0, fused=True)
+    for k, v in state.items():
+        assert (u64(getattr(env, k)) == v).all(), k
+    assert (env.scores[:n].cpu().numpy() == sc).all()
+    assert (env.stats()[:21] == st[:21]).all()
+    assert (env.hist[:, :n].cpu().numpy().T == hist).all()
+    env.close()
+
+
+def test_teacher_forced_replay_at_full_size(oracle):
+    """BASELINE config 2 size: 1,048,576 Navadna deals played on the GPU, then EVERY game replayed
+    card by card through the C oracle (legality, trick winners, scores)."""
+    import tarok_b200.env as E
+    n = 1 << 20
+    env = _env(n, seed=7, history=True)
+    env.deal(0)
+    perm = env.export_perm().cpu().numpy()
+    env.force_contract_synth(E.MODE_NAVADNA_MIX)
+    env.exchange_synth(False)
+    m = _meta(env)
+    disc = u64(env.discard[:n]).copy()
+    for _ in range(48):
+        env.step_random()
+    sc = env.score().cpu().numpy()
+    hist = env.hist[:, :n].cpu().numpy().T
+    cards = np.where(hist == 0xFF, 0xFF, hist & 63).astype(np.uint8)
+    rep = oracle.replay(perm, m["contract"].astype(np.uint8), m["declarer"].astype(np.uint8),
+                        m["king"].astype(np.uint8), m["group"].astype(np.uint8), disc, cards, want_state=False)
+    gerr = _meta(env)["err"]
+    ok = gerr == 0
+    assert ok.mean() > 0.999
+    assert (rep["err"][ok] == 0).all()
+    assert (rep["scores"][ok] == sc[ok]).all()
+    assert ((hist >> 6)[ok] == rep["seat"][ok]).all()
+    # size-independent properties
+    assert (u64(env.hands[:, :n])[:, ok] == 0).all()
+    tot = np.bitwise_or.reduce(u64(env.piles[:, :n]), axis=0) | u64(env.talon[:n])
+    assert (tot[ok] == np.uint64(ALL54)).all()
+    st = env.stats()
+    assert st[19] == 48 * ok.sum() and st[18] == ok.sum()
+    env.close()
+
+
+def test_illegal_action_sets_error_bit_and_stops_the_game():
+    n = 1024
+    env = _env(n, seed=3)
+    env.deal()
+    env.force_contract_synth(0)
+    mask = u64(env.mask[:n])
+    legal_lowest = np.array([int(x & -x).bit_length() - 1 for x in mask.astype(object)], np.uint8)
+    cards = legal_lowest.copy()
+    bad = np.arange(n) % 7 == 0
+    hands0 = u64(env.hands[0, :n])
+    for i in np.nonzero(bad)[0]:   # a card the leader does not hold
+        cards[i] = next(c for c in range(54) if not (int(hands0[i]) >> c) & 1)
+    env.step(cards)
+    m = _meta(env)
+    assert (m["err"] == bad).all()
+    assert (m["phase"][bad] == 3).all() and (m["phase"][~bad] == 2).all()
+    assert env.stats()[21] == bad.sum()
+    assert (u64(env.hands[0, :n])[bad] == hands0[bad]).all()      # state untouched
+    env.close()
+
+
+def test_invalid_exchange_is_an_error():
+    n = 512
+    env = _env(n, seed=5)
+    env.deal()
+    env.force_contract(np.full(n, 1, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8))
+    disc = np.zeros(n, np.uint64)
+    hands = u64(env.hands[0, :n])
+    kings = np.uint64((1 << 7) | (1 << 15) | (1 << 23) | (1 << 31))
+    disc[:] = hands & kings          # kings can never be laid down (Q8); also wrong count
+    env.exchange(np.zeros(n, np.uint8), disc)
+    assert (_meta(env)["err"] == 1).all()
+    env.close()
+
+
+def test_host_buffer_entry_matches_device_path(oracle):
+    import torch
+    n = 50000
+    ref = oracle.rollout(11, 0, n, 16)
+    for fused in (False, True):
+        env = _env(n, seed=11)
+        scores = torch.empty((n, 4), dtype=torch.int16).pin_memory()
+        stats = torch.zeros(32, dtype=torch.int64).pin_memory()
+        env.rollout_host(ref["perm"], ref["contract"], ref["declarer"], ref["king"], scores, stats, fused=fused)
+        torch.cuda.synchronize()
+        assert (scores.numpy() == ref["scores"]).all()
+        assert stats[19] == ref["stats"][8]
+        assert (stats[0:8].numpy() == ref["stats"][0:8]).all()
+        env.close()
+
+
+def test_no_cpu_fallback_symbols_loaded():
+    """The product path is the CUDA library: it must be loaded in-process and have launched kernels."""
+    env = _env(1000)
+    before = env.launches
+    env.rollout(0)
+    assert env.launches - before == 52
+    with open("/proc/self/maps") as f:
+        assert "libtarok_b200.so" in f.read()
+    env.close()
