@@ -9,7 +9,9 @@
  *
  *   word(gid, stream, idx)  = philox4x32_10(key = seed, ctr = {gid.lo, gid.hi, stream | attempt<<16, idx>>2})[idx&3]
  *   draw(gid, stream, idx, n) = Lemire multiply-shift with rejection on word(...) -> uniform in [0,n)
- *   streams: 0 deal, 1 bids, 2 king, 3 exchange, 4 play, 5 forced contract/declarer
+ *   streams: 0 deal, 1 bids, 2 king, 3 exchange, 4 play, 5 forced contract/declarer, 6 play retry
+ *   play draws (n <= 12) use 16-bit lanes: one Philox block per (game pair = gid>>1, trick) holds eight
+ *   16-bit values, lane = (gid&1)*4 + play-in-trick; 16-bit Lemire, rejected sliver -> 32-bit draw on stream 6
  *
  * It doubles as bench.py's CPU baseline ("port": OpenMP over games).
  */
@@ -47,7 +49,7 @@ uint32_t syn_draw(uint64_t seed, uint64_t gid, uint32_t stream, uint32_t idx, ui
     }
 }
 
-enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5 };
+enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5, ST_PLAY_RETRY = 6 };
 enum { MODE_NAVADNA_MIX = 16, MODE_AUCTION_UNIFORM = 17, MODE_AUCTION_BOT = 18 };
 
 /* Uniform deal: card c = 0..53 goes to a uniformly random free slot among the 54-c left; slots
@@ -98,6 +100,17 @@ static int want_bot(void* p, int seat, int call) {
     bid_ctx* b = (bid_ctx*)p;     /* np.random.choice([Naprej,Tri,Dve,Ena], p=[.5,1/6,1/6,1/6]), Igralec.py:151 */
     uint32_t u = syn_draw(b->seed, b->gid, ST_BID, (uint32_t)call, 6);
     return u < 3 ? ORC_NAPREJ : (int)(ORC_TRI + (u - 3));
+}
+
+uint32_t syn_play_draw(uint64_t seed, uint64_t gid, uint32_t t, uint32_t n) {
+    uint64_t pair = gid >> 1;
+    uint32_t c[4] = { (uint32_t)pair, (uint32_t)(pair >> 32), ST_PLAY, t >> 2 };
+    syn_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t lane = ((uint32_t)gid & 1u) * 4u + (t & 3u);
+    uint32_t x = (c[lane >> 1] >> (16 * (lane & 1u))) & 0xFFFFu;
+    uint32_t m = x * n, lo = m & 0xFFFFu;
+    if (lo < n && lo < (65536u % n)) return syn_draw(seed, gid, ST_PLAY_RETRY, t, n);
+    return m >> 16;
 }
 
 static int nth_lowest(uint64_t m, uint32_t r) {
@@ -156,7 +169,7 @@ int syn_rollout(uint64_t seed, uint64_t gid, int mode, orc_game* g, uint8_t perm
     int t = 0;
     while (!g->error && g->phase == 2) {
         uint64_t m = orc_mozne_mask(g);
-        uint32_t r = syn_draw(seed, gid, ST_PLAY, (uint32_t)t, (uint32_t)__builtin_popcountll(m));
+        uint32_t r = syn_play_draw(seed, gid, (uint32_t)t, (uint32_t)__builtin_popcountll(m));
         int c = nth_lowest(m, r);
         cards[t++] = (uint8_t)c;
         orc_igraj(g, c);

@@ -48,15 +48,18 @@ __device__ __forceinline__ bool lemire(u32 x, u32 n, u32& out) {
     return lo >= t;
 }
 
-// Cold path: redraw with attempt = 1, 2, ... until accepted.
-__device__ __noinline__ u32 draw_retry(u64 seed, u64 gid, u32 stream, u32 idx, u32 n) {
-    for (u32 attempt = 1;; attempt++) {
+// Cold path: redraw with attempt = first, first+1, ... until accepted.
+__device__ __noinline__ u32 draw_loop(u64 seed, u64 gid, u32 stream, u32 idx, u32 n, u32 first) {
+    for (u32 attempt = first;; attempt++) {
         Words4 b = philox_block(seed, gid, stream | (attempt << 16), idx >> 2);
         u32 r;
         u32 x = (idx & 3u) == 0 ? b.w[0] : (idx & 3u) == 1 ? b.w[1] : (idx & 3u) == 2 ? b.w[2] : b.w[3];
         if (lemire(x, n, r)) return r;
     }
 }
+
+__device__ __forceinline__ u32 draw_retry(u64 seed, u64 gid, u32 stream, u32 idx, u32 n) { return draw_loop(seed, gid, stream, idx, n, 1u); }
+__device__ __forceinline__ u32 draw_retry0(u64 seed, u64 gid, u32 stream, u32 idx, u32 n) { return draw_loop(seed, gid, stream, idx, n, 0u); }
 
 __device__ __forceinline__ u32 draw_from_word(u32 x, u64 seed, u64 gid, u32 stream, u32 idx, u32 n) {
     u32 r;
@@ -70,6 +73,31 @@ __device__ __forceinline__ u32 draw(u64 seed, u64 gid, u32 stream, u32 idx, u32 
     u32 k = idx & 3u;
     u32 x = k == 0 ? b.w[0] : k == 1 ? b.w[1] : k == 2 ? b.w[2] : b.w[3];
     return draw_from_word(x, seed, gid, stream, idx, n);
+}
+
+// ---- play draws -------------------------------------------------------------------------------------
+// A legal mask holds at most 12 cards, so a play needs far fewer than 32 random bits.  One Philox block is
+// shared by TWO consecutive games (pair = gid >> 1) and the FOUR plays of one trick: eight 16-bit lanes,
+//   lane(g, t) = (g & 1) * 4 + (t & 3),   block = philox(key = seed, ctr = {pair.lo, pair.hi, ST_PLAY, t >> 2}).
+// The stepwise kernel (one lane = one game pair) therefore needs ONE block per lane per step, the fused
+// kernel (one lane = one game) one block per trick.  16-bit Lemire with rejection keeps the draw exactly
+// uniform; the rejected sliver (probability < n / 65536) falls back to a 32-bit draw on stream ST_PLAY_RETRY.
+enum : u32 { ST_PLAY_RETRY = 6 };
+
+__device__ __forceinline__ Words4 play_block(u64 seed, u64 gid, u32 trick) {
+    return philox_block(seed, gid >> 1, ST_PLAY, trick);
+}
+
+__device__ __forceinline__ u32 play_draw(const Words4& b, u64 seed, u64 gid, u32 t, u32 n) {
+    u32 lane = ((u32)gid & 1u) * 4u + (t & 3u);
+    u32 w = (lane >> 1) == 0 ? b.w[0] : (lane >> 1) == 1 ? b.w[1] : (lane >> 1) == 2 ? b.w[2] : b.w[3];
+    u32 x = (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
+    u32 m = x * n;
+    u32 lo = m & 0xFFFFu;
+    if (__builtin_expect(lo < n, 0)) {
+        if (lo < (65536u % n)) return draw_retry0(seed, gid, ST_PLAY_RETRY, t, n);
+    }
+    return m >> 16;
 }
 
 }  // namespace tk

@@ -384,24 +384,25 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
 // ------------------------------------------------------------------------------------------------
 template <bool RANDOM>
 __device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, u64 h0, u64 h1, u64 h2, u64 h3, u32 card,
-                                          u64& next_mask) {
+                                          const Words4& rnd, u64& next_mask) {
     const u64 na = e.n_alloc;
-    u32 mover = mover_of(meta);
+    const u32 mover = mover_of(meta);
     u64 hand = sel4(h0, h1, h2, h3, mover);
-    u32 contract = mget(meta, M_CONTRACT, 4);
-    u32 plays = mget(meta, M_PLAYS, 6);
+    const u32 contract = mget(meta, M_CONTRACT, 4);
+    const u32 plays = mget(meta, M_PLAYS, 6);
     u64 talon = 0, order = 0;
-    bool klop_talon = contract == C_KLOP && mget(meta, M_POS, 2) == 3 && mget(meta, M_TRICKS, 4) < 6;
-    if (klop_talon) { talon = e.talon[g]; order = e.torder[g]; }
+    if (contract == C_KLOP && mget(meta, M_POS, 2) == 3 && mget(meta, M_TRICKS, 4) < 6) {
+        talon = e.talon[g]; order = e.torder[g];
+    }
     if (RANDOM) {
         u64 legal = legal_moves(hand, mget(meta, M_POS, 2) != 0, mget(meta, M_TRICK, 6), klop_rules(contract));
         u32 n = (u32)__popcll(legal);
-        card = n ? nth_set_bit(legal, draw(e.seed, e.first_gid + g, ST_PLAY, plays, n)) : 63u;
+        card = nth_set_bit(legal, play_draw(rnd, e.seed, e.first_gid + g, plays, n));
     }
     PlayResult pr;
-    meta = play_card(meta, hand, card, talon, order, pr);
+    meta = play_card<!RANDOM>(meta, hand, card, talon, order, pr);
     next_mask = 0;
-    if ((meta >> M_ERR) & 1ull) {
+    if (!RANDOM && ((meta >> M_ERR) & 1ull)) {
         atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
         return;
     }
@@ -412,25 +413,35 @@ __device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, u64 h0
         *pp |= pr.pile_bits;
         if (pr.talon_clear) e.talon[g] = talon & ~pr.talon_clear;
     }
-    u32 nx = mover_of(meta);
+    const u32 nx = mover_of(meta);
     next_mask = mask_for_mover(meta, nx == mover ? hand : sel4(h0, h1, h2, h3, nx));
 }
 
 template <bool RANDOM>
-__global__ void __launch_bounds__(CTA) k_step(Env e, const uint8_t* __restrict__ action) {
-    u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
+__global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restrict__ action) {
+    const u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
     if (g >= e.n_alloc) return;
-    ulonglong2 m = ld2(e.meta + g);
-    bool a0 = mget(m.x, M_PHASE, 2) == PH_PLAY, a1 = mget(m.y, M_PHASE, 2) == PH_PLAY;
-    if (!a0 && !a1) return;
     const u64 na = e.n_alloc;
+    // all five 128-bit loads are issued before the first use: one memory round trip per step
+    ulonglong2 m = ld2(e.meta + g);
     ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + na + g), h2 = ld2(e.hands + 2 * na + g),
                h3 = ld2(e.hands + 3 * na + g);
     u32 act = 0;
     if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
+    const bool a0 = mget(m.x, M_PHASE, 2) == PH_PLAY, a1 = mget(m.y, M_PHASE, 2) == PH_PLAY;
+    if (!a0 && !a1) return;
+    Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
+    if (RANDOM) {
+        // one Philox block serves both games of the lane (same pair, same trick) in the common case
+        const u64 gid = e.first_gid + g;
+        const u32 t0 = mget(m.x, M_PLAYS, 6) >> 2, t1 = mget(m.y, M_PLAYS, 6) >> 2;
+        r0 = play_block(e.seed, gid, t0);
+        r1 = r0;
+        if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.seed, gid + 1, t1);
+    }
     u64 k0 = 0, k1 = 0;
-    if (a0) step_game<RANDOM>(e, g, m.x, h0.x, h1.x, h2.x, h3.x, act & 0xFFu, k0);
-    if (a1) step_game<RANDOM>(e, g + 1, m.y, h0.y, h1.y, h2.y, h3.y, act >> 8, k1);
+    if (a0) step_game<RANDOM>(e, g, m.x, h0.x, h1.x, h2.x, h3.x, act & 0xFFu, r0, k0);
+    if (a1) step_game<RANDOM>(e, g + 1, m.y, h0.y, h1.y, h2.y, h3.y, act >> 8, r1, k1);
     st2(e.meta + g, m.x, m.y);
     st2(e.mask + g, k0, k1);
 }
@@ -534,16 +545,16 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         const u32 contract = mget(meta, M_CONTRACT, 4);
         const bool klop = klop_rules(contract);
         for (u32 trick = 0; trick < 12 && mget(meta, M_PHASE, 2) == PH_PLAY; trick++) {
-            Words4 blk = philox_block(e.seed, gid, ST_PLAY, trick);     // 4 plays = one Philox block
+            Words4 blk = play_block(e.seed, gid, trick);                // 4 plays = half of one Philox block
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 u32 mover = mover_of(meta);
                 u64 hand = sel4(h0, h1, h2, h3, mover);
                 u64 legal = legal_moves(hand, j != 0, mget(meta, M_TRICK, 6), klop);
                 u32 n = (u32)__popcll(legal);
-                u32 card = nth_set_bit(legal, draw_from_word(blk.w[j], e.seed, gid, ST_PLAY, trick * 4 + j, n));
+                u32 card = nth_set_bit(legal, play_draw(blk, e.seed, gid, trick * 4 + j, n));
                 PlayResult pr;
-                meta = play_card(meta, hand, card, talon, order, pr);
+                meta = play_card<false>(meta, hand, card, talon, order, pr);
                 if (e.hist && write_state) e.hist[(u64)(trick * 4 + j) * na + g] = (uint8_t)((mover << 6) | card);
                 h0 = mover == 0 ? hand : h0; h1 = mover == 1 ? hand : h1; h2 = mover == 2 ? hand : h2; h3 = mover == 3 ? hand : h3;
                 if (pr.trick_done) {

@@ -258,18 +258,22 @@ struct PlayResult {
     u64 talon_clear;  // Klop: talon bit consumed
 };
 
+// CHECK = validate the card against the legal set (externally supplied actions); the in-kernel random
+// players pick from the legal set by construction and skip it.
+template <bool CHECK>
 __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talon, u64 talon_order,
                                          PlayResult& out) {
     out.trick_done = false; out.winner = 0; out.pile_bits = 0; out.talon_clear = 0;
-    u32 contract = mget(meta, M_CONTRACT, 4);
-    u32 pos = mget(meta, M_POS, 2);
-    u32 leader = mget(meta, M_LEADER, 2);
-    u32 lead = mget(meta, M_TRICK, 6);
-    u64 legal = legal_moves(hand, pos != 0, lead, klop_rules(contract));
-    u64 bit = card < 54 ? (1ull << card) : 0ull;
-    if (!(legal & bit)) {                                 // 'Karte ne mores igarti' (Navadna_igra.py:125-126)
-        meta |= 1ull << M_ERR;
-        return mset(meta, M_PHASE, 2, PH_DONE);
+    const u32 contract = mget(meta, M_CONTRACT, 4);
+    const u32 pos = mget(meta, M_POS, 2);
+    const u32 leader = mget(meta, M_LEADER, 2);
+    const u64 bit = card < 54 ? (1ull << card) : 0ull;
+    if (CHECK) {
+        u64 legal = legal_moves(hand, pos != 0, mget(meta, M_TRICK, 6), klop_rules(contract));
+        if (!(legal & bit)) {                             // 'Karte ne mores igarti' (Navadna_igra.py:125-126)
+            meta |= 1ull << M_ERR;
+            return mset(meta, M_PHASE, 2, PH_DONE);
+        }
     }
     hand ^= bit;
     meta &= ~(1ull << M_TRICKDONE);
