@@ -56,8 +56,42 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.lines, self.proc = index, [], None
+        self.nvml, self.samples, self.stop_flag = None, [], False
+
+    def _nvml_loop(self):
+        import pynvml as N
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+                rs = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def _nvml_result(self):
+        import pynvml as N
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        names = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in self.samples))
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if sm else None,
+                "samples": len(sm), "reasons": reasons, "source": "NVML, 2 ms period, timed region only"}
 
     def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.nvml = N
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
@@ -72,6 +106,8 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            return self._nvml_result()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -253,28 +289,30 @@ def run_ours(args, rank, world, local_rank):
     k_h = torch.from_numpy(rng.integers(0, 4, n, dtype=np.uint8)).pin_memory()
     sc_h = torch.empty((n, 4), dtype=torch.int16).pin_memory()
     st_h = torch.zeros(32, dtype=torch.int64).pin_memory()
-    e2e_steps = 0
+    def e2e_run(fused):
+        def once(i):
+            env.rollout_host(perm_h, c_h, d_h, k_h, sc_h, st_h, first_game_id=i * total + rank * n, fused=fused)
+            torch.cuda.current_stream().synchronize()                     # the host reads the result
+            return int(st_h[S_STEPS])
+        for i in range(args.warmup):
+            once(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cnt = 0
+        e0.record()
+        for i in range(args.steps):
+            cnt += once(args.warmup + i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        c = torch.tensor([cnt], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c)
+        return float(c.item()) / (float(t.item()) * 1e-3), float(t.item()) / args.steps
 
-    def e2e_once(i):
-        env.rollout_host(perm_h, c_h, d_h, k_h, sc_h, st_h, first_game_id=i * total + rank * n, fused=False)
-        torch.cuda.current_stream().synchronize()                         # the host reads the result
-        return int(st_h[S_STEPS])
-
-    for i in range(args.warmup):
-        e2e_once(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        e2e_steps += e2e_once(args.warmup + i)
-    e1.record()
-    barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    e2e_cnt = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_cnt)
-    e2e_value = float(e2e_cnt.item()) / (float(e2e_ms.item()) * 1e-3)
+    e2e_value, e2e_ms = e2e_run(True)          # fused kernel behind an 8-chunk upload/compute/download pipeline
+    e2e_sw_value, e2e_sw_ms = e2e_run(False)   # stepwise kernels, serial upload -> 52 launches -> download
 
     # ---- HBM-bound regime: the same step kernel on a state 8x larger than L2 (informational)
     big = None
@@ -316,8 +354,10 @@ def run_ours(args, rank, world, local_rank):
                              "play_steps revisit the %d MB state as the workload prescribes" % (n * 104 >> 20)},
             "deals_per_sec": deals / (ms * 1e-3), "env_steps": env_steps, "deals": deals, "error_games": errors,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": world * n * 57,
-                    "d2h_bytes_per_step": world * (n * 8 + 256), "ms_per_step": float(e2e_ms.item()) / args.steps,
-                    "api": "tarok_rollout_host (TarokEnv.rollout_host): pinned host deals+contracts in, scores+stats out"},
+                    "d2h_bytes_per_step": world * (n * 8 + 256), "ms_per_step": e2e_ms,
+                    "api": "tarok_rollout_host (TarokEnv.rollout_host): pinned host deals+contracts in, scores+stats out; fused "
+                           "kernel behind an 8-chunk upload/compute/download pipeline",
+                    "stepwise_kernels": {"value": e2e_sw_value, "ms_per_step": e2e_sw_ms}},
             "gpu_launches": launches * world,
             "roofline": roofline, "roofline_large": big,
             "fused_rollout": {"ms_per_rollout": fused_ms, "env_steps_per_sec_per_gpu": env_steps / args.steps / world / (fused_ms * 1e-3),

@@ -13,12 +13,16 @@
 using tk::u64;
 using tk::u32;
 
+#define TK_MAX_CHUNKS 8
+
 struct tarok_env {
     int device;
     u32 flags;
     tk::Env e;
     // staging buffers of the host-buffer entry point
     uint8_t* st_perm; uint8_t* st_contract; uint8_t* st_declarer; uint8_t* st_king;
+    cudaStream_t s_up, s_down;                 // internal copy streams of the chunked host pipeline
+    cudaEvent_t ev_fork, ev_join, ev_up[TK_MAX_CHUNKS], ev_done[TK_MAX_CHUNKS];
     std::atomic<int> exports;
     u64 launches;
     char err[512];
@@ -134,6 +138,11 @@ int tarok_destroy(tarok_t* h) {
     cudaFree(h->e.hands); cudaFree(h->e.piles); cudaFree(h->e.talon); cudaFree(h->e.torder);
     cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats);
     cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard);
+    if (h->st_perm) {
+        cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down);
+        cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+        for (int c = 0; c < TK_MAX_CHUNKS; c++) { cudaEventDestroy(h->ev_up[c]); cudaEventDestroy(h->ev_done[c]); }
+    }
     cudaFree(h->st_perm); cudaFree(h->st_contract); cudaFree(h->st_declarer); cudaFree(h->st_king);
     delete h;
     return 0;
@@ -341,7 +350,7 @@ int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id
     h->e.first_gid = first_global_game_id;
     clear_hist(h, stream);
     tk::k_rollout_fused<false><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr, nullptr,
-                                                                           h->e.scores, 1);
+                                                                           h->e.scores, 1, 0ull);
     TK_LAUNCH_OK(h);
     return 0;
 }
@@ -354,22 +363,60 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
     DeviceGuard dg(h->device);
     const u64 n = h->e.n;
     if (!h->st_perm) {
+        TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+        TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+        TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        for (int c = 0; c < TK_MAX_CHUNKS; c++) {
+            TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[c], cudaEventDisableTiming));
+            TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[c], cudaEventDisableTiming));
+        }
         TK_CUDA(h, cudaMalloc((void**)&h->st_perm, h->e.n_alloc * 54));
         TK_CUDA(h, cudaMalloc((void**)&h->st_contract, h->e.n_alloc));
         TK_CUDA(h, cudaMalloc((void**)&h->st_declarer, h->e.n_alloc));
         TK_CUDA(h, cudaMalloc((void**)&h->st_king, h->e.n_alloc));
     }
     cudaStream_t s = S(stream);
-    TK_CUDA(h, cudaMemcpyAsync(h->st_perm, perm_host, n * 54, cudaMemcpyHostToDevice, s));
-    TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, s));
-    TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, s));
-    if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, s));
     TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
     h->e.first_gid = first_global_game_id;
+    if (!fused) {
+        TK_CUDA(h, cudaMemcpyAsync(h->st_perm, perm_host, n * 54, cudaMemcpyHostToDevice, s));
+        TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, s));
+        TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, s));
+        if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, s));
+    }
     if (fused) {
-        tk::k_rollout_fused<true><<<grid1(h->e.n_alloc), tk::CTA, tk::CTA * 54, s>>>(
-            h->e, 0u, h->st_perm, h->st_contract, h->st_declarer, king_host ? h->st_king : nullptr, h->e.scores, 0);
-        TK_LAUNCH_OK(h);
+        // chunked pipeline: upload chunk c+1 (copy stream) while chunk c plays (caller's stream) and chunk c-1's
+        // scores go back (download stream).  The four per-game inputs are uploaded per chunk.
+        const u64 chunk = (n >= (1ull << 18)) ? (((n + 7) / 8 + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
+        const int nchunks = (int)((n + chunk - 1) / chunk);
+        TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
+        TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));
+        TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_fork, 0));
+        for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
+            const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
+            TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * 54, perm_host + b * 54, len * 54, cudaMemcpyHostToDevice, h->s_up));
+            TK_CUDA(h, cudaMemcpyAsync(h->st_contract + b, contract_host + b, len, cudaMemcpyHostToDevice, h->s_up));
+            TK_CUDA(h, cudaMemcpyAsync(h->st_declarer + b, declarer_host + b, len, cudaMemcpyHostToDevice, h->s_up));
+            if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king + b, king_host + b, len, cudaMemcpyHostToDevice, h->s_up));
+            TK_CUDA(h, cudaEventRecord(h->ev_up[c], h->s_up));
+            TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_up[c], 0));
+            tk::Env ev = h->e;
+            ev.n = e_;
+            const unsigned grid = (unsigned)((len + tk::CTA - 1) / tk::CTA);
+            tk::k_rollout_fused<true><<<grid, tk::CTA, tk::CTA * 54, s>>>(
+                ev, 0u, h->st_perm, h->st_contract, h->st_declarer, king_host ? h->st_king : nullptr, h->e.scores, 0, b);
+            TK_LAUNCH_OK(h);
+            if (scores_host) {
+                TK_CUDA(h, cudaEventRecord(h->ev_done[c], s));
+                TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_done[c], 0));
+                TK_CUDA(h, cudaMemcpyAsync((uint64_t*)scores_host + b, h->e.scores + b, len * 8, cudaMemcpyDeviceToHost, h->s_down));
+            }
+        }
+        TK_CUDA(h, cudaEventRecord(h->ev_join, h->s_down));
+        TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+        if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
+        return 0;
     } else {
         clear_hist(h, stream);
         tk::k_set_deals<<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, h->st_perm);

@@ -499,9 +499,10 @@ __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64
 template <bool FROM_PERM>
 __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const uint8_t* __restrict__ perm,
                                                        const uint8_t* __restrict__ fc, const uint8_t* __restrict__ fd,
-                                                       const uint8_t* __restrict__ fk, u64* __restrict__ out, int write_state) {
+                                                       const uint8_t* __restrict__ fk, u64* __restrict__ out, int write_state,
+                                                       u64 g0) {
     extern __shared__ __align__(16) uint8_t shp[];
-    const u64 base = (u64)blockIdx.x * CTA;
+    const u64 base = g0 + (u64)blockIdx.x * CTA;          // g0: first game of this launch (chunked host pipeline)
     u64 g = base + threadIdx.x;
     const u64 na = e.n_alloc;
     const u64 gid = e.first_gid + g;

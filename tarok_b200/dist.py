@@ -1,0 +1,52 @@
+"""Multi-GPU: independent game shards, one collective.
+
+Games never interact, so N GPUs = N disjoint contiguous ranges of GLOBAL game ids, one process per
+GPU.  Every random draw is keyed by the global game id (Philox counter), and seat rotation depends only
+on it (Tarok.py:34), so the set of games played -- and therefore every statistic -- is identical for
+any GPU count.  The only exchange on the path is the all-reduce of the 32-entry statistics vector
+(per-player returns = ``Tarok.rezultati``, Tarok.py:59-61; contract histogram; counters) after scoring:
+``torch.distributed`` all_reduce, i.e. NCCL over NVLink on a B200 box (gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard(total_games: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous range of global game ids owned by ``rank``: (first id, count).  Ranges tile [0, total)."""
+    base, rem = divmod(int(total_games), int(world))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def allreduce_stats(stats: torch.Tensor) -> torch.Tensor:
+    """Sum the statistics vector over all ranks, in place; no-op without an initialised process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+class ShardedTarok:
+    """This rank's shard of a ``total_games`` batch on its own GPU (one process per GPU)."""
+
+    def __init__(self, total_games: int, seed: int, rank: int = 0, world: int = 1, device: int = 0):
+        from .env import TarokEnv
+
+        self.total, self.rank, self.world = int(total_games), rank, world
+        self.first, self.count = shard(total_games, rank, world)
+        self.env = TarokEnv(self.count, seed=seed, device=device)
+        self._glob = torch.zeros(32, dtype=torch.int64, device=self.env.torch_device)
+
+    def rollout(self, mode: int, batch_index: int = 0, fused: bool = False) -> torch.Tensor:
+        """Plays batch ``batch_index`` (global ids batch_index*total + [first, first+count)) and returns the
+        statistics vector summed over all ranks (device tensor, int64 [32])."""
+        self.env.reset_stats()
+        self.env.rollout(mode, first_game_id=batch_index * self.total + self.first, fused=fused)
+        self._glob.copy_(self.env.stats_dev)
+        return allreduce_stats(self._glob)
+
+    def close(self):
+        self.env.close()
