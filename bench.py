@@ -39,6 +39,11 @@ MODE_NAMES = {16: "Navadna igra (Tri/Dve/Ena forced, uniform declarer+king), tal
               18: "Bot_igralec bidding (Klop/Tri/Dve/Ena)", 0: "Klop forced"}
 
 
+def workload_name(mode, games):
+    return ("config 2: %s; 4 uniform-random legal-move players; %d concurrent deals per GPU; one step = deal, contract, "
+            "talon exchange, 48 x play_step, score" % (MODE_NAMES.get(mode, str(mode)), games))
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -136,7 +141,7 @@ def cpu_port_rate(mode, target_seconds, threads_note=True):
     """Times the C port of the reference engine (oracle/synth.c, OpenMP) on a bounded sample."""
     from oracle import oracle as O
     O.build()
-    cores = os.cpu_count() or 1
+    cores = O.use_all_threads()
     t = time.perf_counter()
     st = O.rollout_stats_only(SEED, 0, 20000, mode)
     dt = max(time.perf_counter() - t, 1e-4)
@@ -153,7 +158,7 @@ def run_reference(args, rank):
         return
     from oracle import oracle as O
     O.build()
-    cores = os.cpu_count() or 1
+    cores = O.use_all_threads()          # torchrun exports OMP_NUM_THREADS=1; the arm uses every host core
     t = time.perf_counter()
     O.rollout_stats_only(SEED, 0, 20000, args.mode)
     rate = 20000 / max(time.perf_counter() - t, 1e-4)
@@ -172,7 +177,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "config 2: %s; %d concurrent deals per GPU" % (MODE_NAMES.get(args.mode, str(args.mode)), args.games)},
+        "config": {"workload": workload_name(args.mode, args.games), "games_per_gpu": args.games, "mode": args.mode,
+                   "seed": hex(SEED)},
         "deals_per_sec": per_step * args.steps / dt,
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -195,8 +201,9 @@ def run_ours(args, rank, world, local_rank):
     n, mode, total = args.games, args.mode, args.games * world
     env = TarokEnv(n, seed=SEED, device=local_rank)
     auction = mode in (17, 18)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    stats_glob = torch.zeros(32, dtype=torch.int64, device=dev)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    stats_ring = torch.zeros((args.warmup + args.steps + 1, 32), dtype=torch.int64, device=dev)
+    pending = []
     step_events = []
 
     def rollout(i, timed):
@@ -210,9 +217,11 @@ def run_ours(args, rank, world, local_rank):
         env.step_random(48)
         b.record()
         env.score()
-        stats_glob.copy_(env.stats_dev)
+        stats_ring[i].copy_(env.stats_dev)
         if world > 1:
-            dist.all_reduce(stats_glob)       # the one collective: returns/statistics (NCCL over NVLink)
+            # the one collective: returns/statistics, 256 B over NCCL/NVLink; asynchronous so that the next
+            # rollout's deal overlaps it (waited for before the timed region closes)
+            pending.append(dist.all_reduce(stats_ring[i], async_op=True))
         if timed:
             step_events.append((a, b))
 
@@ -234,6 +243,8 @@ def run_ours(args, rank, world, local_rank):
     t0.record()
     for i in range(args.steps):
         rollout(args.warmup + i, True)
+    for w in pending:
+        w.wait()
     t1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -244,7 +255,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
     ms, step_ms = float(ms.item()), float(step_ms.item())
-    st = stats_glob.cpu().numpy()
+    st = stats_ring[args.warmup + args.steps - 1].cpu().numpy()
     launches = env.launches - launches0
     env_steps, deals, errors = int(st[S_STEPS]), int(st[S_FINISHED]), int(st[S_ERRORS])
     value = env_steps / (ms * 1e-3)
@@ -347,10 +358,9 @@ def run_ours(args, rank, world, local_rank):
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "config 2: %s; 4 uniform-random legal-move players; %d concurrent deals per GPU, stepwise "
-                                   "kernels (deal, contract, exchange, 48 x play_step, score)" % (MODE_NAMES.get(mode, str(mode)), n),
+            "config": {"workload": workload_name(mode, n),
                        "games_per_gpu": n, "mode": mode, "seed": hex(SEED),
-                       "l2": "256 MiB flush write between iterations (inside the timed region); within one iteration the 48 "
+                       "l2": "160 MiB flush write between iterations (inside the timed region); within one iteration the 48 "
                              "play_steps revisit the %d MB state as the workload prescribes" % (n * 104 >> 20)},
             "deals_per_sec": deals / (ms * 1e-3), "env_steps": env_steps, "deals": deals, "error_games": errors,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": world * n * 57,

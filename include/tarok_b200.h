@@ -78,6 +78,9 @@ enum { TAROK_F_HANDS = 0,   /* uint64 [4, n_alloc]  hand bitboard of seat s     
 int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, tarok_t** out);
 int tarok_destroy(tarok_t* h);                 /* error if exported tensors are still alive */
 const char* tarok_last_error(const tarok_t* h);/* h may be NULL: last error of a failed tarok_create */
+/* Tuning knobs.  TAROK_OPT_STEP_IMPL: 0 auto (default), 1 plain play_step kernel, 2 persistent TMA-staged kernel. */
+#define TAROK_OPT_STEP_IMPL 1
+int tarok_set_option(tarok_t* h, int option, int64_t value);
 uint64_t tarok_n_games(const tarok_t* h);
 uint64_t tarok_n_alloc(const tarok_t* h);      /* n_games rounded up to the kernel tile */
 

@@ -147,3 +147,13 @@ def rollout_stats_only(seed, first_gid, n, mode):
         C.c_uint64(seed), C.c_uint64(first_gid), C.c_int64(n), C.c_int(mode),
         None, None, None, None, None, None, None, None, None, None, _p(stats))
     return stats
+
+
+def use_all_threads():
+    """OpenMP over every core this process may run on (torchrun exports OMP_NUM_THREADS=1); returns the count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().syn_set_threads(C.c_int(n))
+    return int(lib().syn_max_threads())

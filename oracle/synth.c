@@ -225,3 +225,13 @@ void syn_deal_batch(uint64_t seed, uint64_t first_gid, int64_t n, uint8_t* out_p
 }
 
 void syn_philox_kat(uint32_t c[4], uint32_t k0, uint32_t k1) { syn_philox4x32_10(c, k0, k1); }
+
+/* thread control for the CPU-baseline legs (torchrun exports OMP_NUM_THREADS=1) */
+#ifdef _OPENMP
+#include <omp.h>
+void syn_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int syn_max_threads(void) { return omp_get_max_threads(); }
+#else
+void syn_set_threads(int n) { (void)n; }
+int syn_max_threads(void) { return 1; }
+#endif

@@ -18,6 +18,7 @@ SIGNATURES = {
     "tarok_create": (_I, [_I, _U64, _U64, _U32, C.POINTER(_VP)]),
     "tarok_destroy": (_I, [_VP]),
     "tarok_last_error": (C.c_char_p, [_VP]),
+    "tarok_set_option": (_I, [_VP, _I, C.c_int64]),
     "tarok_n_games": (_U64, [_VP]),
     "tarok_n_alloc": (_U64, [_VP]),
     "tarok_deal": (_I, [_VP, _U64, _VP]),

@@ -7,6 +7,11 @@
 // Stateless: any (game, stream, index) can be regenerated anywhere, so results do not depend on how
 // games are sharded over GPUs.  The reference has no seeds at all; parity is by
 // exporting the deal/actions and replaying them through the oracle.
+//
+// Issue-slot notes (B200: the integer ALU pipe retires one warp instruction every 2 cycles per SM
+// sub-partition and is what bounds the step kernel): the ten round keys depend only on the seed, so the
+// host precomputes them into the kernel parameters (constant bank operands, no per-lane adds), and the
+// 32x32 multiplies are written as mul.hi/mul.lo so they land on the FMA pipe.
 #pragma once
 #include <cstdint>
 
@@ -15,26 +20,39 @@ namespace tk {
 using u64 = unsigned long long;
 using u32 = unsigned int;
 
-enum : u32 { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5 };
+enum : u32 { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5, ST_PLAY_RETRY = 6 };
 
-__device__ __forceinline__ void philox4x32_10(u32& c0, u32& c1, u32& c2, u32& c3, u32 k0, u32 k1) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        u64 p0 = (u64)0xD2511F53u * c0;
-        u64 p1 = (u64)0xCD9E8D57u * c2;
-        u32 n0 = (u32)(p1 >> 32) ^ c1 ^ k0;
-        u32 n2 = (u32)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (u32)p1; c3 = (u32)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+constexpr u32 PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u, PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+// Seed + the 10 round keys (k0 + r*W0, k1 + r*W1); filled on the host (philox_keys_init).
+struct Rng {
+    u64 seed;
+    u32 rk[20];
+};
+
+inline void philox_keys_init(Rng& r, u64 seed) {
+    r.seed = seed;
+    u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+    for (int i = 0; i < 10; i++) {
+        r.rk[2 * i] = k0; r.rk[2 * i + 1] = k1;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
     }
 }
 
 struct Words4 { u32 w[4]; };
 
-__device__ __forceinline__ Words4 philox_block(u64 seed, u64 gid, u32 stream_attempt, u32 block) {
+__device__ __forceinline__ Words4 philox_block(const Rng& rng, u64 ctr01, u32 stream_attempt, u32 block) {
+    u32 c0 = (u32)ctr01, c1 = (u32)(ctr01 >> 32), c2 = stream_attempt, c3 = block;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const u32 hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const u32 hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ rng.rk[2 * r];
+        c2 = hi0 ^ c3 ^ rng.rk[2 * r + 1];
+        c1 = lo1; c3 = lo0;
+    }
     Words4 o;
-    o.w[0] = (u32)gid; o.w[1] = (u32)(gid >> 32); o.w[2] = stream_attempt; o.w[3] = block;
-    philox4x32_10(o.w[0], o.w[1], o.w[2], o.w[3], (u32)seed, (u32)(seed >> 32));
+    o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
     return o;
 }
 
@@ -48,31 +66,36 @@ __device__ __forceinline__ bool lemire(u32 x, u32 n, u32& out) {
     return lo >= t;
 }
 
-// Cold path: redraw with attempt = first, first+1, ... until accepted.
+// Cold path (never inlined): redraw with attempt = first, first+1, ... until accepted.  Bumps the key itself.
 __device__ __noinline__ u32 draw_loop(u64 seed, u64 gid, u32 stream, u32 idx, u32 n, u32 first) {
     for (u32 attempt = first;; attempt++) {
-        Words4 b = philox_block(seed, gid, stream | (attempt << 16), idx >> 2);
+        u32 c0 = (u32)gid, c1 = (u32)(gid >> 32), c2 = stream | (attempt << 16), c3 = idx >> 2;
+        u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+        for (int r = 0; r < 10; r++) {
+            const u32 hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+            const u32 hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+            c0 = hi1 ^ c1 ^ k0; c2 = hi0 ^ c3 ^ k1; c1 = lo1; c3 = lo0;
+            k0 += PHILOX_W0; k1 += PHILOX_W1;
+        }
+        const u32 k = idx & 3u;
+        const u32 x = k == 0 ? c0 : k == 1 ? c1 : k == 2 ? c2 : c3;
         u32 r;
-        u32 x = (idx & 3u) == 0 ? b.w[0] : (idx & 3u) == 1 ? b.w[1] : (idx & 3u) == 2 ? b.w[2] : b.w[3];
         if (lemire(x, n, r)) return r;
     }
 }
 
-__device__ __forceinline__ u32 draw_retry(u64 seed, u64 gid, u32 stream, u32 idx, u32 n) { return draw_loop(seed, gid, stream, idx, n, 1u); }
-__device__ __forceinline__ u32 draw_retry0(u64 seed, u64 gid, u32 stream, u32 idx, u32 n) { return draw_loop(seed, gid, stream, idx, n, 0u); }
-
-__device__ __forceinline__ u32 draw_from_word(u32 x, u64 seed, u64 gid, u32 stream, u32 idx, u32 n) {
+__device__ __forceinline__ u32 draw_from_word(u32 x, const Rng& rng, u64 gid, u32 stream, u32 idx, u32 n) {
     u32 r;
-    if (__builtin_expect(!lemire(x, n, r), 0)) r = draw_retry(seed, gid, stream, idx, n);
+    if (__builtin_expect(!lemire(x, n, r), 0)) r = draw_loop(rng.seed, gid, stream, idx, n, 1u);
     return r;
 }
 
 // One-off draw (computes its own Philox block).
-__device__ __forceinline__ u32 draw(u64 seed, u64 gid, u32 stream, u32 idx, u32 n) {
-    Words4 b = philox_block(seed, gid, stream, idx >> 2);
-    u32 k = idx & 3u;
-    u32 x = k == 0 ? b.w[0] : k == 1 ? b.w[1] : k == 2 ? b.w[2] : b.w[3];
-    return draw_from_word(x, seed, gid, stream, idx, n);
+__device__ __forceinline__ u32 draw(const Rng& rng, u64 gid, u32 stream, u32 idx, u32 n) {
+    Words4 b = philox_block(rng, gid, stream, idx >> 2);
+    const u32 k = idx & 3u;
+    const u32 x = k == 0 ? b.w[0] : k == 1 ? b.w[1] : k == 2 ? b.w[2] : b.w[3];
+    return draw_from_word(x, rng, gid, stream, idx, n);
 }
 
 // ---- play draws -------------------------------------------------------------------------------------
@@ -82,20 +105,20 @@ __device__ __forceinline__ u32 draw(u64 seed, u64 gid, u32 stream, u32 idx, u32 
 // The stepwise kernel (one lane = one game pair) therefore needs ONE block per lane per step, the fused
 // kernel (one lane = one game) one block per trick.  16-bit Lemire with rejection keeps the draw exactly
 // uniform; the rejected sliver (probability < n / 65536) falls back to a 32-bit draw on stream ST_PLAY_RETRY.
-enum : u32 { ST_PLAY_RETRY = 6 };
-
-__device__ __forceinline__ Words4 play_block(u64 seed, u64 gid, u32 trick) {
-    return philox_block(seed, gid >> 1, ST_PLAY, trick);
+__device__ __forceinline__ Words4 play_block(const Rng& rng, u64 gid, u32 trick) {
+    return philox_block(rng, gid >> 1, ST_PLAY, trick);
 }
 
-__device__ __forceinline__ u32 play_draw(const Words4& b, u64 seed, u64 gid, u32 t, u32 n) {
-    u32 lane = ((u32)gid & 1u) * 4u + (t & 3u);
-    u32 w = (lane >> 1) == 0 ? b.w[0] : (lane >> 1) == 1 ? b.w[1] : (lane >> 1) == 2 ? b.w[2] : b.w[3];
-    u32 x = (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
-    u32 m = x * n;
-    u32 lo = m & 0xFFFFu;
+__device__ __forceinline__ u32 play_draw(const Words4& b, const Rng& rng, u64 gid, u32 t, u32 n) {
+    const u32 lane = ((u32)gid & 1u) * 4u + (t & 3u);
+    const u32 w = (lane >> 1) == 0 ? b.w[0] : (lane >> 1) == 1 ? b.w[1] : (lane >> 1) == 2 ? b.w[2] : b.w[3];
+    const u32 x = (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
+    const u32 m = x * n;
+    const u32 lo = m & 0xFFFFu;
     if (__builtin_expect(lo < n, 0)) {
-        if (lo < (65536u % n)) return draw_retry0(seed, gid, ST_PLAY_RETRY, t, n);
+        // 65536 % n for n = 0..15, four bits each (n <= 12 on this path)
+        const u32 rem = (u32)((0x1234967024101000ull >> (4u * (n & 15u))) & 15ull);
+        if (lo < rem) return draw_loop(rng.seed, gid, ST_PLAY_RETRY, t, n, 0u);
     }
     return m >> 16;
 }

@@ -17,6 +17,8 @@ using tk::u32;
 
 struct tarok_env {
     int device;
+    int sm_count;
+    int step_impl;                             // 0 auto, 1 plain k_step, 2 persistent TMA-staged k_step_tma
     u32 flags;
     tk::Env e;
     // staging buffers of the host-buffer entry point
@@ -66,7 +68,26 @@ struct DeviceGuard {
     ~DeviceGuard() { if (ok) cudaSetDevice(prev); }
 };
 
+// play_step launcher: persistent TMA-staged kernel (one CTA per resident slot, 4 per SM) once the batch has
+// more tiles than resident CTAs; the plain one-tile-per-CTA kernel for small batches.
+template <bool RANDOM>
+static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
+    const unsigned tiles = grid2(h->e.n_alloc);
+    const unsigned resident = (unsigned)h->sm_count * 4u;
+    // measured on B200 (tools/step_ab.py, profiles/r01): the kernel is bound by integer-ALU issue, not by load
+    // latency, so the plain kernel wins; "auto" therefore picks it and the staged one stays selectable.
+    const bool tma = h->step_impl == 2;
+    if (tma) tk::k_step_tma<RANDOM><<<tiles < resident ? tiles : resident, tk::CTA, 0, s>>>(h->e, action);
+    else tk::k_step<RANDOM><<<tiles, tk::CTA, 0, s>>>(h->e, action);
+}
+
 extern "C" {
+
+int tarok_set_option(tarok_t* h, int option, int64_t value) {
+    TK_CHECK_HANDLE(h);
+    if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 2) { h->step_impl = (int)value; return 0; }
+    return fail(h, -1, "unknown option %d / value %lld", option, (long long)value);
+}
 
 int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, tarok_t** out) {
     if (!out) return fail(nullptr, -1, "out is null");
@@ -85,10 +106,11 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     tarok_env* h = new (std::nothrow) tarok_env();
     if (!h) return fail(nullptr, -4, "out of host memory");
     memset(&h->e, 0, sizeof(h->e));
-    h->device = device; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
+    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
-    h->e.n = n_games; h->e.n_alloc = na; h->e.seed = seed; h->e.first_gid = 0;
+    h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;
+    tk::philox_keys_init(h->e.rng, seed);
 #define TK_ALLOC(ptr, bytes)                                                       \
     do {                                                                           \
         cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                      \
@@ -265,7 +287,7 @@ int tarok_step(tarok_t* h, const uint8_t* card_dev, void* stream) {
     if (!card_dev) return fail(h, -1, "card_dev is null");
     if (((uintptr_t)card_dev) & 1u) return fail(h, -1, "card_dev must be 2-byte aligned");
     DeviceGuard dg(h->device);
-    tk::k_step<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, card_dev);
+    launch_step<false>(h, card_dev, S(stream));
     TK_LAUNCH_OK(h);
     return 0;
 }
@@ -273,7 +295,7 @@ int tarok_step(tarok_t* h, const uint8_t* card_dev, void* stream) {
 int tarok_step_random(tarok_t* h, void* stream) {
     TK_CHECK_HANDLE(h);
     DeviceGuard dg(h->device);
-    tk::k_step<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, nullptr);
+    launch_step<true>(h, nullptr, S(stream));
     TK_LAUNCH_OK(h);
     return 0;
 }
@@ -282,7 +304,7 @@ int tarok_steps_random(tarok_t* h, uint32_t count, void* stream) {
     TK_CHECK_HANDLE(h);
     DeviceGuard dg(h->device);
     for (uint32_t t = 0; t < count; t++) {
-        tk::k_step<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, nullptr);
+        launch_step<true>(h, nullptr, S(stream));
         TK_LAUNCH_OK(h);
     }
     return 0;
@@ -323,7 +345,7 @@ static int play_out_stepwise(tarok_t* h, uint32_t random_group, void* stream) {
     tk::k_exchange<true><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, random_group, nullptr, nullptr);
     TK_LAUNCH_OK(h);
     for (int t = 0; t < 48; t++) {
-        tk::k_step<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, nullptr);
+        launch_step<true>(h, nullptr, S(stream));
         TK_LAUNCH_OK(h);
     }
     tk::k_score<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);

@@ -22,7 +22,8 @@ constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane 
 struct Env {
     u64* hands; u64* piles; u64* talon; u64* torder; u64* meta; u64* mask; u64* scores;
     uint8_t* hist; u64* hands0; u64* discard; long long* stats;
-    u64 n, n_alloc, seed, first_gid;
+    u64 n, n_alloc, first_gid;
+    Rng rng;                               // seed + precomputed Philox round keys
 };
 
 enum : int { S_SEAT = 0, S_PLAYER = 4, S_CONTRACT = 8, S_FINISHED = 18, S_STEPS = 19, S_ERRORS = 20, S_USED = 21, S_ERR_EVENTS = 21 };
@@ -118,18 +119,18 @@ __device__ __forceinline__ u64 order_from_lehmer(u64 talon, u32 L) {
     return order;
 }
 
-__device__ __forceinline__ Dealt deal_philox(u64 seed, u64 gid) {
+__device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
     Dealt d = {0, 0, 0, 0, 0, 0};
     u32 c0 = 12, c1 = 12, c2 = 12, c3 = 12;
     u32 L = 0;
 #pragma unroll
     for (int blk = 0; blk < 14; blk++) {
-        Words4 b = philox_block(seed, gid, ST_DEAL, (u32)blk);
+        Words4 b = philox_block(rng, gid, ST_DEAL, (u32)blk);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int c = blk * 4 + j;
             if (c < 54) {
-                u32 r = draw_from_word(b.w[j], seed, gid, ST_DEAL, (u32)c, (u32)(54 - c));
+                u32 r = draw_from_word(b.w[j], rng, gid, ST_DEAL, (u32)c, (u32)(54 - c));
                 u32 a0 = c0, a1 = a0 + c1, a2 = a1 + c2, a3 = a2 + c3;
                 const u64 bit = 1ull << c;
                 bool p0 = r < a0, p1 = !p0 && r < a1, p2 = r >= a1 && r < a2, p3 = r >= a2 && r < a3, p4 = r >= a3;
@@ -139,7 +140,7 @@ __device__ __forceinline__ Dealt deal_philox(u64 seed, u64 gid) {
                 d.h3 |= p3 ? bit : 0ull; c3 -= p3 ? 1u : 0u;
                 d.talon |= p4 ? bit : 0ull;
             } else if (c == 54) {
-                L = draw_from_word(b.w[j], seed, gid, ST_DEAL, 54u, 720u);
+                L = draw_from_word(b.w[j], rng, gid, ST_DEAL, 54u, 720u);
             }
         }
     }
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(CTA) k_deal(Env e) {
     const u64 na = e.n_alloc;
     Dealt d = {0, 0, 0, 0, 0, 0};
     u64 meta = meta_pad();
-    if (g < e.n) { d = deal_philox(e.seed, e.first_gid + g); meta = meta_fresh(); }
+    if (g < e.n) { d = deal_philox(e.rng, e.first_gid + g); meta = meta_fresh(); }
     e.hands[g] = d.h0; e.hands[na + g] = d.h1; e.hands[2 * na + g] = d.h2; e.hands[3 * na + g] = d.h3;
     e.piles[g] = 0; e.piles[na + g] = 0; e.piles[2 * na + g] = 0; e.piles[3 * na + g] = 0;
     e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = 0;
@@ -245,14 +246,14 @@ enum : int { SRC_FORCED = 0, SRC_INTENTS = 1, SRC_SYNTH = 2 };
 
 struct WantFixed { int tip[4]; __device__ int operator()(int seat, int) const {
     return seat == 0 ? tip[0] : seat == 1 ? tip[1] : seat == 2 ? tip[2] : tip[3]; } };
-struct WantBot { u64 seed, gid; __device__ int operator()(int, int call) const {
+struct WantBot { const Rng& rng; u64 gid; __device__ int operator()(int, int call) const {
     // np.random.choice([Naprej,Tri,Dve,Ena], p=[.5,1/6,1/6,1/6]) at EVERY call (Igralec.py:151)
-    u32 u = draw(seed, gid, ST_BID, (u32)call, 6u);
+    u32 u = draw(rng, gid, ST_BID, (u32)call, 6u);
     return u < 3u ? (int)C_NAPREJ : (int)(C_TRI + (u - 3u)); } };
 
 // Resolves (contract, declarer, king) for one game from the chosen source.
 template <int SRC>
-__device__ __forceinline__ void resolve_contract(u64 seed, u64 gid, u32 mode, const uint8_t* a, const uint8_t* b,
+__device__ __forceinline__ void resolve_contract(const Rng& rng, u64 gid, u32 mode, const uint8_t* a, const uint8_t* b,
                                                  const uint8_t* c, u64 g, u32& contract, u32& declarer, u32& king) {
     if (SRC == SRC_FORCED) {
         contract = a[g]; declarer = b[g]; king = c ? c[g] : NO_KING;
@@ -268,25 +269,25 @@ __device__ __forceinline__ void resolve_contract(u64 seed, u64 gid, u32 mode, co
         king = d == 0 ? su[0] : d == 1 ? su[1] : d == 2 ? su[2] : su[3];
     } else {
         if (mode == 17u) {          // TAROK_MODE_AUCTION_UNIFORM
-            Words4 blk = philox_block(seed, gid, ST_BID, 0u);
+            Words4 blk = philox_block(rng, gid, ST_BID, 0u);
             WantFixed w; u32 su[4];
 #pragma unroll
-            for (int s = 0; s < 4; s++) index2igra(draw_from_word(blk.w[s], seed, gid, ST_BID, (u32)s, 18u), w.tip[s], su[s]);
+            for (int s = 0; s < 4; s++) index2igra(draw_from_word(blk.w[s], rng, gid, ST_BID, (u32)s, 18u), w.tip[s], su[s]);
             int d, k;
             licitacija<true>(w, d, k);
             contract = (u32)k; declarer = (u32)d;
             king = d == 0 ? su[0] : d == 1 ? su[1] : d == 2 ? su[2] : su[3];
         } else if (mode == 18u) {   // TAROK_MODE_AUCTION_BOT
-            WantBot w{seed, gid};
+            WantBot w{rng, gid};
             int d, k;
             licitacija<false>(w, d, k);
             contract = (u32)k; declarer = (u32)d;
-            king = is_king_game(contract) ? draw(seed, gid, ST_KING, 0u, 4u) : NO_KING;   // Igralec.py:155-156
+            king = is_king_game(contract) ? draw(rng, gid, ST_KING, 0u, 4u) : NO_KING;   // Igralec.py:155-156
         } else {
-            Words4 blk = philox_block(seed, gid, ST_FORCE, 0u);
-            contract = mode == 16u ? C_TRI + draw_from_word(blk.w[0], seed, gid, ST_FORCE, 0u, 3u) : mode;
-            declarer = contract == C_KLOP ? 0u : draw_from_word(blk.w[1], seed, gid, ST_FORCE, 1u, 4u);
-            king = is_king_game(contract) ? draw(seed, gid, ST_KING, 0u, 4u) : NO_KING;
+            Words4 blk = philox_block(rng, gid, ST_FORCE, 0u);
+            contract = mode == 16u ? C_TRI + draw_from_word(blk.w[0], rng, gid, ST_FORCE, 0u, 3u) : mode;
+            declarer = contract == C_KLOP ? 0u : draw_from_word(blk.w[1], rng, gid, ST_FORCE, 1u, 4u);
+            king = is_king_game(contract) ? draw(rng, gid, ST_KING, 0u, 4u) : NO_KING;
         }
     }
 }
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(CTA) k_begin(Env e, u32 mode, const uint8_t* _
     const u64 na = e.n_alloc;
     u64 h0 = e.hands[g], h1 = e.hands[na + g], h2 = e.hands[2 * na + g], h3 = e.hands[3 * na + g];
     u32 contract, declarer, king;
-    resolve_contract<SRC>(e.seed, e.first_gid + g, mode, a, b, c, g, contract, declarer, king);
+    resolve_contract<SRC>(e.rng, e.first_gid + g, mode, a, b, c, g, contract, declarer, king);
     meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
     if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
     e.meta[g] = meta;
@@ -314,21 +315,21 @@ __global__ void __launch_bounds__(CTA) k_begin(Env e, u32 mode, const uint8_t* _
 // ------------------------------------------------------------------------------------------------
 // Returns false (error) if the action is invalid or fewer than k cards can be laid down (Q19).
 template <bool SYNTH>
-__device__ __forceinline__ bool exchange_game(u64 seed, u64 gid, u32 random_group, u64& meta, u64& hand, u64& pile,
+__device__ __forceinline__ bool exchange_game(const Rng& rng, u64 gid, u32 random_group, u64& meta, u64& hand, u64& pile,
                                               u64& talon, u64 order, u32 group, u64 discard, u64& discard_out) {
     u32 contract = mget(meta, M_CONTRACT, 4);
     u32 k = talon_k(contract);
     u32 ngroups = 6u / k;
     if (SYNTH) {
-        Words4 blk = philox_block(seed, gid, ST_EXCH, 0u);
-        group = random_group ? draw_from_word(blk.w[0], seed, gid, ST_EXCH, 0u, ngroups) : 0u;   // Bot: group 0 (Igralec.py:162)
+        Words4 blk = philox_block(rng, gid, ST_EXCH, 0u);
+        group = random_group ? draw_from_word(blk.w[0], rng, gid, ST_EXCH, 0u, ngroups) : 0u;   // Bot: group 0 (Igralec.py:162)
         u64 gb = talon_group_bits(order, k, group);
         u64 avail = (hand | gb) & DISCARDABLE;
         if ((u32)__popcll(avail) < k) return false;
         discard = 0;
         for (u32 j = 0; j < k; j++) {               // uniform k-subset = random.sample (Igralec.py:166)
             u32 wj = j == 0 ? blk.w[1] : j == 1 ? blk.w[2] : blk.w[3];
-            u32 r = draw_from_word(wj, seed, gid, ST_EXCH, 1u + j, (u32)__popcll(avail));
+            u32 r = draw_from_word(wj, rng, gid, ST_EXCH, 1u + j, (u32)__popcll(avail));
             u64 bit = 1ull << nth_set_bit(avail, r);
             avail ^= bit; discard |= bit;
         }
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
     u64 hand = sel4(h0, h1, h2, h3, decl);
     u64 pile = e.piles[decl * na + g];
     u64 talon = e.talon[g], order = e.torder[g], dout = 0;
-    bool ok = exchange_game<SYNTH>(e.seed, e.first_gid + g, random_group, meta, hand, pile, talon, order,
+    bool ok = exchange_game<SYNTH>(e.rng, e.first_gid + g, random_group, meta, hand, pile, talon, order,
                                    SYNTH ? 0u : (u32)group[g], SYNTH ? 0ull : discard[g], dout);
     if (!ok) {
         meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
@@ -382,22 +383,35 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
 // Algorithmic traffic per env-step: R meta 8 + hands 16 + action 1, W hand 8 + meta 8
 // + mask 8, per trick /4: pile RW 16 (+ Klop talon) = 64 B.
 // ------------------------------------------------------------------------------------------------
-template <bool RANDOM>
-__device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, u64 h0, u64 h1, u64 h2, u64 h3, u32 card,
+// Where a lane finds the four hands of its game: registers (plain kernel) or the TMA-staged tile in shared
+// memory, where picking the mover's hand is ONE indexed 64-bit LDS instead of a select chain.
+struct RegHands {
+    u64 h0, h1, h2, h3;
+    __device__ __forceinline__ u64 get(u32 seat) const { return sel4(h0, h1, h2, h3, seat); }
+};
+struct SmemHands {
+    const u64* base;                       // &stage.hands[0][game]; seat stride = TILE words
+    __device__ __forceinline__ u64 get(u32 seat) const { return base[seat * TILE]; }
+};
+
+template <bool RANDOM, class Hands>
+__device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, const Hands& hands, u32 card,
                                           const Words4& rnd, u64& next_mask) {
     const u64 na = e.n_alloc;
+    const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 mover = mover_of(meta);
-    u64 hand = sel4(h0, h1, h2, h3, mover);
-    const u32 contract = mget(meta, M_CONTRACT, 4);
-    const u32 plays = mget(meta, M_PLAYS, 6);
+    u64 hand = hands.get(mover);
+    const u32 contract = lo & 15u;
+    const u32 pos = (lo >> M_POS) & 3u;
+    const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
     u64 talon = 0, order = 0;
-    if (contract == C_KLOP && mget(meta, M_POS, 2) == 3 && mget(meta, M_TRICKS, 4) < 6) {
+    if (contract == C_KLOP && pos == 3 && ((lo >> M_TRICKS) & 15u) < 6) {
         talon = e.talon[g]; order = e.torder[g];
     }
     if (RANDOM) {
-        u64 legal = legal_moves(hand, mget(meta, M_POS, 2) != 0, mget(meta, M_TRICK, 6), klop_rules(contract));
+        u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));
         u32 n = (u32)__popcll(legal);
-        card = nth_set_bit(legal, play_draw(rnd, e.seed, e.first_gid + g, plays, n));
+        card = nth_set_bit(legal, play_draw(rnd, e.rng, e.first_gid + g, plays, n));
     }
     PlayResult pr;
     meta = play_card<!RANDOM>(meta, hand, card, talon, order, pr);
@@ -414,7 +428,7 @@ __device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, u64 h0
         if (pr.talon_clear) e.talon[g] = talon & ~pr.talon_clear;
     }
     const u32 nx = mover_of(meta);
-    next_mask = mask_for_mover(meta, nx == mover ? hand : sel4(h0, h1, h2, h3, nx));
+    next_mask = mask_for_mover(meta, nx == mover ? hand : hands.get(nx));
 }
 
 template <bool RANDOM>
@@ -428,22 +442,107 @@ __global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restric
                h3 = ld2(e.hands + 3 * na + g);
     u32 act = 0;
     if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
-    const bool a0 = mget(m.x, M_PHASE, 2) == PH_PLAY, a1 = mget(m.y, M_PHASE, 2) == PH_PLAY;
+    const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
     if (!a0 && !a1) return;
     Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
     if (RANDOM) {
         // one Philox block serves both games of the lane (same pair, same trick) in the common case
         const u64 gid = e.first_gid + g;
-        const u32 t0 = mget(m.x, M_PLAYS, 6) >> 2, t1 = mget(m.y, M_PLAYS, 6) >> 2;
-        r0 = play_block(e.seed, gid, t0);
+        const u32 t0 = ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u, t1 = ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u;
+        r0 = play_block(e.rng, gid, t0);
         r1 = r0;
-        if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.seed, gid + 1, t1);
+        if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
     }
     u64 k0 = 0, k1 = 0;
-    if (a0) step_game<RANDOM>(e, g, m.x, h0.x, h1.x, h2.x, h3.x, act & 0xFFu, r0, k0);
-    if (a1) step_game<RANDOM>(e, g + 1, m.y, h0.y, h1.y, h2.y, h3.y, act >> 8, r1, k1);
+    if (a0) step_game<RANDOM>(e, g, m.x, RegHands{h0.x, h1.x, h2.x, h3.x}, act & 0xFFu, r0, k0);
+    if (a1) step_game<RANDOM>(e, g + 1, m.y, RegHands{h0.y, h1.y, h2.y, h3.y}, act >> 8, r1, k1);
     st2(e.meta + g, m.x, m.y);
     st2(e.mask + g, k0, k1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// play_step, persistent + TMA-staged variant (the one the library launches for large batches).
+// One CTA per resident slot (4 per SM) loops over 512-game tiles.  The five read-only streams of a tile
+// (meta + 4 hands = 5 x 4 KB) are fetched by ONE elected lane with 1-D bulk async copies
+// (cp.async.bulk.shared.global -> UBLKCP) that complete on an mbarrier; two stages are in flight, so the
+// copy of tile i+1 overlaps the integer work on tile i and the global-load latency leaves the critical
+// path.  Lanes read their game pair from shared memory with conflict-free 128-bit LDS.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    u32 done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+struct __align__(128) StepStage { u64 meta[TILE]; u64 hands[4][TILE]; };
+constexpr u32 STEP_STAGE_BYTES = 5u * TILE * 8u;
+
+template <bool RANDOM>
+__global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __restrict__ action) {
+    __shared__ StepStage stage[2];
+    __shared__ __align__(8) u64 full[2];
+    const u64 na = e.n_alloc;
+    const u32 tiles = (u32)(na / TILE);
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto fetch = [&](u32 tile, u32 s) {               // elected lane: arm the barrier, issue the 5 bulk copies
+        const u64 g0 = (u64)tile * TILE;
+        mbar_arrive_expect_tx(&full[s], STEP_STAGE_BYTES);
+        bulk_load(stage[s].meta, e.meta + g0, TILE * 8, &full[s]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) bulk_load(stage[s].hands[k], e.hands + k * na + g0, TILE * 8, &full[s]);
+    };
+    u32 tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < tiles) fetch(tile, 0);
+    const u32 l = threadIdx.x * 2;
+    for (u32 it = 0; tile < tiles; it++, tile += gridDim.x) {
+        const u32 s = it & 1u;
+        if (threadIdx.x == 0 && tile + gridDim.x < tiles) fetch(tile + gridDim.x, s ^ 1u);
+        const u64 g = (u64)tile * TILE + l;
+        u32 act = 0;
+        if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
+        mbar_wait(&full[s], (it >> 1) & 1u);
+        ulonglong2 m = *reinterpret_cast<const ulonglong2*>(&stage[s].meta[l]);
+        const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
+        if (a0 || a1) {
+            Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
+            if (RANDOM) {
+                const u64 gid = e.first_gid + g;
+                const u32 t0 = ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u, t1 = ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u;
+                r0 = play_block(e.rng, gid, t0);
+                r1 = r0;
+                if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
+            }
+            u64 k0 = 0, k1 = 0;
+            if (a0) step_game<RANDOM>(e, g, m.x, SmemHands{&stage[s].hands[0][l]}, act & 0xFFu, r0, k0);
+            if (a1) step_game<RANDOM>(e, g + 1, m.y, SmemHands{&stage[s].hands[0][l + 1]}, act >> 8, r1, k1);
+            st2(e.meta + g, m.x, m.y);
+            st2(e.mask + g, k0, k1);
+        }
+        __syncthreads();                              // stage s may be refilled from the next iteration on
+    }
 }
 
 // Standalone legal mask, recomputed from hands + meta (24 B/env-step algorithmic).
@@ -523,20 +622,20 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         Dealt d;
         bool ok = true;
         if (FROM_PERM) d = deal_from_perm(shp + threadIdx.x * 54, ok);
-        else d = deal_philox(e.seed, gid);
+        else d = deal_philox(e.rng, gid);
         h0 = d.h0; h1 = d.h1; h2 = d.h2; h3 = d.h3; talon = d.talon; order = d.order;
         meta = meta_fresh();
         if (!ok) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
         else {
             u32 contract, declarer, king;
-            if (fc) resolve_contract<SRC_FORCED>(e.seed, gid, mode, fc, fd, fk, g, contract, declarer, king);
-            else resolve_contract<SRC_SYNTH>(e.seed, gid, mode, nullptr, nullptr, nullptr, g, contract, declarer, king);
+            if (fc) resolve_contract<SRC_FORCED>(e.rng, gid, mode, fc, fd, fk, g, contract, declarer, king);
+            else resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, contract, declarer, king);
             meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
         }
         if (mget(meta, M_PHASE, 2) == PH_EXCHANGE) {
             u32 decl = mget(meta, M_DECL, 2);
             u64 hand = sel4(h0, h1, h2, h3, decl), pile = 0, dout;
-            bool ok2 = exchange_game<true>(e.seed, gid, mode == 17u, meta, hand, pile, talon, order, 0u, 0ull, dout);
+            bool ok2 = exchange_game<true>(e.rng, gid, mode == 17u, meta, hand, pile, talon, order, 0u, 0ull, dout);
             if (!ok2) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
             else {
                 h0 = decl == 0 ? hand : h0; h1 = decl == 1 ? hand : h1; h2 = decl == 2 ? hand : h2; h3 = decl == 3 ? hand : h3;
@@ -546,14 +645,14 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         const u32 contract = mget(meta, M_CONTRACT, 4);
         const bool klop = klop_rules(contract);
         for (u32 trick = 0; trick < 12 && mget(meta, M_PHASE, 2) == PH_PLAY; trick++) {
-            Words4 blk = play_block(e.seed, gid, trick);                // 4 plays = half of one Philox block
+            Words4 blk = play_block(e.rng, gid, trick);                // 4 plays = half of one Philox block
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 u32 mover = mover_of(meta);
                 u64 hand = sel4(h0, h1, h2, h3, mover);
                 u64 legal = legal_moves(hand, j != 0, mget(meta, M_TRICK, 6), klop);
                 u32 n = (u32)__popcll(legal);
-                u32 card = nth_set_bit(legal, play_draw(blk, e.seed, gid, trick * 4 + j, n));
+                u32 card = nth_set_bit(legal, play_draw(blk, e.rng, gid, trick * 4 + j, n));
                 PlayResult pr;
                 meta = play_card<false>(meta, hand, card, talon, order, pr);
                 if (e.hist && write_state) e.hist[(u64)(trick * 4 + j) * na + g] = (uint8_t)((mover << 6) | card);

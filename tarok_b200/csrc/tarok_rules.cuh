@@ -41,15 +41,15 @@ __device__ __forceinline__ u32 talon_k(u32 c) {
 }
 
 // ---- meta word layout -----------------------------------------------------------------------
-//  0-3  contract code (15 = none)     4-5  declarer          6-8  king suit (7 = none)
-//  9-12 ekipa (team) seat mask        13-14 leader (zacne)   15-16 pos = cards in current trick
-//  17-20 tricks completed             21-44 trick cards, 6 bits each, play order
-//  45-46 phase 0 dealt 1 await-exchange 2 playing 3 finished     47 error
-//  48-50 chosen talon group (7 none)  51-52 last trick winner    53 trick-just-completed
-//  54-59 plays made (0..48)           60 scored
+// Fields never straddle the 32-bit halves, so every update is 32-bit integer work.
+//  low word : 0-3 contract code (15 = none)   4-5 declarer   6-8 king suit (7 = none)   9-12 ekipa seat mask
+//             13-14 leader (zacne)   15-16 pos = cards in the current trick   17-20 tricks completed
+//             21-22 last trick winner   23 trick-just-completed   24-25 phase (0 dealt 1 await-exchange
+//             2 playing 3 finished)   26 error   27-29 chosen talon group (7 none)
+//  high word: 32-55 trick cards, 6 bits each, play order   56-61 plays made (0..48)   62 scored/pad
 constexpr int M_CONTRACT = 0, M_DECL = 4, M_KING = 6, M_TEAM = 9, M_LEADER = 13, M_POS = 15,
-              M_TRICKS = 17, M_TRICK = 21, M_PHASE = 45, M_ERR = 47, M_GROUP = 48, M_WINNER = 51,
-              M_TRICKDONE = 53, M_PLAYS = 54, M_SCORED = 60;
+              M_TRICKS = 17, M_WINNER = 21, M_TRICKDONE = 23, M_PHASE = 24, M_ERR = 26, M_GROUP = 27,
+              M_TRICK = 32, M_PLAYS = 56, M_SCORED = 62;
 enum : u32 { PH_DEALT = 0, PH_EXCHANGE = 1, PH_PLAY = 2, PH_DONE = 3 };
 
 __device__ __forceinline__ u32 mget(u64 m, int sh, u32 bits) { return (u32)(m >> sh) & ((1u << bits) - 1u); }
@@ -66,20 +66,20 @@ __device__ __forceinline__ u64 sel4(u64 a, u64 b, u64 c, u64 d, u32 i) {
     u64 lo = (i & 1) ? b : a, hi = (i & 1) ? d : c;
     return (i & 2) ? hi : lo;
 }
-// r-th (0-based) lowest set bit of m; r < popc(m)
+// r-th (0-based) lowest set bit of m; r < popc(m).  Binary descent on one 32-bit half.
 __device__ __forceinline__ u32 nth_set_bit(u64 m, u32 r) {
-    u32 lo = (u32)m, hi = (u32)(m >> 32);
-    u32 cl = __popc(lo);
-    u32 w = lo, base = 0;
-    if (r >= cl) { r -= cl; w = hi; base = 32; }
-    // binary descent inside the 32-bit word
-    u32 pos = 0, c;
-    c = __popc(w & 0xFFFFu);            if (r >= c) { r -= c; pos = 16; }
-    c = __popc((w >> pos) & 0xFFu);     if (r >= c) { r -= c; pos += 8; }
-    c = __popc((w >> pos) & 0xFu);      if (r >= c) { r -= c; pos += 4; }
-    c = __popc((w >> pos) & 0x3u);      if (r >= c) { r -= c; pos += 2; }
-    c = (w >> pos) & 1u;                if (r >= c) { pos += 1; }
-    return base + pos;
+    const u32 lo = (u32)m, hi = (u32)(m >> 32);
+    const u32 cl = __popc(lo);
+    const bool up = r >= cl;
+    u32 w = up ? hi : lo;
+    r -= up ? cl : 0u;
+    u32 pos = up ? 32u : 0u, c;
+    c = __popc(w & 0xFFFFu); if (r >= c) { r -= c; w >>= 16; pos += 16; }
+    c = __popc(w & 0xFFu);   if (r >= c) { r -= c; w >>= 8;  pos += 8; }
+    c = __popc(w & 0xFu);    if (r >= c) { r -= c; w >>= 4;  pos += 4; }
+    c = __popc(w & 0x3u);    if (r >= c) { r -= c; w >>= 2;  pos += 2; }
+    pos += (r >= (w & 1u)) ? 1u : 0u;
+    return pos;
 }
 __device__ __forceinline__ u64 suit_mask_of(u32 card) {
     return card >= 32 ? TAROKS : (0xFFull << (card & 24u));
@@ -89,15 +89,20 @@ __device__ __forceinline__ u64 suit_mask_of(u32 card) {
 // Navadna_igra.mozne_karte (Navadna_igra.py:158-168): follow suit, else must trump, else anything.
 // Klop.mozne_karte (Klop.py:96-133), *effective* behaviour (Q1): the overtake filter is computed and
 // dropped (Klop.py:104), leaving the same set minus the pagat whenever more than one card is legal.
+// Written on the 32-bit halves: the low word holds the four suits, the high word only taroks.
 __device__ __forceinline__ u64 legal_moves(u64 hand, bool has_lead, u32 lead, bool klop) {
-    u64 m = hand;
+    const u32 lo = (u32)hand, hi = (u32)(hand >> 32);
+    u32 mlo = lo, mhi = hi;
     if (has_lead) {
-        u64 f = hand & suit_mask_of(lead);
-        u64 t = hand & TAROKS;
-        m = f ? f : (t ? t : hand);
+        const u32 f = lead < 32u ? (lo & (0xFFu << (lead & 24u))) : 0u;   // cards of the led suit (taroks: via hi)
+        mlo = f ? f : (hi ? 0u : lo);
+        mhi = f ? 0u : hi;
     }
-    if (klop && (m & (m - 1))) m &= ~PAGAT;
-    return m;
+    if (klop) {
+        const u32 rest = mhi & ~1u;                                        // without the pagat (tarok I = bit 32)
+        if (mlo | rest) mhi = rest;
+    }
+    return ((u64)mhi << 32) | mlo;
 }
 
 // pobere_stih / primerjaj_karti (Navadna_igra.py:143-156, Klop.py:81-94): scan cards 1..3 against the
@@ -264,47 +269,40 @@ template <bool CHECK>
 __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talon, u64 talon_order,
                                          PlayResult& out) {
     out.trick_done = false; out.winner = 0; out.pile_bits = 0; out.talon_clear = 0;
-    const u32 contract = mget(meta, M_CONTRACT, 4);
-    const u32 pos = mget(meta, M_POS, 2);
-    const u32 leader = mget(meta, M_LEADER, 2);
+    u32 lo = (u32)meta, hi = (u32)(meta >> 32);
+    const u32 contract = lo & 15u;
+    const u32 pos = (lo >> M_POS) & 3u;
     const u64 bit = card < 54 ? (1ull << card) : 0ull;
     if (CHECK) {
-        u64 legal = legal_moves(hand, pos != 0, mget(meta, M_TRICK, 6), klop_rules(contract));
+        u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));
         if (!(legal & bit)) {                             // 'Karte ne mores igarti' (Navadna_igra.py:125-126)
-            meta |= 1ull << M_ERR;
-            return mset(meta, M_PHASE, 2, PH_DONE);
+            lo |= (1u << M_ERR) | (PH_DONE << M_PHASE);
+            return ((u64)hi << 32) | lo;
         }
     }
     hand ^= bit;
-    meta &= ~(1ull << M_TRICKDONE);
-    meta += 1ull << M_PLAYS;
-    u64 tr = (pos == 0 ? 0ull : (meta >> M_TRICK) & 0xFFFFFFull) | ((u64)card << (6 * pos));
+    const u32 tr = (pos ? (hi & 0xFFFFFFu) : 0u) | (card << (6u * pos));
+    hi = tr | ((hi & 0xFF000000u) + (1u << (M_PLAYS - 32)));           // trick cards | plays + 1 (| scored bit)
     if (pos < 3) {
-        meta = (meta & ~(0xFFFFFFull << M_TRICK)) | (tr << M_TRICK);
-        return mset(meta, M_POS, 2, pos + 1);
+        lo = (lo & ~(1u << M_TRICKDONE)) + (1u << M_POS);
+        return ((u64)hi << 32) | lo;
     }
     // trick complete
-    u32 tricks = mget(meta, M_TRICKS, 4);
-    u32 t24 = (u32)tr;
-    u32 w = (leader + trick_winner(t24)) & 3u;
-    u64 bits = (1ull << (t24 & 63u)) | (1ull << ((t24 >> 6) & 63u)) | (1ull << ((t24 >> 12) & 63u))
-             | (1ull << ((t24 >> 18) & 63u));
+    const u32 tricks = (lo >> M_TRICKS) & 15u;
+    const u32 w = (((lo >> M_LEADER) & 3u) + trick_winner(tr)) & 3u;
+    u64 bits = (1ull << (tr & 63u)) | (1ull << ((tr >> 6) & 63u)) | (1ull << ((tr >> 12) & 63u)) | (1ull << (tr >> 18));
     if (contract == C_KLOP && tricks < 6) {
         u64 tc = 1ull << ((talon_order >> (6 * (5 - tricks))) & 63ull);
         out.talon_clear = tc & talon;
         bits |= out.talon_clear;
     }
     out.trick_done = true; out.winner = w; out.pile_bits = bits;
-    tricks += 1;
-    meta = (meta & ~(0xFFFFFFull << M_TRICK)) | (tr << M_TRICK);   // keep the finished trick visible
-    meta = mset(meta, M_POS, 2, 0);
-    meta = mset(meta, M_LEADER, 2, w);
-    meta = mset(meta, M_WINNER, 2, w);
-    meta = mset(meta, M_TRICKS, 4, tricks);
-    meta |= 1ull << M_TRICKDONE;
-    bool fin = tricks == 12 || (is_berac(contract) && w == mget(meta, M_DECL, 2));
-    if (fin) meta = mset(meta, M_PHASE, 2, PH_DONE);
-    return meta;
+    const bool fin = tricks == 11 || (is_berac(contract) && w == ((lo >> M_DECL) & 3u));
+    constexpr u32 CLEAR = (3u << M_LEADER) | (3u << M_POS) | (15u << M_TRICKS) | (3u << M_WINNER) | (1u << M_TRICKDONE)
+                        | (3u << M_PHASE);
+    lo = (lo & ~CLEAR) | (w << M_LEADER) | ((tricks + 1u) << M_TRICKS) | (w << M_WINNER) | (1u << M_TRICKDONE)
+       | ((fin ? (u32)PH_DONE : (u32)PH_PLAY) << M_PHASE);              // the finished trick stays visible in hi
+    return ((u64)hi << 32) | lo;
 }
 
 // Legal mask of the seat to move given the (already updated) meta and that seat's hand.
@@ -313,7 +311,7 @@ __device__ __forceinline__ u64 mask_for_mover(u64 meta, u64 hand) {
     u32 pos = mget(meta, M_POS, 2);
     return legal_moves(hand, pos != 0, mget(meta, M_TRICK, 6), klop_rules(mget(meta, M_CONTRACT, 4)));
 }
-__device__ __forceinline__ u32 mover_of(u64 meta) { return (mget(meta, M_LEADER, 2) + mget(meta, M_POS, 2)) & 3u; }
+__device__ __forceinline__ u32 mover_of(u64 meta) { const u32 lo = (u32)meta; return ((lo >> M_LEADER) + (lo >> M_POS)) & 3u; }
 
 // ---- scoring --------------------------------------------------------------------------------------
 // Epilogues: Navadna_igra.start (Navadna_igra.py:80-113, Q6/Q7), Klop.start (Klop.py:36-45, Q5),

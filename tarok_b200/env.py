@@ -34,8 +34,8 @@ FLAG_HISTORY = 1
 S_SEAT, S_PLAYER, S_CONTRACT, S_FINISHED, S_STEPS, S_ERRORS, S_ERR_EVENTS = 0, 4, 8, 18, 19, 20, 21
 
 # meta word layout (tarok_b200/csrc/tarok_rules.cuh)
-M_CONTRACT, M_DECL, M_KING, M_TEAM, M_LEADER, M_POS, M_TRICKS, M_TRICK = 0, 4, 6, 9, 13, 15, 17, 21
-M_PHASE, M_ERR, M_GROUP, M_WINNER, M_TRICKDONE, M_PLAYS = 45, 47, 48, 51, 53, 54
+M_CONTRACT, M_DECL, M_KING, M_TEAM, M_LEADER, M_POS, M_TRICKS, M_WINNER, M_TRICKDONE = 0, 4, 6, 9, 13, 15, 17, 21, 23
+M_PHASE, M_ERR, M_GROUP, M_TRICK, M_PLAYS = 24, 26, 27, 32, 56
 PH_DEALT, PH_EXCHANGE, PH_PLAY, PH_DONE = 0, 1, 2, 3
 
 _DLTENSOR = b"dltensor"
@@ -121,6 +121,10 @@ class TarokEnv:
     stats_dev = property(lambda self: self.view(F_STATS))        # int64 [32]
     hands0 = property(lambda self: self.view(F_HANDS0))
     discard = property(lambda self: self.view(F_DISCARD))
+
+    def set_step_impl(self, impl: int):
+        """0 auto, 1 plain play_step kernel, 2 persistent TMA-staged kernel (A/B measurements)."""
+        self._check(self._lib.tarok_set_option(self._h, 1, int(impl)))
 
     @property
     def launches(self) -> int:
