@@ -19,6 +19,7 @@ struct tarok_env {
     int device;
     int sm_count;
     int step_impl;                             // 0 auto, 1 plain k_step, 2 persistent TMA-staged k_step_tma
+    int pdl;                                   // chain play_step launches with programmatic dependent launch
     u32 flags;
     tk::Env e;
     // staging buffers of the host-buffer entry point
@@ -77,8 +78,18 @@ static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     // measured on B200 (tools/step_ab.py, profiles/r01): the kernel is bound by integer-ALU issue, not by load
     // latency, so the plain kernel wins; "auto" therefore picks it and the staged one stays selectable.
     const bool tma = h->step_impl == 2;
-    if (tma) tk::k_step_tma<RANDOM><<<tiles < resident ? tiles : resident, tk::CTA, 0, s>>>(h->e, action);
-    else tk::k_step<RANDOM><<<tiles, tk::CTA, 0, s>>>(h->e, action);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tma ? (tiles < resident ? tiles : resident) : tiles);
+    cfg.blockDim = dim3(tk::CTA);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this launch with the previous tail
+    at[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (tma) cudaLaunchKernelEx(&cfg, tk::k_step_tma<RANDOM>, h->e, action);
+    else cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM>, h->e, action);
 }
 
 extern "C" {
@@ -86,13 +97,14 @@ extern "C" {
 int tarok_set_option(tarok_t* h, int option, int64_t value) {
     TK_CHECK_HANDLE(h);
     if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 2) { h->step_impl = (int)value; return 0; }
+    if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
     return fail(h, -1, "unknown option %d / value %lld", option, (long long)value);
 }
 
 int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, tarok_t** out) {
     if (!out) return fail(nullptr, -1, "out is null");
     *out = nullptr;
-    if (n_games == 0) return fail(nullptr, -1, "n_games must be > 0");
+    if (n_games == 0 || n_games > (1ull << 29)) return fail(nullptr, -1, "n_games must be in 1..2^29");
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0)
@@ -106,7 +118,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     tarok_env* h = new (std::nothrow) tarok_env();
     if (!h) return fail(nullptr, -4, "out of host memory");
     memset(&h->e, 0, sizeof(h->e));
-    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
+    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;

@@ -394,10 +394,18 @@ struct SmemHands {
     __device__ __forceinline__ u64 get(u32 seat) const { return base[seat * TILE]; }
 };
 
+// Programmatic dependent launch (PDL): consecutive play_step launches are chained so that the CTAs of step
+// t+1 are scheduled while the tail of step t drains; they park at griddepcontrol.wait until step t has
+// completed and its writes are visible.  This removes the launch ramp / tail bubble between the 48 steps.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Game indices are 32-bit inside the step kernels (n_alloc <= 2^29, enforced by tarok_create): one IMAD.WIDE
+// per address instead of 64-bit multiply chains.
 template <bool RANDOM, class Hands>
-__device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, const Hands& hands, u32 card,
+__device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const Hands& hands, u32 card,
                                           const Words4& rnd, u64& next_mask) {
-    const u64 na = e.n_alloc;
+    const u32 na = (u32)e.n_alloc;
     const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 mover = mover_of(meta);
     u64 hand = hands.get(mover);
@@ -405,8 +413,8 @@ __device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, const 
     const u32 pos = (lo >> M_POS) & 3u;
     const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
     u64 talon = 0, order = 0;
-    if (contract == C_KLOP && pos == 3 && ((lo >> M_TRICKS) & 15u) < 6) {
-        talon = e.talon[g]; order = e.torder[g];
+    if (contract == C_KLOP) {
+        if (pos == 3 && ((lo >> M_TRICKS) & 15u) < 6) { talon = e.talon[g]; order = e.torder[g]; }
     }
     if (RANDOM) {
         u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));
@@ -423,7 +431,7 @@ __device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, const 
     e.hands[mover * na + g] = hand;
     if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
     if (pr.trick_done) {
-        u64* pp = e.piles + pr.winner * na + g;
+        u64* pp = e.piles + (pr.winner * na + g);
         *pp |= pr.pile_bits;
         if (pr.talon_clear) e.talon[g] = talon & ~pr.talon_clear;
     }
@@ -433,13 +441,15 @@ __device__ __forceinline__ void step_game(const Env& e, u64 g, u64& meta, const 
 
 template <bool RANDOM>
 __global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restrict__ action) {
-    const u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
-    if (g >= e.n_alloc) return;
-    const u64 na = e.n_alloc;
+    pdl_launch_dependents();
+    const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
+    const u32 na = (u32)e.n_alloc;
+    if (g >= na) return;
+    pdl_wait();                                    // the previous step's writes are visible from here on
     // all five 128-bit loads are issued before the first use: one memory round trip per step
     ulonglong2 m = ld2(e.meta + g);
-    ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + na + g), h2 = ld2(e.hands + 2 * na + g),
-               h3 = ld2(e.hands + 3 * na + g);
+    ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + (na + g)), h2 = ld2(e.hands + (2 * na + g)),
+               h3 = ld2(e.hands + (3 * na + g));
     u32 act = 0;
     if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
     const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
@@ -499,6 +509,7 @@ template <bool RANDOM>
 __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __restrict__ action) {
     __shared__ StepStage stage[2];
     __shared__ __align__(8) u64 full[2];
+    pdl_launch_dependents();
     const u64 na = e.n_alloc;
     const u32 tiles = (u32)(na / TILE);
     if (threadIdx.x == 0) {
@@ -507,6 +518,7 @@ __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __res
         mbar_fence_init();
     }
     __syncthreads();
+    pdl_wait();
     auto fetch = [&](u32 tile, u32 s) {               // elected lane: arm the barrier, issue the 5 bulk copies
         const u64 g0 = (u64)tile * TILE;
         mbar_arrive_expect_tx(&full[s], STEP_STAGE_BYTES);
@@ -520,7 +532,7 @@ __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __res
     for (u32 it = 0; tile < tiles; it++, tile += gridDim.x) {
         const u32 s = it & 1u;
         if (threadIdx.x == 0 && tile + gridDim.x < tiles) fetch(tile + gridDim.x, s ^ 1u);
-        const u64 g = (u64)tile * TILE + l;
+        const u32 g = tile * TILE + l;
         u32 act = 0;
         if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
         mbar_wait(&full[s], (it >> 1) & 1u);

@@ -126,6 +126,10 @@ class TarokEnv:
         """0 auto, 1 plain play_step kernel, 2 persistent TMA-staged kernel (A/B measurements)."""
         self._check(self._lib.tarok_set_option(self._h, 1, int(impl)))
 
+    def set_pdl(self, on: bool):
+        """Programmatic dependent launch between consecutive play_step kernels (default on)."""
+        self._check(self._lib.tarok_set_option(self._h, 2, 1 if on else 0))
+
     @property
     def launches(self) -> int:
         return int(self._lib.tarok_launch_count(self._h))
