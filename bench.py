@@ -41,7 +41,7 @@ MODE_NAMES = {16: "Navadna igra (Tri/Dve/Ena forced, uniform declarer+king), tal
 
 def workload_name(mode, games):
     return ("config 2: %s; 4 uniform-random legal-move players; %d concurrent deals per GPU; one step = deal, contract, "
-            "talon exchange, 48 x play_step, score" % (MODE_NAMES.get(mode, str(mode)), games))
+            "talon exchange (one fused setup launch), 48 x play_step, score" % (MODE_NAMES.get(mode, str(mode)), games))
 
 
 def hbm_peak():
@@ -66,15 +66,15 @@ class ClockSampler:
     def _nvml_loop(self):
         import pynvml as N
         h = N.nvmlDeviceGetHandleByIndex(self.index)
+        self.mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
         while not self.stop_flag:
             try:
                 sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
-                mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
                 rs = N.nvmlDeviceGetCurrentClocksEventReasons(h)
-                self.samples.append((sm, mx, rs))
+                self.samples.append((sm, self.mx, rs))
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.001)
 
     def _nvml_result(self):
         import pynvml as N
@@ -85,7 +85,7 @@ class ClockSampler:
         reasons = sorted(k for k, bit in names.items() if any(s[2] & bit for s in self.samples))
         sm = [s[0] for s in self.samples]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if sm else None,
-                "samples": len(sm), "reasons": reasons, "source": "NVML, 2 ms period, timed region only"}
+                "samples": len(sm), "reasons": reasons, "source": "NVML polling thread, timed region only"}
 
     def start(self):
         try:
@@ -209,9 +209,7 @@ def run_ours(args, rank, world, local_rank):
     def rollout(i, timed):
         gid0 = i * total + rank * n
         flush.zero_()                                                      # L2 flush between iterations
-        env.deal(gid0)
-        env.auction_synth(mode) if auction else env.force_contract_synth(mode)
-        env.exchange_synth(mode == MODE_AUCTION_UNIFORM)
+        env.setup_synth(mode, gid0)                                        # deal + contract + exchange, one launch
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         env.step_random(48)
@@ -383,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--games", type=int, default=1 << 20, help="concurrent deals per GPU")
     ap.add_argument("--mode", type=int, default=16)

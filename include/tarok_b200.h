@@ -133,8 +133,11 @@ int tarok_reset_stats(tarok_t* h, void* stream);
 int tarok_read_stats(tarok_t* h, int64_t* out_host /* [32] */, void* stream); /* synchronises stream */
 
 /* ---- whole deals ----------------------------------------------------------------------------- */
-/* Stepwise pipeline with in-kernel uniform-random players: deal -> contract(mode) -> exchange ->
-   48 x step_random -> score.  Equivalent to Tarok.paralel_start with Bot-like players. */
+/* deal + contract(mode) + talon exchange with device-side (Philox) decisions in ONE launch; the state it
+   leaves is bit-identical to tarok_deal + tarok_auction_synth/tarok_force_contract_synth + tarok_exchange_synth. */
+int tarok_setup_synth(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream);
+/* Stepwise pipeline with in-kernel uniform-random players: setup (deal, contract(mode), exchange) ->
+   48 x step_random -> score = 50 launches.  Equivalent to Tarok.paralel_start with Bot-like players. */
 int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream);
 /* Same result, one fused kernel with the state in registers (not HBM-bound). */
 int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream);

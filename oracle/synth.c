@@ -49,21 +49,31 @@ uint32_t syn_draw(uint64_t seed, uint64_t gid, uint32_t stream, uint32_t idx, ui
     }
 }
 
-enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5, ST_PLAY_RETRY = 6 };
+enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5, ST_PLAY_RETRY = 6, ST_DEAL_RETRY = 7 };
 enum { MODE_NAVADNA_MIX = 16, MODE_AUCTION_UNIFORM = 17, MODE_AUCTION_BOT = 18 };
 
 /* Uniform deal: card c = 0..53 goes to a uniformly random free slot among the 54-c left; slots
    are exchangeable inside a pile, so this is a walk over the remaining capacities of the piles
-   (seat 0..3: 12 each, then the talon: 6).  The ORDER of the six talon cards (it matters:
-   Navadna_igra.py:44, Klop.py:69) is a uniform permutation decoded from one more draw (idx 54,
+   (seat 0..3: 12 each, then the talon: 6); the 54 draws use 16-bit lanes of Philox blocks 0..6 (16-bit
+   Lemire, rejected sliver -> 32-bit draw on stream 7).  The ORDER of the six talon cards (it matters:
+   Navadna_igra.py:44, Klop.py:69) is a uniform permutation decoded from word 27 (32-bit Lemire,
    n = 720, Lehmer code over the talon ids in ascending order).  Exported as the permutation
    Igra.razdeli would have consumed: seat slices ascending by id, then the ordered talon. */
 void syn_deal(uint64_t seed, uint64_t gid, uint8_t perm[54]) {
     int cap[4] = { 12, 12, 12, 12 }, fill[4] = { 0, 0, 0, 0 };
     uint8_t tal[6];
     int nt = 0;
+    uint32_t w[28];
+    for (uint32_t b = 0; b < 7; b++) {          /* 28 words = 56 sixteen-bit lanes */
+        uint32_t c[4] = { (uint32_t)gid, (uint32_t)(gid >> 32), ST_DEAL, b };
+        syn_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        memcpy(w + 4 * b, c, sizeof(c));
+    }
     for (int c = 0; c < 54; c++) {
-        uint32_t r = syn_draw(seed, gid, ST_DEAL, (uint32_t)c, (uint32_t)(54 - c));
+        uint32_t n = (uint32_t)(54 - c);
+        uint32_t x = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
+        uint32_t m = x * n, r = m >> 16;
+        if ((m & 0xFFFFu) < (65536u % n)) r = syn_draw(seed, gid, ST_DEAL_RETRY, (uint32_t)c, n);
         int s;
         for (s = 0; s < 4; s++) {
             if (r < (uint32_t)cap[s]) break;
@@ -72,7 +82,9 @@ void syn_deal(uint64_t seed, uint64_t gid, uint8_t perm[54]) {
         if (s < 4) { perm[12 * s + fill[s]++] = (uint8_t)c; cap[s]--; }
         else tal[nt++] = (uint8_t)c;
     }
-    uint32_t L = syn_draw(seed, gid, ST_DEAL, 54, 720);
+    uint64_t mm = (uint64_t)w[27] * 720u;
+    uint32_t L = (uint32_t)(mm >> 32);
+    if ((uint32_t)mm < 256u) L = syn_draw(seed, gid, ST_DEAL_RETRY, 54, 720);     /* 2^32 % 720 = 256 */
     static const uint32_t fact[6] = { 120, 24, 6, 2, 1, 1 };
     int left = 6;
     for (int i = 0; i < 6; i++) {

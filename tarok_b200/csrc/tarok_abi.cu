@@ -365,15 +365,30 @@ static int play_out_stepwise(tarok_t* h, uint32_t random_group, void* stream) {
     return 0;
 }
 
+int tarok_setup_synth(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!(mode <= TAROK_ODPRTI_BERAC || (mode >= TAROK_MODE_NAVADNA_MIX && mode <= TAROK_MODE_AUCTION_BOT)))
+        return fail(h, -1, "bad mode %u", mode);
+    DeviceGuard dg(h->device);
+    h->e.first_gid = first_global_game_id;
+    clear_hist(h, stream);
+    tk::k_setup_synth<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
 int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream) {
     TK_CHECK_HANDLE(h);
-    int rc = tarok_deal(h, first_global_game_id, stream);
-    if (rc) return rc;
-    if (mode == TAROK_MODE_AUCTION_UNIFORM || mode == TAROK_MODE_AUCTION_BOT) rc = tarok_auction_synth(h, mode, stream);
-    else rc = tarok_force_contract_synth(h, mode, stream);
+    int rc = tarok_setup_synth(h, mode, first_global_game_id, stream);
     if (rc) return rc;
     DeviceGuard dg(h->device);
-    return play_out_stepwise(h, mode == TAROK_MODE_AUCTION_UNIFORM, stream);
+    for (int t = 0; t < 48; t++) {
+        launch_step<true>(h, nullptr, S(stream));
+        TK_LAUNCH_OK(h);
+    }
+    tk::k_score<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
+    TK_LAUNCH_OK(h);
+    return 0;
 }
 
 int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream) {
@@ -430,9 +445,11 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
         for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
             const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
             TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * 54, perm_host + b * 54, len * 54, cudaMemcpyHostToDevice, h->s_up));
-            TK_CUDA(h, cudaMemcpyAsync(h->st_contract + b, contract_host + b, len, cudaMemcpyHostToDevice, h->s_up));
-            TK_CUDA(h, cudaMemcpyAsync(h->st_declarer + b, declarer_host + b, len, cudaMemcpyHostToDevice, h->s_up));
-            if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king + b, king_host + b, len, cudaMemcpyHostToDevice, h->s_up));
+            if (c == 0) {   // the three 1-byte-per-game inputs go up whole, right behind the first chunk of deals
+                TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, h->s_up));
+                TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, h->s_up));
+                if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, h->s_up));
+            }
             TK_CUDA(h, cudaEventRecord(h->ev_up[c], h->s_up));
             TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_up[c], 0));
             tk::Env ev = h->e;

@@ -119,31 +119,50 @@ __device__ __forceinline__ u64 order_from_lehmer(u64 talon, u32 L) {
     return order;
 }
 
+// 54 bounded draws with n <= 54 need few random bits: they use 16-bit lanes (half c of the 28 words of Philox
+// blocks 0..6; 16-bit Lemire, the rejected sliver -- probability < n/65536 -- redraws on stream ST_DEAL_RETRY);
+// the talon permutation uses the last full word (32-bit Lemire, n = 720).  7 Philox blocks per deal.
+// Card c lives in the low word of a bitboard for c < 32 and in the high word otherwise, which is known at
+// compile time in the unrolled loop: every update is one predicated 32-bit OR.
+enum : u32 { ST_DEAL_RETRY = 7 };
+
 __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
-    Dealt d = {0, 0, 0, 0, 0, 0};
+    u32 lo[5] = {0, 0, 0, 0, 0}, hi[5] = {0, 0, 0, 0, 0};      // seats 0..3, talon
     u32 c0 = 12, c1 = 12, c2 = 12, c3 = 12;
     u32 L = 0;
 #pragma unroll
-    for (int blk = 0; blk < 14; blk++) {
+    for (int blk = 0; blk < 7; blk++) {
         Words4 b = philox_block(rng, gid, ST_DEAL, (u32)blk);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int c = blk * 4 + j;
+        for (int j = 0; j < 8; j++) {
+            const int c = blk * 8 + j;
+            const u32 word = b.w[j >> 1];
             if (c < 54) {
-                u32 r = draw_from_word(b.w[j], rng, gid, ST_DEAL, (u32)c, (u32)(54 - c));
-                u32 a0 = c0, a1 = a0 + c1, a2 = a1 + c2, a3 = a2 + c3;
-                const u64 bit = 1ull << c;
-                bool p0 = r < a0, p1 = !p0 && r < a1, p2 = r >= a1 && r < a2, p3 = r >= a2 && r < a3, p4 = r >= a3;
-                d.h0 |= p0 ? bit : 0ull; c0 -= p0 ? 1u : 0u;
-                d.h1 |= p1 ? bit : 0ull; c1 -= p1 ? 1u : 0u;
-                d.h2 |= p2 ? bit : 0ull; c2 -= p2 ? 1u : 0u;
-                d.h3 |= p3 ? bit : 0ull; c3 -= p3 ? 1u : 0u;
-                d.talon |= p4 ? bit : 0ull;
-            } else if (c == 54) {
-                L = draw_from_word(b.w[j], rng, gid, ST_DEAL, 54u, 720u);
+                const u32 n = (u32)(54 - c);
+                const u32 x = (j & 1) ? (word >> 16) : (word & 0xFFFFu);
+                const u32 m = x * n;
+                u32 r = m >> 16;
+                if (__builtin_expect((m & 0xFFFFu) < (65536u % n), 0)) r = draw_loop(rng.seed, gid, ST_DEAL_RETRY, (u32)c, n, 0u);
+                const u32 a0 = c0, a1 = a0 + c1, a2 = a1 + c2, a3 = a2 + c3;
+                const bool p0 = r < a0, p1 = !p0 && r < a1, p2 = r >= a1 && r < a2, p3 = r >= a2 && r < a3, p4 = r >= a3;
+                const u32 bit = 1u << (c & 31);
+                u32* half = c < 32 ? lo : hi;
+                half[0] |= p0 ? bit : 0u; c0 -= p0 ? 1u : 0u;
+                half[1] |= p1 ? bit : 0u; c1 -= p1 ? 1u : 0u;
+                half[2] |= p2 ? bit : 0u; c2 -= p2 ? 1u : 0u;
+                half[3] |= p3 ? bit : 0u; c3 -= p3 ? 1u : 0u;
+                half[4] |= p4 ? bit : 0u;
+            } else if (c == 55) {                               // word 27 whole: the talon order
+                const u64 m = (u64)word * 720u;
+                L = (u32)(m >> 32);
+                if (__builtin_expect((u32)m < 256u, 0)) L = draw_loop(rng.seed, gid, ST_DEAL_RETRY, 54u, 720u, 0u);   // 2^32 % 720 = 256
             }
         }
     }
+    Dealt d;
+    d.h0 = ((u64)hi[0] << 32) | lo[0]; d.h1 = ((u64)hi[1] << 32) | lo[1];
+    d.h2 = ((u64)hi[2] << 32) | lo[2]; d.h3 = ((u64)hi[3] << 32) | lo[3];
+    d.talon = ((u64)hi[4] << 32) | lo[4];
     d.order = order_from_lehmer(d.talon, L);
     return d;
 }
@@ -393,6 +412,48 @@ struct SmemHands {
     const u64* base;                       // &stage.hands[0][game]; seat stride = TILE words
     __device__ __forceinline__ u64 get(u32 seat) const { return base[seat * TILE]; }
 };
+
+// ------------------------------------------------------------------------------------------------
+// setup: deal -> contract (synthetic mode) -> talon exchange fused into ONE launch for pipelines whose
+// pre-play decisions are all made on the device (uniform-random / Bot players).  Same device functions and
+// Philox draws as k_deal + k_begin<SYNTH> + k_exchange<SYNTH>, so the resulting state is bit-identical; the
+// state is written once instead of written, re-read and patched twice.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA) k_setup_synth(Env e, u32 mode) {
+    const u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
+    const u64 na = e.n_alloc;
+    if (g >= na) return;
+    Dealt d = {0, 0, 0, 0, 0, 0};
+    u64 meta = meta_pad(), mask = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0, dout = 0;
+    u64 s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (g < e.n) {
+        const u64 gid = e.first_gid + g;
+        d = deal_philox(e.rng, gid);
+        s0 = d.h0; s1 = d.h1; s2 = d.h2; s3 = d.h3;
+        u32 contract, declarer, king;
+        resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, contract, declarer, king);
+        meta = begin_contract(meta_fresh(), contract, declarer, king, d.h0, d.h1, d.h2, d.h3);
+        if (mget(meta, M_PHASE, 2) == PH_EXCHANGE) {
+            const u32 decl = mget(meta, M_DECL, 2);
+            u64 hand = sel4(d.h0, d.h1, d.h2, d.h3, decl), pile = 0;
+            if (exchange_game<true>(e.rng, gid, mode == 17u, meta, hand, pile, d.talon, d.order, 0u, 0ull, dout)) {
+                d.h0 = decl == 0 ? hand : d.h0; d.h1 = decl == 1 ? hand : d.h1;
+                d.h2 = decl == 2 ? hand : d.h2; d.h3 = decl == 3 ? hand : d.h3;
+                p0 = decl == 0 ? pile : 0ull; p1 = decl == 1 ? pile : 0ull;
+                p2 = decl == 2 ? pile : 0ull; p3 = decl == 3 ? pile : 0ull;
+            } else {
+                meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
+            }
+        }
+        if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
+        mask = mask_for_mover(meta, sel4(d.h0, d.h1, d.h2, d.h3, mover_of(meta)));
+    }
+    e.hands[g] = d.h0; e.hands[na + g] = d.h1; e.hands[2 * na + g] = d.h2; e.hands[3 * na + g] = d.h3;
+    e.piles[g] = p0; e.piles[na + g] = p1; e.piles[2 * na + g] = p2; e.piles[3 * na + g] = p3;
+    e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = mask;
+    if (e.hands0) { e.hands0[g] = s0; e.hands0[na + g] = s1; e.hands0[2 * na + g] = s2; e.hands0[3 * na + g] = s3; }
+    if (e.discard) e.discard[g] = dout;
+}
 
 // Programmatic dependent launch (PDL): consecutive play_step launches are chained so that the CTAs of step
 // t+1 are scheduled while the tail of step t drains; they park at griddepcontrol.wait until step t has

@@ -219,6 +219,10 @@ class TarokEnv:
         return out
 
     # ------------------------------------------------------------------ whole deals
+    def setup_synth(self, mode: int, first_game_id: int = 0):
+        """deal + contract(mode) + talon exchange with device-side decisions, one launch."""
+        self._check(self._lib.tarok_setup_synth(self._h, int(mode), int(first_game_id), self._stream()))
+
     def rollout(self, mode: int, first_game_id: int = 0, fused: bool = False):
         """deal -> contract(mode) -> exchange -> random play -> score, all on the device."""
         fn = self._lib.tarok_rollout_fused if fused else self._lib.tarok_rollout_stepwise

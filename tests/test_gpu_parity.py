@@ -193,6 +193,21 @@ def test_rollout_matches_oracle(oracle, mode):
     env.close()
 
 
+def test_fused_setup_equals_separate_kernels():
+    import tarok_b200.env as E
+    n = 70001
+    for mode in (16, 17, 18, 0, 7, 8):
+        a, b = _env(n, seed=99, history=True), _env(n, seed=99, history=True)
+        a.setup_synth(mode, 555)
+        b.deal(555)
+        b.auction_synth(mode) if mode in (17, 18) else b.force_contract_synth(mode)
+        b.exchange_synth(mode == E.MODE_AUCTION_UNIFORM)
+        for f in ("hands", "piles", "talon", "talon_order", "meta", "mask", "hands0", "discard"):
+            assert (u64(getattr(a, f)) == u64(getattr(b, f))).all(), (mode, f)
+        assert a.stats()[21] == b.stats()[21]
+        a.close(); b.close()
+
+
 def test_teacher_forced_replay_at_full_size(oracle):
     """BASELINE config 2 size: 1,048,576 Navadna deals played on the GPU, then EVERY game replayed
     card by card through the C oracle (legality, trick winners, scores)."""
@@ -283,7 +298,7 @@ def test_no_cpu_fallback_symbols_loaded():
     env = _env(1000)
     before = env.launches
     env.rollout(0)
-    assert env.launches - before == 52
+    assert env.launches - before == 50          # setup + 48 x play_step + score
     with open("/proc/self/maps") as f:
         assert "libtarok_b200.so" in f.read()
     env.close()
