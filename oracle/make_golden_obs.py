@@ -1,0 +1,141 @@
+"""TEST INFRASTRUCTURE ONLY -- freezes OBSERVATIONS of the real reference into tests/golden/obs.npz.
+
+    python -m oracle.make_golden_obs
+
+The observation encoder is the reference's own ``Nevronski_igralec.stanje_v_vektor_rek_navadna``
+(Igralec.py:453-533), called unmodified through ``pripravi_igraj_karto`` (Igralec.py:312-314) at every
+decision of every seat.  Only the *decisions* are scripted (seeded random legal cards / groups / discards);
+the nets are never built (``ignor_models=True``).  Per observation the fixture stores the bit-packed
+concatenation of the reference's input arrays (all entries are 0/1) in the reference's list order.
+"""
+from __future__ import annotations
+
+import os
+import random
+
+import numpy as np
+
+from . import ref_harness as H
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+NET_TYPES = {"Klop": 0, "Navadna_igra": 1, "Solo": 2, "Berac": 3}     # Nevronski_igralec.Tipi_NN values
+
+
+def make_obs_player(ref, rng, log):
+    NN = ref.Igralec.Nevronski_igralec
+    Base = ref.Igralec.Igralec
+
+    class ObsPlayer(NN):
+        def __init__(self, seat):
+            super().__init__(ignor_models=True, ime="seat%d" % seat)
+            self.seat = seat
+            self.game_row = 0
+
+        # ---- decisions are scripted; everything else is the reference's own code ----
+        def pripravi_izbral_iz_talona(self, talon, st_kart, id_igre):
+            pass
+
+        def predict_izberi_iz_talona(self):
+            pass
+
+        def predict_igraj_karto(self):
+            for k in self.predict_queue:
+                self.predict_queue[k] = []
+
+        def menjaj_iz_talona(self, kupcki, st_kart, id_igre):
+            g = rng.randrange(len(kupcki))
+            self.roka[id_igre].dodaj_karte(kupcki[g])
+            mozno = self.roka[id_igre].mozno_zalozit()
+            zalozi = rng.sample(mozno, st_kart)
+            self.kupcek[id_igre].extend(zalozi)
+            self.zalozil[id_igre] = True                                     # Igralec.py:380
+            for k in zalozi:
+                self.roka[id_igre].igraj_karto(k)
+            self.zalaganje2tocke[id_igre] = [None, zalozi, st_kart, None, mozno]   # Igralec.py:384
+            log["group"], log["discard"] = g, H.cards_to_mask(zalozi)
+            return g
+
+        def pripravi_igraj_karto(self, karte_na_mizi, mozne, zgodovina, id_igre):
+            super().pripravi_igraj_karto(karte_na_mizi, mozne, zgodovina, id_igre)   # builds self.stanje[id]
+            arrs = self.stanje[id_igre]
+            flat = np.concatenate([np.asarray(a, np.float64).reshape(-1) for a in arrs])
+            assert set(np.unique(flat)) <= {0.0, 1.0}
+            log["obs"].append(dict(seat=self.seat, T=int(arrs[0].shape[1]), kind=NET_TYPES[self.tip_igre[id_igre]],
+                                   shapes=[tuple(a.shape[1:]) for a in arrs], bits=np.packbits(flat.astype(np.uint8))))
+
+        def igraj_karto(self, karte_na_mizi, mozne, zgodovina, id_igre):
+            karta = mozne[rng.randrange(len(mozne))]
+            log["cards"].append(karta.v_id())
+            return Base.igraj_karto(self, karta, id_igre)
+
+        def rezultat_stiha(self, stih, sem_pobral, id_igre):
+            pass
+
+        def rezultat_igre(self, st_tock, povzetek_igre, id_igre):
+            pass
+
+        def poglej_karte_odprtega_beraca(self, roka, id_igre):
+            pass
+
+    return ObsPlayer
+
+
+def run_game(ref, rng, perm, contract, declarer, king):
+    Tip = ref.Tip_igre.Tip_igre
+    log = dict(obs=[], cards=[], group=0xFF, discard=0)
+    P = make_obs_player(ref, rng, log)
+    players = [P(s) for s in range(4)]
+    H.inject_deal(ref, perm)
+    talon = ref.Igra.Igra(players).razdeli()
+    name = H.CONTRACT_NAMES[contract]
+    barva = ref.Karta.Barva(king) if king != H.NO_KING else None
+    for p in players:      # what Igra.start does right after the auction (Igra.py:57-58)
+        p.lic[0] = Tip(contract * 10)
+        p.konec_licitiranja(players[declarer], Tip(contract * 10), 0, barva)
+    if name == "Klop":
+        g = ref.Klop.Klop(players, talon, 0)
+    elif name in ("Berac", "Odprti_berac"):
+        g = ref.Berac.Berac(players, players[declarer], talon, name == "Odprti_berac", 0)
+    else:
+        g = ref.Navadna_igra.Navadna_igra(players, Tip(contract * 10), barva, players[declarer], talon, 0)
+    list(g.start())
+    return log
+
+
+def main(per_contract=6, seed=424242):
+    ref = H.load_reference()
+    rng = random.Random(seed)
+    games, obs_rows, blobs = [], [], []
+    for c in range(10):
+        done = 0
+        while done < per_contract:
+            perm = list(range(54))
+            rng.shuffle(perm)
+            d = 0 if c == 0 else rng.randrange(4)
+            k = rng.randrange(4) if 1 <= c <= 3 else H.NO_KING
+            try:
+                log = run_game(ref, rng, perm, c, d, k)
+            except ValueError:
+                continue
+            gi = len(games)
+            cards = log["cards"] + [0xFF] * (48 - len(log["cards"]))
+            games.append(dict(perm=perm, contract=c, declarer=d, king=k, group=log["group"], discard=log["discard"],
+                              cards=cards))
+            for t, o in enumerate(log["obs"]):
+                obs_rows.append((gi, t, o["seat"], o["T"], o["kind"], len(o["bits"])))
+                blobs.append(o["bits"])
+            done += 1
+    off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])]).astype(np.int64)
+    np.savez_compressed(
+        os.path.join(OUT, "obs.npz"),
+        perm=np.array([g["perm"] for g in games], np.uint8), contract=np.array([g["contract"] for g in games], np.uint8),
+        declarer=np.array([g["declarer"] for g in games], np.uint8), king=np.array([g["king"] for g in games], np.uint8),
+        group=np.array([g["group"] for g in games], np.uint8), discard_mask=np.array([g["discard"] for g in games], np.uint64),
+        card=np.array([g["cards"] for g in games], np.uint8),
+        obs_index=np.array(obs_rows, np.int32),          # (game, play, seat, T, kind, packed bytes)
+        obs_offset=off, obs_bits=np.concatenate(blobs))
+    print("obs.npz: %d games, %d observations, %d packed bytes" % (len(games), len(obs_rows), off[-1]))
+
+
+if __name__ == "__main__":
+    main()
