@@ -150,6 +150,20 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
                        uint64_t first_global_game_id, int fused,
                        int16_t* scores_host, int64_t* stats_host, void* stream);
 
+/* ---- observations: Nevronski_igralec.stanje_v_vektor_rek_navadna (Igralec.py:453-533) --------- */
+/* Needs TAROK_FLAG_HISTORY.  net_type follows Nevronski_igralec.Tipi_NN: 0 Klop, 1 Navadna_igra (Tri/Dve/Ena),
+   2 Solo (Solo_*), 3 Berac.  tarok_obs_shape gives, per game, the net type of its contract (255 = not waiting
+   for a card) and the reference's padded history length T (multiple of 8), i.e. the (net, T) bucket
+   predict_igraj_karto (Igralec.py:316-342) batches by.  tarok_obs_expand writes, for the seat to move of the
+   n_sel selected games (sel_dev: int32 game indices, NULL = 0..n_sel-1), the fp32 input arrays in the reference's
+   layout: opp [n_sel,T,3,54], hand [n_sel,T,54], talon [n_sel,6,55] (types 1,2) / [n_sel,54] (type 0),
+   king [n_sel,4] (type 1), decl [n_sel,4], discard [n_sel,54], mozne [n_sel,54]; optional outputs may be NULL.
+   Games that do not belong to the (net_type, rows) bucket get zeros and ok = 0. */
+int tarok_obs_shape(tarok_t* h, uint8_t* type_dev, uint8_t* rows_dev, void* stream);
+int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel_dev, uint64_t n_sel, float* opp_dev,
+                     float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev, float* discard_dev,
+                     float* mozne_dev, uint8_t* ok_dev, void* stream);
+
 /* ---- zero-copy views ------------------------------------------------------------------------- */
 /* Lends a field as a DLPack tensor that aliases the handle's device memory.  The caller (e.g.
    torch.from_dlpack) must call the deleter; the handle cannot be destroyed before that. */

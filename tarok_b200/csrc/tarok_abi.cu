@@ -9,6 +9,7 @@
 #include <new>
 
 #include "tarok_kernels.cuh"
+#include "tarok_obs.cuh"
 
 using tk::u64;
 using tk::u32;
@@ -480,6 +481,36 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
     }
     if (scores_host) TK_CUDA(h, cudaMemcpyAsync(scores_host, h->e.scores, n * 8, cudaMemcpyDeviceToHost, s));
     if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+// ---- observations ------------------------------------------------------------------------
+
+int tarok_obs_shape(tarok_t* h, uint8_t* type_dev, uint8_t* rows_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!type_dev || !rows_dev) return fail(h, -1, "type_dev/rows_dev is null");
+    DeviceGuard dg(h->device);
+    tk::k_obs_shape<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, type_dev, rows_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel_dev, uint64_t n_sel, float* opp_dev,
+                     float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev, float* discard_dev,
+                     float* mozne_dev, uint8_t* ok_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!h->e.hist) return fail(h, -1, "observations need TAROK_FLAG_HISTORY at tarok_create");
+    if (net_type < 0 || net_type > 3) return fail(h, -1, "net_type must be 0..3");
+    if (rows == 0 || (rows & 7u) || rows > 56) return fail(h, -1, "rows must be a multiple of 8 in 8..56");
+    if (!opp_dev || !hand_dev) return fail(h, -1, "opp_dev/hand_dev is null");
+    if ((((uintptr_t)opp_dev) | ((uintptr_t)hand_dev)) & 15u) return fail(h, -1, "opp_dev/hand_dev must be 16-byte aligned");
+    if (n_sel == 0) return 0;
+    DeviceGuard dg(h->device);
+    tk::ObsOut o = {opp_dev, hand_dev, talon_dev, king_dev, decl_dev, discard_dev, mozne_dev, ok_dev};
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_obs_expand<<<(unsigned)((n_sel + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, net_type, rows, (const int*)sel_dev, n_sel, o);
+    TK_LAUNCH_OK(h);
     return 0;
 }
 

@@ -1,0 +1,146 @@
+// Observation expansion on the device: Nevronski_igralec.stanje_v_vektor_rek_navadna (Igralec.py:453-533).
+//
+// For the seat to move of every selected game the reference builds, per decision, a list of float arrays
+// from the game history; here one WARP builds them straight from the compact state (history bytes, hands as
+// dealt, discards, talon order, meta) and writes fp32 in the reference's layout.  Write-dominated:
+// (T*216 + extras) * 4 bytes per acting game.
+//
+// Reference behaviour reproduced:
+//  * T = n + (8 - n % 8) with n = len(zgodovina) counting EVERY entry: the plays, the ("Talon", ...) entry of an
+//    exchange and the (None, card) entries of Klop talon cards (the filter at Igralec.py:457 is always true).
+//  * rows advance on player plays only: row i = i-th card play.  nasprotniki[i, opp, card] for opponents'
+//    plays; roka_input[i, :] for own plays = the hand AS DEALT (pre-exchange, Igralec.py:264,465) minus the own
+//    cards played before row i (discards and talon pick-ups never change it).
+//  * opponent index = position among the other three players in seat order; self = 3 (Igralec.py:271-274).
+//  * talon_input: Navadna/Solo [6,55] row j = j-th talon card one-hot, column 54 = "in the chosen group"
+//    (only once the exchange is in the history; Solo_brez never has one); Klop [54] multi-hot of the talon cards
+//    revealed so far; Berac none.  zalozil[54] = own discards, only for the seat that exchanged.
+#pragma once
+#include "tarok_kernels.cuh"
+
+namespace tk {
+
+enum : int { NET_KLOP = 0, NET_NAVADNA = 1, NET_SOLO = 2, NET_BERAC = 3 };     // Nevronski_igralec.Tipi_NN
+
+__device__ __forceinline__ u32 net_type_of(u32 contract) {       // tip_igre_v_tip_izbire, Igralec.py:179-188
+    return contract == C_KLOP ? NET_KLOP : is_king_game(contract) ? NET_NAVADNA : is_berac(contract) ? NET_BERAC : NET_SOLO;
+}
+__device__ __forceinline__ u32 history_len(u64 meta) {
+    const u32 contract = mget(meta, M_CONTRACT, 4);
+    u32 n = mget(meta, M_PLAYS, 6);
+    if (mget(meta, M_GROUP, 3) != NO_GROUP) n += 1;                                   // the ("Talon", ...) entry
+    if (contract == C_KLOP) n += min(mget(meta, M_TRICKS, 4), 6u);                    // (None, talon card) entries
+    return n;
+}
+__device__ __forceinline__ u32 padded_rows(u32 n) { return n + (8u - (n & 7u)); }
+
+// Per game: net type (0..3, 255 = not waiting for a card) and T, so the host can bucket like predict_igraj_karto.
+__global__ void __launch_bounds__(CTA) k_obs_shape(Env e, uint8_t* __restrict__ type_out, uint8_t* __restrict__ rows_out) {
+    const u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
+    if (g >= e.n) return;
+    const u64 meta = e.meta[g];
+    const bool live = mget(meta, M_PHASE, 2) == PH_PLAY;
+    type_out[g] = live ? (uint8_t)net_type_of(mget(meta, M_CONTRACT, 4)) : (uint8_t)255;
+    rows_out[g] = live ? (uint8_t)padded_rows(history_len(meta)) : (uint8_t)0;
+}
+
+struct ObsOut {
+    float* opp;      // [n_sel, T, 3, 54]
+    float* hand;     // [n_sel, T, 54]
+    float* talon;    // [n_sel, 6, 55] (Navadna, Solo) | [n_sel, 54] (Klop) | unused (Berac)
+    float* king;     // [n_sel, 4]      (Navadna)
+    float* decl;     // [n_sel, 4]      (Navadna, Solo, Berac)
+    float* discard;  // [n_sel, 54]     (Navadna, Solo)
+    float* mozne;    // [n_sel, 54]
+    uint8_t* ok;     // [n_sel] 1 = game matched (net_type, T) and was expanded
+};
+
+__device__ __forceinline__ void warp_zero(float* p, u32 count, u32 lane) {       // count % 2 == 0, p 8-byte aligned
+    float2* q = reinterpret_cast<float2*>(p);
+    for (u32 i = lane; i < count / 2; i += 32) q[i] = make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ void warp_zero4(float* p, u32 count, u32 lane) {      // count % 4 == 0, p 16-byte aligned
+    float4* q = reinterpret_cast<float4*>(p);
+    for (u32 i = lane; i < count / 4; i += 32) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void warp_bits(float* p, u64 bits, u32 lane) {         // 54 floats from a bitboard
+    p[lane] = (float)((bits >> lane) & 1ull);
+    if (lane + 32 < 54) p[lane + 32] = (float)((bits >> (lane + 32)) & 1ull);
+}
+
+__global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, const int* __restrict__ sel, u64 n_sel,
+                                                    ObsOut o) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;        // one warp per selected game
+    if (i >= n_sel) return;
+    const u64 g = sel ? (u64)sel[i] : i;
+    const u64 na = e.n_alloc;
+    const bool in_range = g < e.n;
+    const u64 meta = in_range ? e.meta[g] : meta_pad();
+    const u32 contract = mget(meta, M_CONTRACT, 4);
+    const u32 plays = mget(meta, M_PLAYS, 6);
+    const bool match = mget(meta, M_PHASE, 2) == PH_PLAY && net_type_of(contract) == (u32)net_type
+                    && padded_rows(history_len(meta)) == T;
+    float* opp = o.opp + i * (u64)T * 162u;
+    float* hand = o.hand + i * (u64)T * 54u;
+    warp_zero4(opp, T * 162u, lane);                                 // T % 8 == 0: both blocks are 16-byte multiples
+    warp_zero4(hand, T * 54u, lane);
+    if (o.talon && net_type != NET_BERAC) warp_zero(o.talon + i * (net_type == NET_KLOP ? 54u : 330u), net_type == NET_KLOP ? 54u : 330u, lane);
+    if (o.king && lane < 4) o.king[i * 4 + lane] = 0.f;
+    if (o.decl && lane < 4) o.decl[i * 4 + lane] = 0.f;
+    if (o.discard) warp_zero(o.discard + i * 54u, 54u, lane);
+    if (o.mozne) warp_zero(o.mozne + i * 54u, 54u, lane);
+    if (o.ok && lane == 0) o.ok[i] = match ? 1 : 0;
+    __syncwarp();                                                    // zero fill ordered before the ones below
+    if (!match) return;
+
+    const u32 self = mover_of(meta);
+    const u32 decl = mget(meta, M_DECL, 2);
+    // the two history slots of this lane: plays lane and lane + 32
+    u32 h0 = 0xFF, h1 = 0xFF;
+    if (lane < plays) h0 = e.hist[(u64)lane * na + g];
+    if (lane + 32 < plays) h1 = e.hist[(u64)(lane + 32) * na + g];
+    const bool own0 = h0 != 0xFF && (h0 >> 6) == self, own1 = h1 != 0xFF && (h1 >> 6) == self;
+    // opponents' plays: one 1.0 each
+    if (h0 != 0xFF && !own0) { u32 s = h0 >> 6; opp[(u64)lane * 162u + (s < self ? s : s - 1) * 54u + (h0 & 63u)] = 1.f; }
+    if (h1 != 0xFF && !own1) { u32 s = h1 >> 6; opp[(u64)(lane + 32) * 162u + (s < self ? s : s - 1) * 54u + (h1 & 63u)] = 1.f; }
+    // own plays: exclusive prefix-OR of the own cards played before each row (warp scan over 64 slots)
+    u64 b0 = own0 ? 1ull << (h0 & 63u) : 0ull, b1 = own1 ? 1ull << (h1 & 63u) : 0ull;
+    u64 inc0 = b0, inc1 = b1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t0 = __shfl_up_sync(0xFFFFFFFFu, inc0, d), t1 = __shfl_up_sync(0xFFFFFFFFu, inc1, d);
+        if (lane >= (u32)d) { inc0 |= t0; inc1 |= t1; }
+    }
+    const u64 all0 = __shfl_sync(0xFFFFFFFFu, inc0, 31);
+    const u64 before0 = inc0 & ~b0, before1 = (all0 | inc1) & ~b1;   // own cards are distinct, so "& ~own" = exclusive
+    const u64 dealt = e.hands0[self * na + g];
+    u32 rows0 = __ballot_sync(0xFFFFFFFFu, own0), rows1 = __ballot_sync(0xFFFFFFFFu, own1);
+    while (rows0) {
+        const u32 src = __ffs(rows0) - 1; rows0 &= rows0 - 1;
+        warp_bits(hand + (u64)src * 54u, dealt & ~__shfl_sync(0xFFFFFFFFu, before0, src), lane);
+    }
+    while (rows1) {
+        const u32 src = __ffs(rows1) - 1; rows1 &= rows1 - 1;
+        warp_bits(hand + (u64)(src + 32) * 54u, dealt & ~__shfl_sync(0xFFFFFFFFu, before1, src), lane);
+    }
+    // small vectors
+    const u64 order = e.torder[g];
+    if (o.talon && net_type == NET_KLOP) {
+        const u32 shown = min(mget(meta, M_TRICKS, 4), 6u);           // Klop.py:69 pops from the end
+        if (lane < shown) o.talon[i * 54u + ((order >> (6 * (5 - lane))) & 63ull)] = 1.f;
+    } else if (o.talon && (net_type == NET_NAVADNA || net_type == NET_SOLO)) {
+        const u32 grp = mget(meta, M_GROUP, 3), k = talon_k(contract);
+        if (grp != NO_GROUP && lane < 6) {
+            float* row = o.talon + i * 330u + lane * 55u;
+            row[(order >> (6 * lane)) & 63ull] = 1.f;
+            if (lane / k == grp) row[54] = 1.f;
+        }
+    }
+    if (o.king && lane == 0) { u32 kg = mget(meta, M_KING, 3); if (kg < 4) o.king[i * 4 + kg] = 1.f; }
+    if (o.decl && lane == 0) o.decl[i * 4 + (decl == self ? 3u : (decl < self ? decl : decl - 1))] = 1.f;
+    if (o.discard && self == decl && mget(meta, M_GROUP, 3) != NO_GROUP) warp_bits(o.discard + i * 54u, e.discard[g], lane);
+    if (o.mozne) warp_bits(o.mozne + i * 54u, e.mask[g], lane);
+}
+
+}  // namespace tk

@@ -247,6 +247,42 @@ class TarokEnv:
             self._h, hp(perm), hp(contract), hp(declarer), hp(king), int(first_game_id), 1 if fused else 0,
             hp(scores_out), hp(stats_out), self._stream()))
 
+    # ------------------------------------------------------------------ observations (Igralec.py:453-533)
+    def obs_shape(self):
+        """Per game: (net type uint8 [n] -- 0 Klop 1 Navadna_igra 2 Solo 3 Berac, 255 = not to move; T uint8 [n])."""
+        t = torch.empty(self.n, dtype=torch.uint8, device=self.torch_device)
+        r = torch.empty(self.n, dtype=torch.uint8, device=self.torch_device)
+        self._check(self._lib.tarok_obs_shape(self._h, C.c_void_p(t.data_ptr()), C.c_void_p(r.data_ptr()), self._stream()))
+        return t, r
+
+    def obs_expand(self, net_type: int, rows: int, sel=None):
+        """The network inputs of ``Nevronski_igralec.stanje_v_vektor_rek_navadna`` for the seat to move of the
+        selected games (int32 indices; None = all), as fp32 tensors in the reference's list order
+        (A.4): Navadna [opp, king, hand, talon, decl, discard, mozne]; Solo [opp, hand, talon, decl, discard, mozne];
+        Klop [opp, hand, talon, mozne]; Berac [opp, hand, decl, mozne].  Returns (list of tensors, ok uint8 [n_sel])."""
+        if not self.history:
+            raise ValueError("observations need TarokEnv(..., history=True)")
+        if sel is None:
+            n_sel, sel_ptr = self.n, None
+        else:
+            sel = torch.as_tensor(sel, dtype=torch.int32, device=self.torch_device).contiguous()
+            n_sel, sel_ptr = int(sel.numel()), C.c_void_p(sel.data_ptr())
+        dev, f = self.torch_device, torch.float32
+        opp = torch.empty((n_sel, rows, 3, 54), dtype=f, device=dev)
+        hand = torch.empty((n_sel, rows, 54), dtype=f, device=dev)
+        talon = torch.empty((n_sel, 54) if net_type == 0 else (n_sel, 6, 55), dtype=f, device=dev) if net_type != 3 else None
+        king = torch.empty((n_sel, 4), dtype=f, device=dev) if net_type == 1 else None
+        decl = torch.empty((n_sel, 4), dtype=f, device=dev) if net_type != 0 else None
+        disc = torch.empty((n_sel, 54), dtype=f, device=dev) if net_type in (1, 2) else None
+        mozne = torch.empty((n_sel, 54), dtype=f, device=dev)
+        ok = torch.empty(n_sel, dtype=torch.uint8, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self._check(self._lib.tarok_obs_expand(self._h, int(net_type), int(rows), sel_ptr, n_sel, p(opp), p(hand), p(talon),
+                                               p(king), p(decl), p(disc), p(mozne), p(ok), self._stream()))
+        order = {1: [opp, king, hand, talon, decl, disc, mozne], 2: [opp, hand, talon, decl, disc, mozne],
+                 0: [opp, hand, talon, mozne], 3: [opp, hand, decl, mozne]}[int(net_type)]
+        return order, ok
+
     # ------------------------------------------------------------------ helpers
     def errors(self) -> int:
         """Number of games whose error bit is set (illegal action / invalid exchange / bad deal)."""

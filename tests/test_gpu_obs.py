@@ -1,0 +1,56 @@
+"""GPU: observation expansion (tarok_obs_expand) against observations frozen from the REAL reference's
+Nevronski_igralec.stanje_v_vektor_rek_navadna (tests/golden/obs.npz, made by oracle/make_golden_obs.py).
+Bit-exact: every entry of every input array is 0/1."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_observations_match_reference(golden):
+    import torch
+    from tarok_b200.env import TarokEnv
+    g = golden("obs.npz")
+    n = len(g["perm"])
+    env = TarokEnv(n, history=True)
+    env.set_deals(g["perm"])
+    env.force_contract(g["contract"], g["declarer"], g["king"])
+    env.exchange(g["group"], g["discard_mask"])
+    assert env.errors() == 0
+    idx = g["obs_index"]                                   # (game, play, seat, T, kind, packed bytes)
+    row_of = {(int(r[0]), int(r[1])): k for k, r in enumerate(idx)}
+    off, bits = g["obs_offset"], g["obs_bits"]
+    checked = 0
+    for t in range(48):
+        kinds, rows = env.obs_shape()
+        kinds, rows = kinds.cpu().numpy(), rows.cpu().numpy()
+        live = kinds != 255
+        for kind in range(4):
+            for T in np.unique(rows[live & (kinds == kind)]):
+                sel = np.nonzero(live & (kinds == kind) & (rows == T))[0].astype(np.int32)
+                arrs, ok = env.obs_expand(kind, int(T), sel)
+                assert ok.cpu().numpy().all()
+                arrs = [a.cpu().numpy() for a in arrs]
+                for j, game in enumerate(sel):
+                    k = row_of[(int(game), t)]
+                    assert idx[k][3] == T and idx[k][4] == kind, (game, t)
+                    flat = np.concatenate([a[j].reshape(-1) for a in arrs])
+                    assert set(np.unique(flat)) <= {0.0, 1.0}
+                    want = np.unpackbits(bits[off[k]:off[k + 1]])[:flat.size]
+                    assert (flat.astype(np.uint8) == want).all(), (int(game), t, kind, int(T))
+                    checked += 1
+        env.step(g["card"][:, t])
+    assert env.errors() == 0
+    assert checked == len(idx)
+    # a bucket that does not match is reported, not silently filled
+    arrs, ok = env.obs_expand(1, 8, np.arange(4, dtype=np.int32))
+    assert not ok.cpu().numpy().any() and float(arrs[0].abs().sum()) == 0.0
+    env.close()
+
+
+def test_observations_need_history():
+    from tarok_b200.env import TarokEnv
+    env = TarokEnv(64)
+    with pytest.raises(ValueError):
+        env.obs_expand(0, 8)
+    env.close()
