@@ -164,6 +164,13 @@ int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel
                      float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev, float* discard_dev,
                      float* mozne_dev, uint8_t* ok_dev, void* stream);
 
+/* Action selection: Nevronski_igralec.igraj_karto (Igralec.py:344-355).  q_dev: fp32 [n_sel,54] network outputs
+   for the selected games; writes card_dev[game] (uint8 [n_games], indexed by GAME, ready for tarok_step; 0xFF for
+   games not to move) = first argmax over the legal cards in the reference's `mozne` order, or with probability
+   random_card a uniform legal card (Philox stream 8); qmax_dev[game] (fp32 [n_games], optional) = next_Q_max. */
+int tarok_select_action(tarok_t* h, const float* q_dev, const int32_t* sel_dev, uint64_t n_sel, float random_card,
+                        uint8_t* card_dev, float* qmax_dev, void* stream);
+
 /* ---- zero-copy views ------------------------------------------------------------------------- */
 /* Lends a field as a DLPack tensor that aliases the handle's device memory.  The caller (e.g.
    torch.from_dlpack) must call the deleter; the handle cannot be destroyed before that. */

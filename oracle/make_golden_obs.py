@@ -64,9 +64,17 @@ def make_obs_player(ref, rng, log):
                                    shapes=[tuple(a.shape[1:]) for a in arrs], bits=np.packbits(flat.astype(np.uint8))))
 
         def igraj_karto(self, karte_na_mizi, mozne, zgodovina, id_igre):
-            karta = mozne[rng.randrange(len(mozne))]
+            # the card is chosen by the REFERENCE's own action selection (Igralec.py:344-355) from a fake network
+            # output with few distinct values, so that argmax ties (broken by the order of `mozne`) are exercised
+            import torch
+            q = np.array([rng.randrange(3) for _ in range(54)], np.float32)
+            self.predicted_resoult[self.tip_igre[id_igre]][id_igre] = torch.from_numpy(q)
+            self.random_card = 0.0
+            karta = NN.igraj_karto(self, karte_na_mizi, mozne, zgodovina, id_igre)
             log["cards"].append(karta.v_id())
-            return Base.igraj_karto(self, karta, id_igre)
+            log["q"].append(q)
+            log["qmax"].append(float(self.next_Q_max[id_igre]))
+            return karta
 
         def rezultat_stiha(self, stih, sem_pobral, id_igre):
             pass
@@ -82,7 +90,7 @@ def make_obs_player(ref, rng, log):
 
 def run_game(ref, rng, perm, contract, declarer, king):
     Tip = ref.Tip_igre.Tip_igre
-    log = dict(obs=[], cards=[], group=0xFF, discard=0)
+    log = dict(obs=[], cards=[], q=[], qmax=[], group=0xFF, discard=0)
     P = make_obs_player(ref, rng, log)
     players = [P(s) for s in range(4)]
     H.inject_deal(ref, perm)
@@ -105,7 +113,7 @@ def run_game(ref, rng, perm, contract, declarer, king):
 def main(per_contract=6, seed=424242):
     ref = H.load_reference()
     rng = random.Random(seed)
-    games, obs_rows, blobs = [], [], []
+    games, obs_rows, blobs, qs, qmaxs = [], [], [], [], []
     for c in range(10):
         done = 0
         while done < per_contract:
@@ -124,6 +132,8 @@ def main(per_contract=6, seed=424242):
             for t, o in enumerate(log["obs"]):
                 obs_rows.append((gi, t, o["seat"], o["T"], o["kind"], len(o["bits"])))
                 blobs.append(o["bits"])
+                qs.append(log["q"][t])
+                qmaxs.append(log["qmax"][t])
             done += 1
     off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])]).astype(np.int64)
     np.savez_compressed(
@@ -133,7 +143,8 @@ def main(per_contract=6, seed=424242):
         group=np.array([g["group"] for g in games], np.uint8), discard_mask=np.array([g["discard"] for g in games], np.uint64),
         card=np.array([g["cards"] for g in games], np.uint8),
         obs_index=np.array(obs_rows, np.int32),          # (game, play, seat, T, kind, packed bytes)
-        obs_offset=off, obs_bits=np.concatenate(blobs))
+        obs_offset=off, obs_bits=np.concatenate(blobs),
+        q=np.array(qs, np.float32), qmax=np.array(qmaxs, np.float32))       # fake net outputs -> reference's choice = card
     print("obs.npz: %d games, %d observations, %d packed bytes" % (len(games), len(obs_rows), off[-1]))
 
 

@@ -514,6 +514,22 @@ int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel
     return 0;
 }
 
+int tarok_select_action(tarok_t* h, const float* q_dev, const int32_t* sel_dev, uint64_t n_sel, float random_card,
+                        uint8_t* card_dev, float* qmax_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!q_dev || !card_dev) return fail(h, -1, "q_dev/card_dev is null");
+    if (!(random_card >= 0.f && random_card <= 1.f)) return fail(h, -1, "random_card must be in [0,1]");
+    if (n_sel == 0) return 0;
+    DeviceGuard dg(h->device);
+    const double thr = (double)random_card * 4294967296.0;
+    const u32 threshold = thr >= 4294967295.0 ? 0xFFFFFFFFu : (u32)thr;
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_select_action<<<(unsigned)((n_sel + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, q_dev, (const int*)sel_dev, n_sel, threshold, card_dev, qmax_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
 // ---- zero-copy views ------------------------------------------------------------------------------------
 
 struct ExportCtx {

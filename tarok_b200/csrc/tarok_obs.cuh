@@ -143,4 +143,69 @@ __global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, 
     if (o.mozne) warp_bits(o.mozne + i * 54u, e.mask[g], lane);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Action selection on the device: Nevronski_igralec.igraj_karto (Igralec.py:344-355).
+//   id = argmax(p[mozne_id]); karta = mozne[id]; next_Q_max = p[karta]; with probability random_card a uniform
+//   legal card instead.  np.argmax returns the FIRST maximum in the order of the list `mozne`, so ties are broken
+//   by that order (A.2): when following suit / trumping it is the player's suit list -- the cards as dealt in
+//   ascending order, then the cards picked up from the talon in talon order (Roka.py:10-11,19-21); otherwise all
+//   cards sorted ascending.  One warp per game; lanes hold cards lane and lane+32.
+// ------------------------------------------------------------------------------------------------
+enum : u32 { ST_EXPLORE = 8 };
+
+__global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __restrict__ q, const int* __restrict__ sel,
+                                                       u64 n_sel, u32 explore_threshold, uint8_t* __restrict__ card_out,
+                                                       float* __restrict__ qmax_out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_sel) return;
+    const u64 g = sel ? (u64)sel[i] : i;
+    if (g >= e.n) return;
+    const u64 na = e.n_alloc;
+    const u64 meta = e.meta[g];
+    if (mget(meta, M_PHASE, 2) != PH_PLAY) { if (lane == 0) card_out[g] = 0xFF; return; }
+    const u64 legal = e.mask[g];
+    const u32 self = mover_of(meta);
+    const u32 pos = mget(meta, M_POS, 2), lead = mget(meta, M_TRICK, 6);
+    const u64 hand = e.hands[self * na + g];
+    // is `mozne` one of the player's own suit lists (list order) or the sorted union (id order)?
+    bool list_order = false;
+    if (pos != 0) list_order = (hand & suit_mask_of(lead)) != 0 || (hand & TAROKS) != 0;
+    const u64 dealt = e.hands0 ? e.hands0[self * na + g] : ~0ull;
+    const u64 order = e.torder[g];
+    float best = -3.4e38f;
+    u32 best_key = 0xFFFFFFFFu, best_card = 0xFF;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const u32 c = lane + 32u * h;
+        if (c < 54 && ((legal >> c) & 1ull)) {
+            u32 key = c;
+            if (list_order && !((dealt >> c) & 1ull)) {          // picked up from the talon: after the dealt cards
+                u32 tp = 0;
+                for (u32 j = 0; j < 6; j++) if (((order >> (6 * j)) & 63ull) == c) tp = j;
+                key = 64u + tp;
+            }
+            const float v = q[i * 54u + c];
+            if (v > best || (v == best && key < best_key)) { best = v; best_key = key; best_card = c; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const float ov = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+        const u32 ok = __shfl_xor_sync(0xFFFFFFFFu, best_key, d), oc = __shfl_xor_sync(0xFFFFFFFFu, best_card, d);
+        if (ov > best || (ov == best && ok < best_key)) { best = ov; best_key = ok; best_card = oc; }
+    }
+    if (lane == 0) {
+        u32 card = best_card;
+        if (explore_threshold) {                                  // random.random() < random_card (Igralec.py:352-353)
+            const u64 gid = e.first_gid + g;
+            const u32 plays = mget(meta, M_PLAYS, 6);
+            Words4 b = philox_block(e.rng, gid, ST_EXPLORE, plays);
+            if (b.w[0] < explore_threshold) card = nth_set_bit(legal, draw_from_word(b.w[1], e.rng, gid, ST_EXPLORE, plays * 4 + 1, (u32)__popcll(legal)));
+        }
+        card_out[g] = (uint8_t)card;
+        if (qmax_out) qmax_out[g] = best;                         // next_Q_max = p[argmax card] (Igralec.py:351)
+    }
+}
+
 }  // namespace tk

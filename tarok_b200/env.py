@@ -190,8 +190,12 @@ class TarokEnv:
 
     def step(self, cards):
         """One card per live game (``igraj_karto``); cards: uint8 [n] card ids."""
-        x = self._dev_u8(cards, (self.n,))
-        if self.n_alloc != self.n:   # kernel reads two actions per lane
+        if isinstance(cards, torch.Tensor) and cards.dtype == torch.uint8 and cards.device == self.torch_device \
+                and cards.is_contiguous() and cards.numel() == self.n_alloc:
+            x = cards                    # already padded to the kernel tile (e.g. from select_action)
+        else:
+            x = self._dev_u8(cards, (self.n,))
+        if x.numel() != self.n_alloc:    # kernel reads two actions per lane
             pad = torch.zeros(self.n_alloc, dtype=torch.uint8, device=self.torch_device)
             pad[: self.n] = x
             x = pad
@@ -282,6 +286,26 @@ class TarokEnv:
         order = {1: [opp, king, hand, talon, decl, disc, mozne], 2: [opp, hand, talon, decl, disc, mozne],
                  0: [opp, hand, talon, mozne], 3: [opp, hand, decl, mozne]}[int(net_type)]
         return order, ok
+
+    def select_action(self, q, sel=None, random_card: float = 0.0, cards=None, qmax=None):
+        """``Nevronski_igralec.igraj_karto`` (Igralec.py:344-355) for the selected games: first argmax of ``q`` (fp32
+        [n_sel,54]) over the legal cards in the reference's ``mozne`` order, epsilon-greedy with ``random_card``.
+        Writes into ``cards`` (uint8 [n], by game index; allocated if None) and returns (cards, qmax)."""
+        q = q.to(device=self.torch_device, dtype=torch.float32).contiguous()
+        if sel is None:
+            n_sel, sel_ptr = self.n, None
+        else:
+            sel = torch.as_tensor(sel, dtype=torch.int32, device=self.torch_device).contiguous()
+            n_sel, sel_ptr = int(sel.numel()), C.c_void_p(sel.data_ptr())
+        if tuple(q.shape) != (n_sel, 54):
+            raise ValueError("q must have shape (n_sel, 54)")
+        if cards is None:
+            cards = torch.full((self.n_alloc,), 0xFF, dtype=torch.uint8, device=self.torch_device)
+        if qmax is None:
+            qmax = torch.zeros(self.n, dtype=torch.float32, device=self.torch_device)
+        self._check(self._lib.tarok_select_action(self._h, C.c_void_p(q.data_ptr()), sel_ptr, n_sel, float(random_card),
+                                                  C.c_void_p(cards.data_ptr()), C.c_void_p(qmax.data_ptr()), self._stream()))
+        return cards, qmax
 
     # ------------------------------------------------------------------ helpers
     def errors(self) -> int:

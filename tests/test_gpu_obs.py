@@ -39,12 +39,40 @@ def test_observations_match_reference(golden):
                     want = np.unpackbits(bits[off[k]:off[k + 1]])[:flat.size]
                     assert (flat.astype(np.uint8) == want).all(), (int(game), t, kind, int(T))
                     checked += 1
-        env.step(g["card"][:, t])
+        # the reference chose its card from the (tie-prone) fake net output q: the device selection must agree
+        live_games = np.nonzero(live)[0].astype(np.int32)
+        if len(live_games):
+            qrows = np.stack([g["q"][row_of[(int(game), t)]] for game in live_games])
+            cards, qmax = env.select_action(torch.from_numpy(qrows), live_games)
+            got = cards[:n].cpu().numpy()
+            assert (got[live_games] == g["card"][live_games, t]).all(), t
+            want_q = np.array([g["qmax"][row_of[(int(game), t)]] for game in live_games], np.float32)
+            assert (qmax.cpu().numpy()[live_games] == want_q).all()
+            env.step(cards)
     assert env.errors() == 0
     assert checked == len(idx)
     # a bucket that does not match is reported, not silently filled
     arrs, ok = env.obs_expand(1, 8, np.arange(4, dtype=np.int32))
     assert not ok.cpu().numpy().any() and float(arrs[0].abs().sum()) == 0.0
+    env.close()
+
+
+def test_epsilon_greedy_explores_uniformly_over_legal_cards():
+    import torch
+    from tarok_b200.env import TarokEnv
+    n = 200000
+    env = TarokEnv(n, seed=12, history=True)
+    env.setup_synth(0)                                   # Klop: seat 0 leads with 12 cards (11 legal if it holds the pagat)
+    q = torch.zeros((n, 54), dtype=torch.float32, device="cuda")
+    greedy, _ = env.select_action(q, random_card=0.0)
+    mixed, _ = env.select_action(q, random_card=0.5)
+    mask = env.mask[:n].cpu().numpy().view(np.uint64)
+    gc, mc = greedy[:n].cpu().numpy(), mixed[:n].cpu().numpy()
+    assert ((mask >> gc.astype(np.uint64)) & np.uint64(1)).all() and ((mask >> mc.astype(np.uint64)) & np.uint64(1)).all()
+    lowest = np.array([int(x & -x).bit_length() - 1 for x in mask.astype(object)], np.uint8)
+    assert (gc == lowest).all()                          # all-equal q: first card in mozne order = lowest id when leading
+    frac_changed = (mc != gc).mean()                     # explore w.p. 0.5, then uniform over ~11.8 legal cards
+    assert 0.42 < frac_changed < 0.49
     env.close()
 
 
