@@ -302,3 +302,48 @@ def test_no_cpu_fallback_symbols_loaded():
     with open("/proc/self/maps") as f:
         assert "libtarok_b200.so" in f.read()
     env.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 511, 512, 513, 1025])
+def test_ragged_batch_sizes(oracle, n):
+    """Batches that do not fill the 512-game tile (incl. a single game) match the oracle."""
+    for mode in (16, 18):
+        ref = oracle.rollout(5, 40, n, mode)
+        env = _env(n, seed=5, history=True)
+        env.rollout(mode, first_game_id=40)
+        assert (env.scores[:n].cpu().numpy() == ref["scores"]).all()
+        hist = env.hist[:, :n].cpu().numpy().T
+        played = ref["cards"] != 0xFF
+        assert ((hist & 63)[played] == ref["cards"][played]).all()
+        st = env.stats()
+        assert st[19] == ref["stats"][8] and st[18] + st[20] == n
+        env.close()
+
+
+def test_config5_size_properties():
+    """16,777,216 concurrent deals (BASELINE config 5 total) with bidding: size-independent invariants."""
+    import tarok_b200.env as E
+    n = 1 << 24
+    env = _env(n, seed=2026)
+    env.rollout(E.MODE_AUCTION_UNIFORM, first_game_id=0)
+    st = env.stats()
+    assert st[18] + st[20] == n                                   # every deal finished or was flagged
+    assert st[8:18].sum() == st[18] and st[20] < n // 10000
+    assert (st[0:4].sum() == st[4:8].sum())                        # seat sums and player sums are the same total
+    import torch
+    hands = env.hands[:, :n]
+    meta = env.meta[:n]
+    err = ((meta >> E.M_ERR) & 1).bool()
+    berac = (((meta & 15) == 7) | ((meta & 15) == 9))
+    assert bool(((hands != 0).any(dim=0) <= (berac | err)).all())  # only Berac (early stop) leaves cards in hand
+    allc = env.piles[0, :n] | env.piles[1, :n] | env.piles[2, :n] | env.piles[3, :n] | env.talon[:n] \
+        | hands[0] | hands[1] | hands[2] | hands[3]
+    assert bool((allc == ALL54).all())                              # hands, piles and talon partition the deck
+    plays = (meta >> E.M_PLAYS) & 63
+    assert int(plays.sum().item()) == st[19]
+    # fused kernel reproduces the statistics at this size
+    env.reset_stats()
+    env.rollout(E.MODE_AUCTION_UNIFORM, first_game_id=0, fused=True)
+    assert (env.stats()[:21] == st[:21]).all()
+    del hands, meta, err, berac, allc, plays        # zero-copy views must be dropped before the handle can be destroyed
+    env.close()
