@@ -378,6 +378,34 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_config4(args, local_rank):
+    """BASELINE config 4: policy-net forward + GPU env step, 65,536 envs per GPU (informational; one JSON line)."""
+    import torch
+    from tarok_b200.samoigra import Samoigra
+    torch.cuda.set_device(local_rank)
+    n = args.games if args.games != (1 << 20) else 65536
+    s = Samoigra(n, device=local_rank, seed=SEED, random_card=0.05)
+    for i in range(2):
+        s.odigraj(i * n)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    steps, parts = 0, {}
+    for i in range(args.steps):
+        st, ms = s.odigraj((2 + i) * n, meri=True)
+        steps += int(st[19])
+        for k, v in ms.items():
+            parts[k] = parts.get(k, 0.0) + v
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "env_steps_per_sec", "value": steps / dt, "unit": "env-steps/s", "n_gpus": 1, "steps": args.steps,
+                      "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "dtype": "u64 env / fp32 nets", "data": "synthetic",
+                      "config": {"workload": "config 4: self-play, restated policy nets (random init) forward + GPU env step, %d envs" % n},
+                      "device_ms_per_rollout": {k: v / args.steps for k, v in parts.items()},
+                      "note": "env = deal/auction/exchange/step/score kernels; obs = obs_shape/obs_expand/bucketing; forward = the "
+                              "reference-architecture nets (cuDNN LSTM, out of scope to accelerate); select = action-selection kernels"}))
+    s.zapri()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -388,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-large", action="store_true")
+    ap.add_argument("--config", type=int, default=2, help="2 (default, the headline workload) or 4 (neural self-play)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -395,6 +424,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.config == 4:
+        if rank == 0:
+            args.steps = min(args.steps, 5) if args.steps == 100 else args.steps
+            run_config4(args, local_rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         print("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus, file=sys.stderr)

@@ -171,6 +171,18 @@ int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel
 int tarok_select_action(tarok_t* h, const float* q_dev, const int32_t* sel_dev, uint64_t n_sel, float random_card,
                         uint8_t* card_dev, float* qmax_dev, void* stream);
 
+/* Bidding / exchange side of the neural player.
+   tarok_obs_hands: pripavi_licitiram (Igralec.py:278-281), out_dev fp32 [n_games,4,54] = every seat's hand.
+   tarok_obs_exchange: menjaj_talon_v_vektor (Igralec.py:535-543) for games waiting for an exchange:
+     hand [n_sel,54] (declarer), talon [n_sel,54,6] (card x group), game [n_sel,15] one-hot.
+   tarok_select_exchange: menjaj_iz_talona (Igralec.py:365-385) from the 60 network outputs p_dev [n_sel,60]:
+     group_dev[game] (uint8 [n_games]) and discard_dev[game] (uint64 [n_games]) ready for tarok_exchange. */
+int tarok_obs_hands(tarok_t* h, float* out_dev, void* stream);
+int tarok_obs_exchange(tarok_t* h, const int32_t* sel_dev, uint64_t n_sel, float* hand_dev, float* talon_dev, float* game_dev,
+                       uint8_t* ok_dev, void* stream);
+int tarok_select_exchange(tarok_t* h, const float* p_dev, const int32_t* sel_dev, uint64_t n_sel, float random_card,
+                          uint8_t* group_dev, uint64_t* discard_dev, void* stream);
+
 /* ---- zero-copy views ------------------------------------------------------------------------- */
 /* Lends a field as a DLPack tensor that aliases the handle's device memory.  The caller (e.g.
    torch.from_dlpack) must call the deleter; the handle cannot be destroyed before that. */

@@ -33,26 +33,32 @@ def make_obs_player(ref, rng, log):
 
         # ---- decisions are scripted; everything else is the reference's own code ----
         def pripravi_izbral_iz_talona(self, talon, st_kart, id_igre):
-            pass
+            NN.pripravi_izbral_iz_talona(self, talon, st_kart, id_igre)      # reference: menjaj_talon_v_vektor (Igralec.py:357-360)
+            st = self.zalaganje2tocke[id_igre][0]
+            flat = np.concatenate([np.asarray(a, np.float64).reshape(-1) for a in st[:3]])
+            assert set(np.unique(flat)) <= {0.0, 1.0}
+            log["xobs"] = np.packbits(flat.astype(np.uint8))
 
         def predict_izberi_iz_talona(self):
-            pass
+            self.predict_queue["Zalaganje"] = []
 
         def predict_igraj_karto(self):
             for k in self.predict_queue:
                 self.predict_queue[k] = []
 
         def menjaj_iz_talona(self, kupcki, st_kart, id_igre):
-            g = rng.randrange(len(kupcki))
-            self.roka[id_igre].dodaj_karte(kupcki[g])
-            mozno = self.roka[id_igre].mozno_zalozit()
-            zalozi = rng.sample(mozno, st_kart)
-            self.kupcek[id_igre].extend(zalozi)
-            self.zalozil[id_igre] = True                                     # Igralec.py:380
-            for k in zalozi:
-                self.roka[id_igre].igraj_karto(k)
-            self.zalaganje2tocke[id_igre] = [None, zalozi, st_kart, None, mozno]   # Igralec.py:384
-            log["group"], log["discard"] = g, H.cards_to_mask(zalozi)
+            # the REFERENCE's own decision code (Igralec.py:365-385) on a fake, tie-prone network output
+            import torch
+            # card scores are distinct (np.argsort's order among equal values depends on the numpy build: SIMD sorts are
+            # not stable), group scores are tie-prone (np.argmax = first maximum is well defined)
+            cards_part = list(range(54))
+            rng.shuffle(cards_part)
+            pvec = np.array(cards_part + [rng.randrange(3) for _ in range(6)], np.float32)
+            self.predicted_resoult["Zalaganje"][id_igre] = torch.from_numpy(pvec)
+            self.random_card = 0.0
+            g = int(NN.menjaj_iz_talona(self, kupcki, st_kart, id_igre))
+            log["group"], log["discard"] = g, H.cards_to_mask(self.zalaganje2tocke[id_igre][1])
+            log["xp"] = pvec
             return g
 
         def pripravi_igraj_karto(self, karte_na_mizi, mozne, zgodovina, id_igre):
@@ -90,7 +96,7 @@ def make_obs_player(ref, rng, log):
 
 def run_game(ref, rng, perm, contract, declarer, king):
     Tip = ref.Tip_igre.Tip_igre
-    log = dict(obs=[], cards=[], q=[], qmax=[], group=0xFF, discard=0)
+    log = dict(obs=[], cards=[], q=[], qmax=[], group=0xFF, discard=0, xobs=None, xp=None)
     P = make_obs_player(ref, rng, log)
     players = [P(s) for s in range(4)]
     H.inject_deal(ref, perm)
@@ -128,7 +134,8 @@ def main(per_contract=6, seed=424242):
             gi = len(games)
             cards = log["cards"] + [0xFF] * (48 - len(log["cards"]))
             games.append(dict(perm=perm, contract=c, declarer=d, king=k, group=log["group"], discard=log["discard"],
-                              cards=cards))
+                              cards=cards, xobs=log["xobs"] if log["xobs"] is not None else np.zeros(50, np.uint8),
+                              xp=log["xp"] if log["xp"] is not None else np.zeros(60, np.float32)))
             for t, o in enumerate(log["obs"]):
                 obs_rows.append((gi, t, o["seat"], o["T"], o["kind"], len(o["bits"])))
                 blobs.append(o["bits"])
@@ -142,6 +149,7 @@ def main(per_contract=6, seed=424242):
         declarer=np.array([g["declarer"] for g in games], np.uint8), king=np.array([g["king"] for g in games], np.uint8),
         group=np.array([g["group"] for g in games], np.uint8), discard_mask=np.array([g["discard"] for g in games], np.uint64),
         card=np.array([g["cards"] for g in games], np.uint8),
+        exch_obs_bits=np.array([g["xobs"] for g in games], np.uint8), exch_p=np.array([g["xp"] for g in games], np.float32),
         obs_index=np.array(obs_rows, np.int32),          # (game, play, seat, T, kind, packed bytes)
         obs_offset=off, obs_bits=np.concatenate(blobs),
         q=np.array(qs, np.float32), qmax=np.array(qmaxs, np.float32))       # fake net outputs -> reference's choice = card

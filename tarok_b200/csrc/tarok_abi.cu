@@ -530,6 +530,45 @@ int tarok_select_action(tarok_t* h, const float* q_dev, const int32_t* sel_dev, 
     return 0;
 }
 
+int tarok_obs_hands(tarok_t* h, float* out_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!out_dev) return fail(h, -1, "out_dev is null");
+    DeviceGuard dg(h->device);
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_obs_hands<<<(unsigned)((h->e.n + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(h->e, out_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_obs_exchange(tarok_t* h, const int32_t* sel_dev, uint64_t n_sel, float* hand_dev, float* talon_dev, float* game_dev,
+                       uint8_t* ok_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!hand_dev || !talon_dev || !game_dev) return fail(h, -1, "hand_dev/talon_dev/game_dev is null");
+    if (n_sel == 0) return 0;
+    DeviceGuard dg(h->device);
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_obs_exchange<<<(unsigned)((n_sel + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, (const int*)sel_dev, n_sel, hand_dev, talon_dev, game_dev, ok_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_select_exchange(tarok_t* h, const float* p_dev, const int32_t* sel_dev, uint64_t n_sel, float random_card,
+                          uint8_t* group_dev, uint64_t* discard_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!p_dev || !group_dev || !discard_dev) return fail(h, -1, "p_dev/group_dev/discard_dev is null");
+    if (!(random_card >= 0.f && random_card <= 1.f)) return fail(h, -1, "random_card must be in [0,1]");
+    if (n_sel == 0) return 0;
+    DeviceGuard dg(h->device);
+    const double thr = (double)random_card * 4294967296.0;
+    const u32 threshold = thr >= 4294967295.0 ? 0xFFFFFFFFu : (u32)thr;
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_select_exchange<<<(unsigned)((n_sel + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, p_dev, (const int*)sel_dev, n_sel, threshold, group_dev, (u64*)discard_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
 // ---- zero-copy views ------------------------------------------------------------------------------------
 
 struct ExportCtx {

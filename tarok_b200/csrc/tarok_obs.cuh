@@ -208,4 +208,119 @@ __global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bidding and talon-exchange side of the neural player.
+//   hand observation (pripavi_licitiram, Igralec.py:278-281): 54 multi-hot of each seat's hand;
+//   exchange observation (menjaj_talon_v_vektor, Igralec.py:535-543): [hand 54, talon (54,6) card x group,
+//     game one-hot 15 (igra_zalozi2index: (Tri|Dve|Ena, suit) -> 0..11, Solo_tri/dve/ena -> 12..14)];
+//   exchange decision (menjaj_iz_talona, Igralec.py:365-385): group = first argmax of p[54:54+groups]; discards =
+//     the st_kart best-valued cards of mozno_zalozit() after the pick-up, np.argsort()[-k:].  Among EQUAL values
+//     numpy's order is build-dependent (its SIMD sorts are not stable), so ties are unpinned; here they go to the later
+//     card in the order of mozno_zalozit (suits in Barva order, inside a suit the hand ascending, then the picked-up
+//     cards in talon order), i.e. what a stable sort gives.  Each of the two choices is replaced by a uniform one
+//     with probability random_card.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA) k_obs_hands(Env e, float* __restrict__ out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (g >= e.n) return;
+    const u64 na = e.n_alloc;
+#pragma unroll
+    for (int s = 0; s < 4; s++) warp_bits(out + (g * 4 + s) * 54u, e.hands[s * na + g], lane);
+}
+
+__global__ void __launch_bounds__(CTA) k_obs_exchange(Env e, const int* __restrict__ sel, u64 n_sel, float* __restrict__ hand,
+                                                      float* __restrict__ talon, float* __restrict__ game, uint8_t* __restrict__ ok) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_sel) return;
+    const u64 g = sel ? (u64)sel[i] : i;
+    const u64 na = e.n_alloc;
+    const u64 meta = g < e.n ? e.meta[g] : meta_pad();
+    const bool match = mget(meta, M_PHASE, 2) == PH_EXCHANGE;
+    warp_zero(hand + i * 54u, 54u, lane);
+    warp_zero(talon + i * 324u, 324u, lane);
+    if (lane < 15) game[i * 15u + lane] = 0.f;
+    if (ok && lane == 0) ok[i] = match ? 1 : 0;
+    __syncwarp();
+    if (!match) return;
+    const u32 contract = mget(meta, M_CONTRACT, 4), decl = mget(meta, M_DECL, 2), king = mget(meta, M_KING, 3);
+    const u32 k = talon_k(contract);
+    warp_bits(hand + i * 54u, e.hands[decl * na + g], lane);
+    const u64 order = e.torder[g];
+    if (lane < 6) talon[i * 324u + ((order >> (6 * lane)) & 63ull) * 6u + lane / k] = 1.f;
+    if (lane == 0) game[i * 15u + (is_king_game(contract) ? (contract - C_TRI) * 4u + king : 12u + (contract - C_SOLO_TRI))] = 1.f;
+}
+
+__global__ void __launch_bounds__(CTA) k_select_exchange(Env e, const float* __restrict__ p, const int* __restrict__ sel, u64 n_sel,
+                                                         u32 explore_threshold, uint8_t* __restrict__ group_out,
+                                                         u64* __restrict__ discard_out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_sel) return;
+    const u64 g = sel ? (u64)sel[i] : i;
+    if (g >= e.n) return;
+    const u64 na = e.n_alloc;
+    const u64 meta = e.meta[g];
+    if (mget(meta, M_PHASE, 2) != PH_EXCHANGE) { if (lane == 0) { group_out[g] = 0xFF; discard_out[g] = 0; } return; }
+    const u32 contract = mget(meta, M_CONTRACT, 4), decl = mget(meta, M_DECL, 2);
+    const u32 k = talon_k(contract), groups = 6u / k;
+    const u64 gid = e.first_gid + g;
+    const unsigned full = 0xFFFFFFFFu;
+    // group: first argmax of p[54 .. 54+groups)
+    float bv = lane < groups ? p[i * 60u + 54u + lane] : -3.4e38f;
+    u32 bi = lane < groups ? lane : 0xFFu;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const float ov = __shfl_xor_sync(full, bv, d);
+        const u32 oi = __shfl_xor_sync(full, bi, d);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    u32 group = bi;
+    Words4 rnd = philox_block(e.rng, gid, ST_EXPLORE, 50u);                       // same words on every lane
+    if (explore_threshold && rnd.w[0] < explore_threshold) group = draw_from_word(rnd.w[1], e.rng, gid, ST_EXPLORE, 201u, groups);
+    const u64 order = e.torder[g];
+    const u64 hand = e.hands[decl * na + g];
+    const u64 gb = talon_group_bits(order, k, group);
+    u64 avail = (hand | gb) & DISCARDABLE;
+    u64 discard = 0;
+    if ((u32)__popcll(avail) < k) { if (lane == 0) { group_out[g] = (uint8_t)group; discard_out[g] = 0; } return; }   // Q19
+    if (explore_threshold && rnd.w[2] < explore_threshold) {                       // random.sample(mozno, st_kart)
+        Words4 r2 = philox_block(e.rng, gid, ST_EXPLORE, 51u);
+        for (u32 j = 0; j < k; j++) {
+            const u32 w = j == 0 ? r2.w[0] : j == 1 ? r2.w[1] : r2.w[2];
+            const u64 bit = 1ull << nth_set_bit(avail, draw_from_word(w, e.rng, gid, ST_EXPLORE, 204u + j, (u32)__popcll(avail)));
+            avail ^= bit; discard |= bit;
+        }
+    } else {
+        for (u32 j = 0; j < k; j++) {                                              // k times: warp arg-max by (value, position)
+            float v = -3.4e38f; u32 key = 0, card = 0xFF;
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const u32 c = lane + 32u * hh;
+                if (c < 54 && ((avail >> c) & 1ull)) {
+                    u32 pos = c & 63u;                                             // hand cards: ascending inside the suit
+                    if (!((hand >> c) & 1ull)) {                                   // picked up: appended in talon order
+                        u32 tp = 0;
+                        for (u32 t = 0; t < 6; t++) if (((order >> (6 * t)) & 63ull) == c) tp = t;
+                        pos = 64u + tp;
+                    }
+                    const u32 kk = ((c >= 32 ? 4u : (c >> 3)) << 8) | pos;
+                    const float pv = p[i * 60u + c];
+                    if (pv > v || (pv == v && kk > key)) { v = pv; key = kk; card = c; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const float ov = __shfl_xor_sync(full, v, d);
+                const u32 ok2 = __shfl_xor_sync(full, key, d), oc = __shfl_xor_sync(full, card, d);
+                if (ov > v || (ov == v && ok2 > key)) { v = ov; key = ok2; card = oc; }
+            }
+            const u64 bit = 1ull << card;
+            avail ^= bit; discard |= bit;
+        }
+    }
+    if (lane == 0) { group_out[g] = (uint8_t)group; discard_out[g] = discard; }
+}
+
 }  // namespace tk

@@ -307,6 +307,42 @@ class TarokEnv:
                                                   C.c_void_p(cards.data_ptr()), C.c_void_p(qmax.data_ptr()), self._stream()))
         return cards, qmax
 
+    def obs_hands(self) -> torch.Tensor:
+        """``pripavi_licitiram`` (Igralec.py:278-281): fp32 [n,4,54], the hand of every seat."""
+        out = torch.empty((self.n, 4, 54), dtype=torch.float32, device=self.torch_device)
+        self._check(self._lib.tarok_obs_hands(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def _sel(self, sel):
+        if sel is None:
+            return self.n, None, None
+        sel = torch.as_tensor(sel, dtype=torch.int32, device=self.torch_device).contiguous()
+        return int(sel.numel()), C.c_void_p(sel.data_ptr()), sel
+
+    def obs_exchange(self, sel=None):
+        """``menjaj_talon_v_vektor`` (Igralec.py:535-543): ([hand (B,54), talon (B,54,6), game (B,15)], ok)."""
+        n_sel, sel_ptr, keep = self._sel(sel)
+        dev, f = self.torch_device, torch.float32
+        hand = torch.empty((n_sel, 54), dtype=f, device=dev)
+        talon = torch.empty((n_sel, 54, 6), dtype=f, device=dev)
+        game = torch.empty((n_sel, 15), dtype=f, device=dev)
+        ok = torch.empty(n_sel, dtype=torch.uint8, device=dev)
+        self._check(self._lib.tarok_obs_exchange(self._h, sel_ptr, n_sel, C.c_void_p(hand.data_ptr()), C.c_void_p(talon.data_ptr()),
+                                                 C.c_void_p(game.data_ptr()), C.c_void_p(ok.data_ptr()), self._stream()))
+        return [hand, talon, game], ok
+
+    def select_exchange(self, p, sel=None, random_card: float = 0.0):
+        """``menjaj_iz_talona`` (Igralec.py:365-385) from the exchange net's 60 outputs: (group uint8 [n], discard int64 [n])."""
+        n_sel, sel_ptr, keep = self._sel(sel)
+        p = p.to(device=self.torch_device, dtype=torch.float32).contiguous()
+        if tuple(p.shape) != (n_sel, 60):
+            raise ValueError("p must have shape (n_sel, 60)")
+        group = torch.full((self.n,), 0xFF, dtype=torch.uint8, device=self.torch_device)
+        discard = torch.zeros(self.n, dtype=torch.int64, device=self.torch_device)
+        self._check(self._lib.tarok_select_exchange(self._h, C.c_void_p(p.data_ptr()), sel_ptr, n_sel, float(random_card),
+                                                    C.c_void_p(group.data_ptr()), C.c_void_p(discard.data_ptr()), self._stream()))
+        return group, discard
+
     # ------------------------------------------------------------------ helpers
     def errors(self) -> int:
         """Number of games whose error bit is set (illegal action / invalid exchange / bad deal)."""

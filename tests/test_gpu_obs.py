@@ -82,3 +82,40 @@ def test_observations_need_history():
     with pytest.raises(ValueError):
         env.obs_expand(0, 8)
     env.close()
+
+
+def test_hand_and_exchange_observations_and_exchange_decision(golden):
+    """pripavi_licitiram / menjaj_talon_v_vektor / menjaj_iz_talona against the reference (obs.npz)."""
+    import torch
+    from tarok_b200.env import TarokEnv
+    g = golden("obs.npz")
+    n = len(g["perm"])
+    env = TarokEnv(n, history=True)
+    env.set_deals(g["perm"])
+    hands = env.obs_hands().cpu().numpy()
+    for s in range(4):                                   # one-hot of perm[12s:12s+12]
+        want = np.zeros((n, 54), np.float32)
+        np.put_along_axis(want, g["perm"][:, 12 * s:12 * s + 12].astype(np.int64), 1.0, axis=1)
+        assert (hands[:, s] == want).all()
+    env.force_contract(g["contract"], g["declarer"], g["king"])
+    ex = np.nonzero((g["contract"] >= 1) & (g["contract"] <= 6))[0].astype(np.int32)
+    (hand, talon, game), ok = env.obs_exchange(ex)
+    assert ok.cpu().numpy().all()
+    flat = torch.cat([hand.flatten(1), talon.flatten(1), game.flatten(1)], dim=1).cpu().numpy().astype(np.uint8)
+    want = np.unpackbits(g["exch_obs_bits"][ex], axis=1)[:, :393]
+    assert (flat == want).all()
+    _, ok_all = env.obs_exchange()                       # games without an exchange are flagged, not filled
+    assert (ok_all.cpu().numpy() == ((g["contract"] >= 1) & (g["contract"] <= 6))).all()
+    group, discard = env.select_exchange(torch.from_numpy(g["exch_p"][ex]), ex)
+    assert (group.cpu().numpy()[ex] == g["group"][ex]).all()
+    assert (discard.cpu().numpy().view(np.uint64)[ex] == g["discard_mask"][ex]).all()
+    env.exchange(group, discard)
+    assert env.errors() == 0
+    # exploring decisions stay valid exchanges
+    env2 = TarokEnv(50000, seed=4, history=True)
+    env2.deal(); env2.force_contract_synth(16)
+    gr, di = env2.select_exchange(torch.zeros((50000, 60)), random_card=1.0)
+    env2.exchange(gr, di)
+    assert env2.errors() <= 2                            # only hands with fewer than k discardable cards (Q19)
+    assert len(torch.unique(gr)) >= 2
+    env.close(); env2.close()
