@@ -197,6 +197,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        from tarok_b200.dist import bind_to_gpu_numa
+        bind_to_gpu_numa(local_rank)              # pinned e2e buffers on the GPU's NUMA node
         dist.init_process_group("nccl", device_id=dev)
     n, mode, total = args.games, args.mode, args.games * world
     env = TarokEnv(n, seed=SEED, device=local_rank)

@@ -22,6 +22,25 @@ def shard(total_games: int, rank: int, world: int) -> Tuple[int, int]:
     return first, base + (1 if rank < rem else 0)
 
 
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that pinned host buffers (and the
+    upload/download DMA of the host-buffer entry point) stay on the GPU's NUMA node.  Best effort."""
+    try:
+        import os
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(device_index)
+        words = N.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return True
+    except Exception:
+        pass
+    return False
+
+
 def allreduce_stats(stats: torch.Tensor) -> torch.Tensor:
     """Sum the statistics vector over all ranks, in place; no-op without an initialised process group."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
