@@ -68,7 +68,8 @@ enum { TAROK_F_HANDS = 0,   /* uint64 [4, n_alloc]  hand bitboard of seat s     
        TAROK_F_HIST = 7,    /* uint8  [48, n_alloc] play t of game g: seat<<6|card, 0xFF = not played        */
        TAROK_F_STATS = 8,   /* int64  [32]          accumulated statistics (layout below)                    */
        TAROK_F_HANDS0 = 9,  /* uint64 [4, n_alloc]  hands as dealt (Nevronski_igralec.zacetna_roka); HISTORY flag */
-       TAROK_F_DISCARD = 10 /* uint64 [n_alloc]     declarer's discards (zalozil); HISTORY flag              */
+       TAROK_F_DISCARD = 10,/* uint64 [n_alloc]     declarer's discards (zalozil); HISTORY flag              */
+       TAROK_F_QMAX_HIST = 11 /* float [48, n_alloc] next_Q_max recorded by tarok_select_action at play t; HISTORY flag */
 };
 /* stats vector: [0..3] score sum by seat, [4..7] score sum by player ((seat+game_id)%4, Tarok.py:34,59-61),
    [8..17] contract histogram, [18] finished deals, [19] env-steps (card plays), [20] error games */
@@ -170,6 +171,19 @@ int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel
    random_card a uniform legal card (Philox stream 8); qmax_dev[game] (fp32 [n_games], optional) = next_Q_max. */
 int tarok_select_action(tarok_t* h, const float* q_dev, const int32_t* sel_dev, uint64_t n_sel, float random_card,
                         uint8_t* card_dev, float* qmax_dev, void* stream);
+
+/* tarok_obs_expand_at: the same arrays as they were at the decision of card play `play` (0..47) of each selected game,
+   for the seat that made that play -- the `stanje` half of a replay sample (mozne_dev is left zero).
+   tarok_targets: Nevronski_igralec.rezultat_stiha / rezultat_igre (Igralec.py:387-446): for finished games, dy_dev fp32
+   [n_sel,48,54] row t = the target vector of card play t (-70 on illegal cards, +-trick value + final_reword_factor *
+   next_Q_max / final score on the played card), seat_dev uint8 [n_sel,48] = the seat that played (0xFF = no play),
+   rows_dev uint8 [n_sel,48] (optional) = the T of that sample's observation.  Uses the next_Q_max values recorded by
+   tarok_select_action (TAROK_F_QMAX_HIST). */
+int tarok_obs_expand_at(tarok_t* h, int play, int net_type, uint32_t rows, const int32_t* sel_dev, uint64_t n_sel,
+                        float* opp_dev, float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev,
+                        float* discard_dev, float* mozne_dev, uint8_t* ok_dev, void* stream);
+int tarok_targets(tarok_t* h, const int32_t* sel_dev, uint64_t n_sel, float final_reword_factor, float* dy_dev,
+                  uint8_t* seat_dev, uint8_t* rows_dev, void* stream);
 
 /* Bidding / exchange side of the neural player.
    tarok_obs_hands: pripavi_licitiram (Igralec.py:278-281), out_dev fp32 [n_games,4,54] = every seat's hand.

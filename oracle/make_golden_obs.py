@@ -82,11 +82,12 @@ def make_obs_player(ref, rng, log):
             log["qmax"].append(float(self.next_Q_max[id_igre]))
             return karta
 
-        def rezultat_stiha(self, stih, sem_pobral, id_igre):
-            pass
-
+        # rezultat_stiha / rezultat_igre are the REFERENCE's own (Igralec.py:387-446): they build the replay samples
         def rezultat_igre(self, st_tock, povzetek_igre, id_igre):
-            pass
+            try:
+                NN.rezultat_igre(self, st_tock, povzetek_igre, id_igre)
+            except KeyError:          # Odprti_berac is not in igra2index (Q20): the reference cannot finish such a game
+                log["targets_ok"] = False
 
         def poglej_karte_odprtega_beraca(self, roka, id_igre):
             pass
@@ -96,7 +97,7 @@ def make_obs_player(ref, rng, log):
 
 def run_game(ref, rng, perm, contract, declarer, king):
     Tip = ref.Tip_igre.Tip_igre
-    log = dict(obs=[], cards=[], q=[], qmax=[], group=0xFF, discard=0, xobs=None, xp=None)
+    log = dict(obs=[], cards=[], q=[], qmax=[], group=0xFF, discard=0, xobs=None, xp=None, targets_ok=True)
     P = make_obs_player(ref, rng, log)
     players = [P(s) for s in range(4)]
     H.inject_deal(ref, perm)
@@ -113,13 +114,20 @@ def run_game(ref, rng, perm, contract, declarer, king):
     else:
         g = ref.Navadna_igra.Navadna_igra(players, Tip(contract * 10), barva, players[declarer], talon, 0)
     list(g.start())
+    # the samples the reference stored: zgodovina[(tip, T)] = [(stanje, dy), ...] per player, in trick order
+    log["dy"] = []
+    for p in players:
+        rows = []
+        for key in sorted(p.zgodovina, key=lambda k: k[1]):
+            rows.extend(dy for _, dy in p.zgodovina[key])
+        log["dy"].append(np.array(rows, np.float32).reshape(-1, 54))
     return log
 
 
 def main(per_contract=6, seed=424242):
     ref = H.load_reference()
     rng = random.Random(seed)
-    games, obs_rows, blobs, qs, qmaxs = [], [], [], [], []
+    games, obs_rows, blobs, qs, qmaxs, dys = [], [], [], [], [], []
     for c in range(10):
         done = 0
         while done < per_contract:
@@ -136,6 +144,15 @@ def main(per_contract=6, seed=424242):
             games.append(dict(perm=perm, contract=c, declarer=d, king=k, group=log["group"], discard=log["discard"],
                               cards=cards, xobs=log["xobs"] if log["xobs"] is not None else np.zeros(50, np.uint8),
                               xp=log["xp"] if log["xp"] is not None else np.zeros(60, np.float32)))
+            tgt = np.full((48, 54), np.nan, np.float32)           # row t = the dy of card play t (seat = obs seat)
+            if log["targets_ok"]:
+                nxt = [0, 0, 0, 0]
+                for t, o in enumerate(log["obs"]):
+                    seat = o["seat"]
+                    if nxt[seat] < len(log["dy"][seat]):
+                        tgt[t] = log["dy"][seat][nxt[seat]]
+                    nxt[seat] += 1
+            dys.append(tgt)
             for t, o in enumerate(log["obs"]):
                 obs_rows.append((gi, t, o["seat"], o["T"], o["kind"], len(o["bits"])))
                 blobs.append(o["bits"])
@@ -152,7 +169,8 @@ def main(per_contract=6, seed=424242):
         exch_obs_bits=np.array([g["xobs"] for g in games], np.uint8), exch_p=np.array([g["xp"] for g in games], np.float32),
         obs_index=np.array(obs_rows, np.int32),          # (game, play, seat, T, kind, packed bytes)
         obs_offset=off, obs_bits=np.concatenate(blobs),
-        q=np.array(qs, np.float32), qmax=np.array(qmaxs, np.float32))       # fake net outputs -> reference's choice = card
+        q=np.array(qs, np.float32), qmax=np.array(qmaxs, np.float32),
+        dy=np.array(dys, np.float32))                     # [games,48,54] the reference's replay targets (NaN = none)       # fake net outputs -> reference's choice = card
     print("obs.npz: %d games, %d observations, %d packed bytes" % (len(games), len(obs_rows), off[-1]))
 
 

@@ -43,6 +43,8 @@ SIGNATURES = {
     "tarok_rollout_host": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _I, _VP, _VP, _VP]),
     "tarok_obs_shape": (_I, [_VP, _VP, _VP, _VP]),
     "tarok_obs_expand": (_I, [_VP, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tarok_obs_expand_at": (_I, [_VP, _I, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tarok_targets": (_I, [_VP, _VP, _U64, C.c_float, _VP, _VP, _VP, _VP]),
     "tarok_select_action": (_I, [_VP, _VP, _VP, _U64, C.c_float, _VP, _VP, _VP]),
     "tarok_obs_hands": (_I, [_VP, _VP, _VP]),
     "tarok_obs_exchange": (_I, [_VP, _VP, _U64, _VP, _VP, _VP, _VP, _VP]),

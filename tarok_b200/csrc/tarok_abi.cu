@@ -145,6 +145,8 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
         TK_ALLOC(h->e.hist, 48 * na);
         TK_ALLOC(h->e.hands0, 4 * na * 8);
         TK_ALLOC(h->e.discard, na * 8);
+        TK_ALLOC(h->e.qmax_hist, 48 * na * 4);
+        cudaMemset(h->e.qmax_hist, 0, 48 * na * 4);
         cudaMemset(h->e.hist, 0xFF, 48 * na);
     }
 #undef TK_ALLOC
@@ -172,7 +174,7 @@ int tarok_destroy(tarok_t* h) {
     DeviceGuard dg(h->device);
     cudaFree(h->e.hands); cudaFree(h->e.piles); cudaFree(h->e.talon); cudaFree(h->e.torder);
     cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats);
-    cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard);
+    cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist);
     if (h->st_perm) {
         cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down);
         cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
@@ -498,7 +500,15 @@ int tarok_obs_shape(tarok_t* h, uint8_t* type_dev, uint8_t* rows_dev, void* stre
 int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel_dev, uint64_t n_sel, float* opp_dev,
                      float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev, float* discard_dev,
                      float* mozne_dev, uint8_t* ok_dev, void* stream) {
+    return tarok_obs_expand_at(h, -1, net_type, rows, sel_dev, n_sel, opp_dev, hand_dev, talon_dev, king_dev, decl_dev,
+                               discard_dev, mozne_dev, ok_dev, stream);
+}
+
+int tarok_obs_expand_at(tarok_t* h, int play, int net_type, uint32_t rows, const int32_t* sel_dev, uint64_t n_sel,
+                        float* opp_dev, float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev,
+                        float* discard_dev, float* mozne_dev, uint8_t* ok_dev, void* stream) {
     TK_CHECK_HANDLE(h);
+    if (play >= 48) return fail(h, -1, "play must be < 48");
     if (!h->e.hist) return fail(h, -1, "observations need TAROK_FLAG_HISTORY at tarok_create");
     if (net_type < 0 || net_type > 3) return fail(h, -1, "net_type must be 0..3");
     if (rows == 0 || (rows & 7u) || rows > 56) return fail(h, -1, "rows must be a multiple of 8 in 8..56");
@@ -509,7 +519,7 @@ int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel
     tk::ObsOut o = {opp_dev, hand_dev, talon_dev, king_dev, decl_dev, discard_dev, mozne_dev, ok_dev};
     const u64 warps_per_cta = tk::CTA / 32;
     tk::k_obs_expand<<<(unsigned)((n_sel + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
-        h->e, net_type, rows, (const int*)sel_dev, n_sel, o);
+        h->e, net_type, rows, (const int*)sel_dev, n_sel, o, play < 0 ? -1 : play);
     TK_LAUNCH_OK(h);
     return 0;
 }
@@ -569,6 +579,21 @@ int tarok_select_exchange(tarok_t* h, const float* p_dev, const int32_t* sel_dev
     return 0;
 }
 
+int tarok_targets(tarok_t* h, const int32_t* sel_dev, uint64_t n_sel, float final_reword_factor, float* dy_dev,
+                  uint8_t* seat_dev, uint8_t* rows_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!h->e.hist) return fail(h, -1, "replay targets need TAROK_FLAG_HISTORY at tarok_create");
+    if (!dy_dev || !seat_dev) return fail(h, -1, "dy_dev/seat_dev is null");
+    if (((uintptr_t)dy_dev) & 15u) return fail(h, -1, "dy_dev must be 16-byte aligned");
+    if (n_sel == 0) return 0;
+    DeviceGuard dg(h->device);
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_targets<<<(unsigned)((n_sel + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, (const int*)sel_dev, n_sel, final_reword_factor, dy_dev, seat_dev, rows_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
 // ---- zero-copy views ------------------------------------------------------------------------------------
 
 struct ExportCtx {
@@ -587,7 +612,7 @@ static void export_deleter(DLManagedTensor* self) {
 static int field_desc(tarok_env* h, int field, void** ptr, int* ndim, int64_t shape[2], DLDataType* dt) {
     const int64_t na = (int64_t)h->e.n_alloc;
     // bitboards are lent as int64 (same bits; torch has no general uint64 support), bit 63 is never set
-    DLDataType u64t = {0, 64, 1}, i16t = {0, 16, 1}, u8t = {1, 8, 1}, i64t = {0, 64, 1};
+    DLDataType u64t = {0, 64, 1}, i16t = {0, 16, 1}, u8t = {1, 8, 1}, i64t = {0, 64, 1}, f32t = {2, 32, 1};
     switch (field) {
         case TAROK_F_HANDS: *ptr = h->e.hands; *ndim = 2; shape[0] = 4; shape[1] = na; *dt = u64t; break;
         case TAROK_F_PILES: *ptr = h->e.piles; *ndim = 2; shape[0] = 4; shape[1] = na; *dt = u64t; break;
@@ -600,6 +625,7 @@ static int field_desc(tarok_env* h, int field, void** ptr, int* ndim, int64_t sh
         case TAROK_F_STATS: *ptr = h->e.stats; *ndim = 1; shape[0] = TAROK_STATS_LEN; *dt = i64t; break;
         case TAROK_F_HANDS0: *ptr = h->e.hands0; *ndim = 2; shape[0] = 4; shape[1] = na; *dt = u64t; break;
         case TAROK_F_DISCARD: *ptr = h->e.discard; *ndim = 1; shape[0] = na; *dt = u64t; break;
+        case TAROK_F_QMAX_HIST: *ptr = h->e.qmax_hist; *ndim = 2; shape[0] = 48; shape[1] = na; *dt = f32t; break;
         default: return fail(h, -1, "unknown field %d", field);
     }
     if (!*ptr) return fail(h, -1, "field %d needs TAROK_FLAG_HISTORY at tarok_create", field);

@@ -21,7 +21,7 @@ constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane 
 
 struct Env {
     u64* hands; u64* piles; u64* talon; u64* torder; u64* meta; u64* mask; u64* scores;
-    uint8_t* hist; u64* hands0; u64* discard; long long* stats;
+    uint8_t* hist; u64* hands0; u64* discard; float* qmax_hist; long long* stats;
     u64 n, n_alloc, first_gid;
     Rng rng;                               // seed + precomputed Philox round keys
 };

@@ -68,16 +68,27 @@ __device__ __forceinline__ void warp_bits(float* p, u64 bits, u32 lane) {       
     if (lane + 32 < 54) p[lane + 32] = (float)((bits >> (lane + 32)) & 1ull);
 }
 
+// `upto` < 0: the observation of the seat to move NOW.  `upto` = t >= 0: the observation the seat that made play t
+// had at that decision (history truncated to the first t plays) -- the `stanje` of a replay sample; the legal-mask
+// vector is not produced in that mode (it is not a network input, Igralec.py:333).
 __global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, const int* __restrict__ sel, u64 n_sel,
-                                                    ObsOut o) {
+                                                    ObsOut o, int upto) {
     const u32 lane = threadIdx.x & 31u;
     const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;        // one warp per selected game
     if (i >= n_sel) return;
     const u64 g = sel ? (u64)sel[i] : i;
     const u64 na = e.n_alloc;
     const bool in_range = g < e.n;
-    const u64 meta = in_range ? e.meta[g] : meta_pad();
+    u64 meta = in_range ? e.meta[g] : meta_pad();
     const u32 contract = mget(meta, M_CONTRACT, 4);
+    u32 self_at = 0;
+    if (upto >= 0) {                                     // rewind the counters of meta to "before play upto"
+        const bool had = (u32)upto < mget(meta, M_PLAYS, 6) && !((meta >> M_ERR) & 1ull);
+        self_at = had ? (u32)(e.hist[(u64)upto * na + g] >> 6) : 0u;
+        meta = mset(meta, M_PLAYS, 6, (u32)upto);
+        meta = mset(meta, M_TRICKS, 4, (u32)upto >> 2);
+        meta = mset(meta, M_PHASE, 2, had ? (u32)PH_PLAY : (u32)PH_DONE);
+    }
     const u32 plays = mget(meta, M_PLAYS, 6);
     const bool match = mget(meta, M_PHASE, 2) == PH_PLAY && net_type_of(contract) == (u32)net_type
                     && padded_rows(history_len(meta)) == T;
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, 
     __syncwarp();                                                    // zero fill ordered before the ones below
     if (!match) return;
 
-    const u32 self = mover_of(meta);
+    const u32 self = upto >= 0 ? self_at : mover_of(meta);
     const u32 decl = mget(meta, M_DECL, 2);
     // the two history slots of this lane: plays lane and lane + 32
     u32 h0 = 0xFF, h1 = 0xFF;
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, 
     if (o.king && lane == 0) { u32 kg = mget(meta, M_KING, 3); if (kg < 4) o.king[i * 4 + kg] = 1.f; }
     if (o.decl && lane == 0) o.decl[i * 4 + (decl == self ? 3u : (decl < self ? decl : decl - 1))] = 1.f;
     if (o.discard && self == decl && mget(meta, M_GROUP, 3) != NO_GROUP) warp_bits(o.discard + i * 54u, e.discard[g], lane);
-    if (o.mozne) warp_bits(o.mozne + i * 54u, e.mask[g], lane);
+    if (o.mozne && upto < 0) warp_bits(o.mozne + i * 54u, e.mask[g], lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +216,7 @@ __global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __res
         }
         card_out[g] = (uint8_t)card;
         if (qmax_out) qmax_out[g] = best;                         // next_Q_max = p[argmax card] (Igralec.py:351)
+        if (e.qmax_hist) e.qmax_hist[(u64)mget(meta, M_PLAYS, 6) * na + g] = best;   // kept for the replay targets
     }
 }
 
@@ -321,6 +333,94 @@ __global__ void __launch_bounds__(CTA) k_select_exchange(Env e, const float* __r
         }
     }
     if (lane == 0) { group_out[g] = (uint8_t)group; discard_out[g] = discard; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Replay targets on the device: Nevronski_igralec.rezultat_stiha / rezultat_igre (Igralec.py:387-446).
+// For every card play t of a finished game the reference stores a sample (stanje, dy) for the seat that played:
+//   dy[c] = -70 for every card that was illegal at that decision (Igralec.py:393);
+//   dy[card] = +vrednost_stiha(trick) if the seat took the trick else -vrednost_stiha(trick)  -- the Klop/Berac
+//     branches compare a dict with a string and are dead (Q18); the 4- or 5-card trick counts sum-2 (Roka.py:92-95);
+//   dy[card] += final_reword_factor * next, next = the seat's next_Q_max at its decision in the FOLLOWING trick, or for
+//     its last sample the final score (st_tock; for Berac non-declarers -20 if all 12 tricks were played else +20,
+//     Igralec.py:433-437).
+// One warp per game replays the game from the hands as dealt + the exchange + the play history (so no per-step mask
+// log is needed) and writes dy rows [48,54] (row t = play t; rows of unplayed slots are zero) plus the seat per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA) k_targets(Env e, const int* __restrict__ sel, u64 n_sel, float factor,
+                                                 float* __restrict__ dy, uint8_t* __restrict__ seat_out,
+                                                 uint8_t* __restrict__ rows_out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_sel) return;
+    const u64 g = sel ? (u64)sel[i] : i;
+    const u64 na = e.n_alloc;
+    float* out = dy + i * (48u * 54u);
+    warp_zero4(out, 48u * 54u, lane);
+    for (u32 t = lane; t < 48; t += 32) { seat_out[i * 48u + t] = 0xFF; if (rows_out) rows_out[i * 48u + t] = 0; }
+    __syncwarp();
+    if (g >= e.n) return;
+    const u64 meta = e.meta[g];
+    if (mget(meta, M_PHASE, 2) != PH_DONE || ((meta >> M_ERR) & 1ull)) return;
+    const u32 contract = mget(meta, M_CONTRACT, 4), decl = mget(meta, M_DECL, 2), plays = mget(meta, M_PLAYS, 6);
+    const u32 grp = mget(meta, M_GROUP, 3);
+    const bool klop = klop_rules(contract);
+    const u64 order = e.torder[g];
+    u64 h0 = e.hands0[g], h1 = e.hands0[na + g], h2 = e.hands0[2 * na + g], h3 = e.hands0[3 * na + g];
+    if (grp != NO_GROUP) {                               // the exchange: group picked up, discards laid down
+        const u64 nh = (sel4(h0, h1, h2, h3, decl) | talon_group_bits(order, talon_k(contract), grp)) & ~e.discard[g];
+        h0 = decl == 0 ? nh : h0; h1 = decl == 1 ? nh : h1; h2 = decl == 2 ? nh : h2; h3 = decl == 3 ? nh : h3;
+    }
+    const u64 sc = e.scores[g];
+    const u32 tricks_total = plays >> 2;
+    const u32 extra = (grp != NO_GROUP ? 1u : 0u);
+    for (u32 k = 0; k < tricks_total; k++) {
+        u32 lead = 0;
+        u64 bits = 0;
+        u32 t24 = 0;
+        u32 seats = 0;
+#pragma unroll
+        for (u32 j = 0; j < 4; j++) {
+            const u32 t = 4 * k + j;
+            const u32 hb = e.hist[(u64)t * na + g];
+            const u32 s = hb >> 6, c = hb & 63u;
+            if (j == 0) lead = c;
+            const u64 hand = sel4(h0, h1, h2, h3, s);
+            const u64 legal = legal_moves(hand, j != 0, lead, klop);
+            // -70 on every illegal card of this row
+            float* row = out + t * 54u;
+            if (!((legal >> lane) & 1ull)) row[lane] = -70.f;
+            if (lane + 32 < 54 && !((legal >> (lane + 32)) & 1ull)) row[lane + 32] = -70.f;
+            if (lane == 0) {
+                seat_out[i * 48u + t] = (uint8_t)s;
+                if (rows_out) rows_out[i * 48u + t] = (uint8_t)padded_rows(t + extra + (contract == C_KLOP ? min(k, 6u) : 0u));
+            }
+            const u64 bit = 1ull << c;
+            h0 ^= s == 0 ? bit : 0ull; h1 ^= s == 1 ? bit : 0ull; h2 ^= s == 2 ? bit : 0ull; h3 ^= s == 3 ? bit : 0ull;
+            bits |= bit; t24 |= c << (6 * j); seats |= s << (2 * j);
+        }
+        if (contract == C_KLOP && k < 6) bits |= 1ull << ((order >> (6 * (5 - k))) & 63ull);
+        const float v = (float)vrednost_stiha_bits(bits);
+        const u32 wj = trick_winner(t24);
+        __syncwarp();                                    // the -70 fills above precede the card entries below
+        if (lane < 4) {
+            const u32 t = 4 * k + lane;
+            const u32 s = (seats >> (2 * lane)) & 3u, c = (t24 >> (6 * lane)) & 63u;
+            float next;
+            if (k + 1 < tricks_total) {                  // the seat's next_Q_max in the following trick
+                next = 0.f;
+                for (u32 jj = 0; jj < 4; jj++) {
+                    const u32 t2 = 4 * (k + 1) + jj;
+                    if ((u32)(e.hist[(u64)t2 * na + g] >> 6) == s) next = e.qmax_hist[(u64)t2 * na + g];
+                }
+            } else {                                     // final reward (Igralec.py:433-438)
+                next = (float)(int16_t)(sc >> (16 * s));
+                if (is_berac(contract) && s != decl) next = tricks_total == 12 ? -20.f : 20.f;
+            }
+            out[t * 54u + c] = (lane == wj ? v : -v) + factor * next;
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace tk

@@ -28,7 +28,7 @@ MODE_AUCTION_BOT = 18
 FLAG_HISTORY = 1
 
 (F_HANDS, F_PILES, F_TALON, F_TALON_ORDER, F_META, F_MASK, F_SCORES, F_HIST, F_STATS, F_HANDS0,
- F_DISCARD) = range(11)
+ F_DISCARD, F_QMAX_HIST) = range(12)
 
 # stats vector layout (include/tarok_b200.h)
 S_SEAT, S_PLAYER, S_CONTRACT, S_FINISHED, S_STEPS, S_ERRORS, S_ERR_EVENTS = 0, 4, 8, 18, 19, 20, 21
@@ -121,6 +121,7 @@ class TarokEnv:
     stats_dev = property(lambda self: self.view(F_STATS))        # int64 [32]
     hands0 = property(lambda self: self.view(F_HANDS0))
     discard = property(lambda self: self.view(F_DISCARD))
+    qmax_hist = property(lambda self: self.view(F_QMAX_HIST))    # float32 [48, n_alloc]
 
     def set_step_impl(self, impl: int):
         """0 auto, 1 plain play_step kernel, 2 persistent TMA-staged kernel (A/B measurements)."""
@@ -259,11 +260,12 @@ class TarokEnv:
         self._check(self._lib.tarok_obs_shape(self._h, C.c_void_p(t.data_ptr()), C.c_void_p(r.data_ptr()), self._stream()))
         return t, r
 
-    def obs_expand(self, net_type: int, rows: int, sel=None):
+    def obs_expand(self, net_type: int, rows: int, sel=None, play=None):
         """The network inputs of ``Nevronski_igralec.stanje_v_vektor_rek_navadna`` for the seat to move of the
         selected games (int32 indices; None = all), as fp32 tensors in the reference's list order
         (A.4): Navadna [opp, king, hand, talon, decl, discard, mozne]; Solo [opp, hand, talon, decl, discard, mozne];
-        Klop [opp, hand, talon, mozne]; Berac [opp, hand, decl, mozne].  Returns (list of tensors, ok uint8 [n_sel])."""
+        Klop [opp, hand, talon, mozne]; Berac [opp, hand, decl, mozne].  Returns (list of tensors, ok uint8 [n_sel]).
+        ``play=t`` gives the observation as it was at card play t, for the seat that made it (replay samples)."""
         if not self.history:
             raise ValueError("observations need TarokEnv(..., history=True)")
         if sel is None:
@@ -281,8 +283,9 @@ class TarokEnv:
         mozne = torch.empty((n_sel, 54), dtype=f, device=dev)
         ok = torch.empty(n_sel, dtype=torch.uint8, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        self._check(self._lib.tarok_obs_expand(self._h, int(net_type), int(rows), sel_ptr, n_sel, p(opp), p(hand), p(talon),
-                                               p(king), p(decl), p(disc), p(mozne), p(ok), self._stream()))
+        self._check(self._lib.tarok_obs_expand_at(self._h, -1 if play is None else int(play), int(net_type), int(rows), sel_ptr,
+                                                  n_sel, p(opp), p(hand), p(talon), p(king), p(decl), p(disc), p(mozne), p(ok),
+                                                  self._stream()))
         order = {1: [opp, king, hand, talon, decl, disc, mozne], 2: [opp, hand, talon, decl, disc, mozne],
                  0: [opp, hand, talon, mozne], 3: [opp, hand, decl, mozne]}[int(net_type)]
         return order, ok
@@ -306,6 +309,19 @@ class TarokEnv:
         self._check(self._lib.tarok_select_action(self._h, C.c_void_p(q.data_ptr()), sel_ptr, n_sel, float(random_card),
                                                   C.c_void_p(cards.data_ptr()), C.c_void_p(qmax.data_ptr()), self._stream()))
         return cards, qmax
+
+    def targets(self, sel=None, final_reword_factor: float = 0.1):
+        """Replay targets of ``Nevronski_igralec.rezultat_stiha`` / ``rezultat_igre`` (Igralec.py:387-446) for finished games:
+        (dy fp32 [n_sel,48,54], seat uint8 [n_sel,48] (0xFF = no play), T uint8 [n_sel,48])."""
+        if not self.history:
+            raise ValueError("replay targets need TarokEnv(..., history=True)")
+        n_sel, sel_ptr, keep = self._sel(sel)
+        dy = torch.empty((n_sel, 48, 54), dtype=torch.float32, device=self.torch_device)
+        seat = torch.empty((n_sel, 48), dtype=torch.uint8, device=self.torch_device)
+        rows = torch.empty((n_sel, 48), dtype=torch.uint8, device=self.torch_device)
+        self._check(self._lib.tarok_targets(self._h, sel_ptr, n_sel, float(final_reword_factor), C.c_void_p(dy.data_ptr()),
+                                            C.c_void_p(seat.data_ptr()), C.c_void_p(rows.data_ptr()), self._stream()))
+        return dy, seat, rows
 
     def obs_hands(self) -> torch.Tensor:
         """``pripavi_licitiram`` (Igralec.py:278-281): fp32 [n,4,54], the hand of every seat."""

@@ -132,5 +132,50 @@ class Samoigra:
         st = env.stats()
         return st, (ura.ms() if meri else None)
 
+    @torch.no_grad()
+    def vzorci(self, final_reword_factor: float = 0.1):
+        """Replay samples of the batch just played, bucketed like ``Nevronski_igralec.zgodovina[(tip, T)]``
+        (Igralec.py:441-443): yields (net name, T, stanje list without the legal-mask vector, dy [B,54])."""
+        env, n = self.env, self.n
+        dy, seat, rows = env.targets(final_reword_factor=final_reword_factor)
+        vrsta = E.meta_field(env.meta[:n], E.M_CONTRACT, 4)
+        kind = torch.full_like(vrsta, 2)                                   # Solo_* ...
+        kind = torch.where(vrsta == 0, torch.zeros_like(kind), kind)       # Klop
+        kind = torch.where((vrsta >= 1) & (vrsta <= 3), torch.ones_like(kind), kind)
+        kind = torch.where((vrsta == 7) | (vrsta == 9), torch.full_like(kind, 3), kind)
+        for t in range(48):
+            igrano = seat[:, t] != 0xFF
+            if not bool(igrano.any()):
+                break
+            kljuc = kind * 64 + rows[:, t].to(kind.dtype)
+            for k in torch.unique(kljuc[igrano]).tolist():
+                vr, T = k // 64, k % 64
+                sel = torch.nonzero(igrano & (kljuc == k)).flatten().to(torch.int32)
+                stanje, ok = env.obs_expand(vr, T, sel, play=t)
+                yield _NET_OF_KIND[vr], T, stanje[:-1], dy[sel.long(), t]
+
+    def nauci(self, final_reword_factor: float = 0.1, lr: float = 1e-3):
+        """One optimisation pass over the samples of the last batch: Huber(delta=25) + Adam per play net, the loss and
+        optimiser of the reference's models (train.py:23-25; Igralec.py:545-607 fits them with Lightning).  Training is
+        outside the accelerated path; this exists so the self-play loop closes.  Returns {net name: mean loss}."""
+        opt = {k: torch.optim.Adam(self.mreze[k].parameters(), lr=lr) for k in _NET_OF_KIND.values()}
+        izguba, stevec = {}, {}
+        for ime, T, stanje, dy in self.vzorci(final_reword_factor):
+            m = self.mreze[ime]
+            m.train()
+            with torch.enable_grad():
+                for a in range(0, dy.shape[0], 4096):
+                    x = [s[a:a + 4096] for s in stanje]
+                    if x[0].shape[0] < 2:
+                        continue                                           # BatchNorm needs more than one sample
+                    l = torch.nn.functional.huber_loss(m(x), dy[a:a + 4096], delta=25.0)
+                    opt[ime].zero_grad(set_to_none=True)
+                    l.backward()
+                    opt[ime].step()
+                    izguba[ime] = izguba.get(ime, 0.0) + float(l.detach())
+                    stevec[ime] = stevec.get(ime, 0) + 1
+            m.eval()
+        return {k: izguba[k] / stevec[k] for k in izguba}
+
     def zapri(self):
         self.env.close()

@@ -51,6 +51,27 @@ def test_observations_match_reference(golden):
             env.step(cards)
     assert env.errors() == 0
     assert checked == len(idx)
+    # ---- replay samples (Igralec.py:387-446): targets dy and the observation "as of play t"
+    env.score()
+    dy, seat, rows = env.targets(final_reword_factor=0.1)
+    dy, seat, rows = dy.cpu().numpy(), seat.cpu().numpy(), rows.cpu().numpy()
+    want = g["dy"]
+    have = ~np.isnan(want[:, :, 0])
+    played = g["card"] != 0xFF
+    assert (seat[played] != 0xFF).all() and (seat[~played] == 0xFF).all() and (dy[~played] == 0).all()
+    assert have.sum() > 2000
+    # the only floating-point arithmetic on the path: value + 0.1 * next.  The reference does it in float64 (numpy), the
+    # kernel in fp32 -> tolerance 1e-4 absolute (values are |x| <= 200); the -70 (illegal card) pattern must be exact
+    assert np.allclose(dy[have], want[have], rtol=0.0, atol=1e-4)
+    assert np.array_equal(dy[have] == -70.0, want[have] == -70.0)
+    for (game, t), k in list(row_of.items())[::7]:
+        kind, T = int(idx[k][4]), int(idx[k][3])
+        assert rows[game, t] == T and seat[game, t] == idx[k][2]
+        arrs, ok = env.obs_expand(kind, T, np.array([game], np.int32), play=t)
+        assert bool(ok.all())
+        flat = np.concatenate([a[0].cpu().numpy().reshape(-1) for a in arrs]).astype(np.uint8)
+        ref = np.unpackbits(bits[off[k]:off[k + 1]])[:flat.size]
+        assert (flat[:-54] == ref[:-54]).all(), (game, t)   # everything but the legal-mask vector (not a net input)
     # a bucket that does not match is reported, not silently filled
     arrs, ok = env.obs_expand(1, 8, np.arange(4, dtype=np.int32))
     assert not ok.cpu().numpy().any() and float(arrs[0].abs().sum()) == 0.0

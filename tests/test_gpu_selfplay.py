@@ -37,3 +37,25 @@ def test_nets_follow_the_reference_call_contract():
     assert nets["Berac"]([z(B, T, 3, 54), z(B, T, 54), z(B, 4)]).shape == (B, 54)
     assert nets["Vrednotenje_roke"](z(B, 54)).shape == (B, 18)
     assert nets["Zalaganje"]([z(B, 54), z(B, 54, 6), z(B, 15)]).shape == (B, 60)
+
+
+def test_replay_samples_and_one_training_pass():
+    import torch
+    from tarok_b200.samoigra import Samoigra
+    torch.manual_seed(1)
+    n = 2048
+    s = Samoigra(n, seed=5, random_card=0.2)
+    st, _ = s.odigraj()
+    total = 0
+    for ime, T, stanje, dy in s.vzorci():
+        B = dy.shape[0]
+        assert stanje[0].shape == (B, T, 3, 54) and dy.shape == (B, 54) and T % 8 == 0
+        assert bool(((dy == -70) | (dy > -70)).all())
+        total += B
+    assert total == st[19]                                   # one sample per card play (Igralec.py:416)
+    before = [p.detach().clone() for p in s.mreze["Navadna_igra"].parameters()]
+    loss = s.nauci()
+    assert loss and all(np.isfinite(v) for v in loss.values())
+    after = list(s.mreze["Navadna_igra"].parameters())
+    assert any(not torch.equal(a, b) for a, b in zip(before, after))
+    s.zapri()
