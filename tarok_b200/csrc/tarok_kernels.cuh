@@ -93,7 +93,7 @@ __device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, 
 // deal: Igra.razdeli (Igra.py:65-73) with a counter-based Philox generator.
 // Card c goes to a uniformly random free slot among the 54-c left = a walk over the remaining pile
 // capacities (12,12,12,12,6); the talon ORDER is a uniform permutation decoded from one more draw.
-// 55 bounded draws = 14 Philox blocks per deal: ALU-bound, not HBM-bound.
+// 55 bounded draws = 7 Philox blocks per deal (16-bit lanes): ALU-bound, not HBM-bound.
 // ------------------------------------------------------------------------------------------------
 struct Dealt { u64 h0, h1, h2, h3, talon, order; };
 
