@@ -82,6 +82,7 @@ const char* tarok_last_error(const tarok_t* h);/* h may be NULL: last error of a
 /* Tuning knobs.  TAROK_OPT_STEP_IMPL: 0 auto (default), 1 plain play_step kernel, 2 persistent TMA-staged kernel. */
 #define TAROK_OPT_STEP_IMPL 1
 #define TAROK_OPT_PDL 2        /* 1 (default): chain play_step launches with programmatic dependent launch */
+#define TAROK_OPT_LOCKSTEP 3   /* 1 (default): play_step variants specialised per trick position for lock-step batches */
 int tarok_set_option(tarok_t* h, int option, int64_t value);
 uint64_t tarok_n_games(const tarok_t* h);
 uint64_t tarok_n_alloc(const tarok_t* h);      /* n_games rounded up to the kernel tile */

@@ -109,10 +109,18 @@ __device__ __forceinline__ Words4 play_block(const Rng& rng, u64 gid, u32 trick)
     return philox_block(rng, gid >> 1, ST_PLAY, trick);
 }
 
+// POS >= 0: position in the trick known at compile time (lock-step batches): the lane pick becomes one select.
+template <int POS = -1>
 __device__ __forceinline__ u32 play_draw(const Words4& b, const Rng& rng, u64 gid, u32 t, u32 n) {
-    const u32 lane = ((u32)gid & 1u) * 4u + (t & 3u);
-    const u32 w = (lane >> 1) == 0 ? b.w[0] : (lane >> 1) == 1 ? b.w[1] : (lane >> 1) == 2 ? b.w[2] : b.w[3];
-    const u32 x = (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
+    u32 w, x;
+    if (POS >= 0) {
+        w = ((u32)gid & 1u) ? b.w[2 + (POS >> 1)] : b.w[POS >> 1];
+        x = (POS & 1) ? (w >> 16) : (w & 0xFFFFu);
+    } else {
+        const u32 lane = ((u32)gid & 1u) * 4u + (t & 3u);
+        w = (lane >> 1) == 0 ? b.w[0] : (lane >> 1) == 1 ? b.w[1] : (lane >> 1) == 2 ? b.w[2] : b.w[3];
+        x = (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
+    }
     const u32 m = x * n;
     const u32 lo = m & 0xFFFFu;
     if (__builtin_expect(lo < n, 0)) {

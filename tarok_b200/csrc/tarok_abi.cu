@@ -21,6 +21,8 @@ struct tarok_env {
     int sm_count;
     int step_impl;                             // 0 auto, 1 plain k_step, 2 persistent TMA-staged k_step_tma
     int pdl;                                   // chain play_step launches with programmatic dependent launch
+    int lockstep;                              // pass the lock-step hint to play_step (specialised per trick position)
+    int lock_plays;                            // plays made by every live game since the last deal, -1 = unknown
     u32 flags;
     tk::Env e;
     // staging buffers of the host-buffer entry point
@@ -90,7 +92,10 @@ static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (tma) cudaLaunchKernelEx(&cfg, tk::k_step_tma<RANDOM>, h->e, action);
-    else cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM>, h->e, action);
+    else cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM>, h->e, action, h->lockstep ? h->lock_plays : -1);
+    // lock-step bookkeeping (only a hint to the kernel, which verifies it per warp): every live game has made
+    // `lock_plays` plays since the last deal; one more after this launch
+    if (h->lock_plays >= 0) h->lock_plays = h->lock_plays < 47 ? h->lock_plays + 1 : -1;
 }
 
 extern "C" {
@@ -99,6 +104,7 @@ int tarok_set_option(tarok_t* h, int option, int64_t value) {
     TK_CHECK_HANDLE(h);
     if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 2) { h->step_impl = (int)value; return 0; }
     if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
+    if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
     return fail(h, -1, "unknown option %d / value %lld", option, (long long)value);
 }
 
@@ -119,7 +125,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     tarok_env* h = new (std::nothrow) tarok_env();
     if (!h) return fail(nullptr, -4, "out of host memory");
     memset(&h->e, 0, sizeof(h->e));
-    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
+    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;
@@ -199,6 +205,7 @@ static void clear_hist(tarok_t* h, void* stream) {
 int tarok_deal(tarok_t* h, uint64_t first_global_game_id, void* stream) {
     TK_CHECK_HANDLE(h);
     DeviceGuard dg(h->device);
+    h->lock_plays = 0;
     h->e.first_gid = first_global_game_id;
     clear_hist(h, stream);
     tk::k_deal<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e);
@@ -210,6 +217,7 @@ int tarok_set_deals(tarok_t* h, const uint8_t* perm_dev, uint64_t first_global_g
     TK_CHECK_HANDLE(h);
     if (!perm_dev) return fail(h, -1, "perm_dev is null");
     DeviceGuard dg(h->device);
+    h->lock_plays = 0;
     h->e.first_gid = first_global_game_id;
     clear_hist(h, stream);
     tk::k_set_deals<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, perm_dev);
@@ -373,6 +381,7 @@ int tarok_setup_synth(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, 
     if (!(mode <= TAROK_ODPRTI_BERAC || (mode >= TAROK_MODE_NAVADNA_MIX && mode <= TAROK_MODE_AUCTION_BOT)))
         return fail(h, -1, "bad mode %u", mode);
     DeviceGuard dg(h->device);
+    h->lock_plays = 0;
     h->e.first_gid = first_global_game_id;
     clear_hist(h, stream);
     tk::k_setup_synth<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode);
@@ -399,6 +408,7 @@ int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id
     if (!(mode <= TAROK_ODPRTI_BERAC || (mode >= TAROK_MODE_NAVADNA_MIX && mode <= TAROK_MODE_AUCTION_BOT)))
         return fail(h, -1, "bad mode %u", mode);
     DeviceGuard dg(h->device);
+    h->lock_plays = 0;
     h->e.first_gid = first_global_game_id;
     clear_hist(h, stream);
     tk::k_rollout_fused<false><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr, nullptr,
@@ -430,6 +440,7 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
     }
     cudaStream_t s = S(stream);
     TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
+    h->lock_plays = 0;
     h->e.first_gid = first_global_game_id;
     if (!fused) {
         TK_CUDA(h, cudaMemcpyAsync(h->st_perm, perm_host, n * 54, cudaMemcpyHostToDevice, s));

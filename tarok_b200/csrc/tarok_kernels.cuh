@@ -463,27 +463,29 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // Game indices are 32-bit inside the step kernels (n_alloc <= 2^29, enforced by tarok_create): one IMAD.WIDE
 // per address instead of 64-bit multiply chains.
-template <bool RANDOM, class Hands>
+// POS >= 0 = lock-step specialisation: every live game of the warp is at play `plays` (position POS = plays & 3 of its
+// trick), checked by the caller, so position-dependent work folds at compile time; POS = -1 is the general path.
+template <bool RANDOM, int POS, class Hands>
 __device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const Hands& hands, u32 card,
                                           const Words4& rnd, u64& next_mask) {
     const u32 na = (u32)e.n_alloc;
     const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
-    const u32 mover = mover_of(meta);
+    const u32 pos = POS >= 0 ? (u32)POS : ((lo >> M_POS) & 3u);
+    const u32 mover = ((lo >> M_LEADER) + pos) & 3u;
     u64 hand = hands.get(mover);
     const u32 contract = lo & 15u;
-    const u32 pos = (lo >> M_POS) & 3u;
     const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
     u64 talon = 0, order = 0;
-    if (contract == C_KLOP) {
+    if ((POS < 0 || POS == 3) && contract == C_KLOP) {
         if (pos == 3 && ((lo >> M_TRICKS) & 15u) < 6) { talon = e.talon[g]; order = e.torder[g]; }
     }
     if (RANDOM) {
         u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));
         u32 n = (u32)__popcll(legal);
-        card = nth_set_bit(legal, play_draw(rnd, e.rng, e.first_gid + g, plays, n));
+        card = nth_set_bit(legal, play_draw<POS>(rnd, e.rng, e.first_gid + g, plays, n));
     }
     PlayResult pr;
-    meta = play_card<!RANDOM>(meta, hand, card, talon, order, pr);
+    meta = play_card<!RANDOM, POS>(meta, hand, card, talon, order, pr);
     next_mask = 0;
     if (!RANDOM && ((meta >> M_ERR) & 1ull)) {
         atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
@@ -491,21 +493,48 @@ __device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const 
     }
     e.hands[mover * na + g] = hand;
     if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
-    if (pr.trick_done) {
+    if ((POS < 0 || POS == 3) && pr.trick_done) {
         u64* pp = e.piles + (pr.winner * na + g);
         *pp |= pr.pile_bits;
         if (pr.talon_clear) e.talon[g] = talon & ~pr.talon_clear;
     }
-    const u32 nx = mover_of(meta);
-    next_mask = mask_for_mover(meta, nx == mover ? hand : hands.get(nx));
+    if (POS >= 0 && POS < 3) {                                   // same trick goes on: next seat follows the same lead
+        next_mask = legal_moves(hands.get((mover + 1u) & 3u), true, (u32)(meta >> 32) & 63u, klop_rules(contract));
+    } else {
+        const u32 nx = mover_of(meta);
+        next_mask = mask_for_mover(meta, nx == mover ? hand : hands.get(nx));
+    }
 }
 
+// Philox block(s) + the two games of a lane + the two 128-bit stores.
+template <bool RANDOM, int POS, class H0, class H1>
+__device__ __forceinline__ void step_pair(const Env& e, u32 g, ulonglong2& m, bool a0, bool a1, const H0& hx, const H1& hy,
+                                          u32 act, u32 lock_trick) {
+    Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
+    if (RANDOM) {
+        // one Philox block serves both games of the lane (same pair, same trick) in the common case.  In the lock-step
+        // path the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used.
+        const u64 gid = e.first_gid + g;
+        const u32 t0 = POS >= 0 ? lock_trick : ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u;
+        const u32 t1 = POS >= 0 ? lock_trick : ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u;
+        r0 = play_block(e.rng, gid, t0);
+        r1 = r0;
+        if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
+    }
+    u64 k0 = 0, k1 = 0;
+    if (a0) step_game<RANDOM, POS>(e, g, m.x, hx, act & 0xFFu, r0, k0);
+    if (a1) step_game<RANDOM, POS>(e, g + 1, m.y, hy, act >> 8, r1, k1);
+    st2(e.meta + g, m.x, m.y);
+    st2(e.mask + g, k0, k1);
+}
+
+// `hint` = the number of plays every live game has made so far (lock-step pipelines know it on the host), or -1.
+// It is only a hint: each warp votes whether all its live games really are at `hint` and otherwise takes the general path.
 template <bool RANDOM>
-__global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restrict__ action) {
+__global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restrict__ action, int hint) {
     pdl_launch_dependents();
     const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
-    const u32 na = (u32)e.n_alloc;
-    if (g >= na) return;
+    const u32 na = (u32)e.n_alloc;                 // the grid covers n_alloc exactly: no partial warps
     pdl_wait();                                    // the previous step's writes are visible from here on
     // all five 128-bit loads are issued before the first use: one memory round trip per step
     ulonglong2 m = ld2(e.meta + g);
@@ -514,21 +543,21 @@ __global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restric
     u32 act = 0;
     if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
     const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
+    const u32 p0 = ((u32)(m.x >> 32) >> (M_PLAYS - 32)) & 63u, p1 = ((u32)(m.y >> 32) >> (M_PLAYS - 32)) & 63u;
+    const bool in_step = (!a0 || p0 == (u32)hint) && (!a1 || p1 == (u32)hint);
+    const bool lock = hint >= 0 && __all_sync(0xFFFFFFFFu, in_step);
     if (!a0 && !a1) return;
-    Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
-    if (RANDOM) {
-        // one Philox block serves both games of the lane (same pair, same trick) in the common case
-        const u64 gid = e.first_gid + g;
-        const u32 t0 = ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u, t1 = ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u;
-        r0 = play_block(e.rng, gid, t0);
-        r1 = r0;
-        if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
+    const RegHands hx{h0.x, h1.x, h2.x, h3.x}, hy{h0.y, h1.y, h2.y, h3.y};
+    if (lock) {
+        switch (hint & 3) {
+            case 0: step_pair<RANDOM, 0>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
+            case 1: step_pair<RANDOM, 1>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
+            case 2: step_pair<RANDOM, 2>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
+            default: step_pair<RANDOM, 3>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
+        }
+    } else {
+        step_pair<RANDOM, -1>(e, g, m, a0, a1, hx, hy, act, 0u);
     }
-    u64 k0 = 0, k1 = 0;
-    if (a0) step_game<RANDOM>(e, g, m.x, RegHands{h0.x, h1.x, h2.x, h3.x}, act & 0xFFu, r0, k0);
-    if (a1) step_game<RANDOM>(e, g + 1, m.y, RegHands{h0.y, h1.y, h2.y, h3.y}, act >> 8, r1, k1);
-    st2(e.meta + g, m.x, m.y);
-    st2(e.mask + g, k0, k1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -599,21 +628,8 @@ __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __res
         mbar_wait(&full[s], (it >> 1) & 1u);
         ulonglong2 m = *reinterpret_cast<const ulonglong2*>(&stage[s].meta[l]);
         const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
-        if (a0 || a1) {
-            Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
-            if (RANDOM) {
-                const u64 gid = e.first_gid + g;
-                const u32 t0 = ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u, t1 = ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u;
-                r0 = play_block(e.rng, gid, t0);
-                r1 = r0;
-                if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
-            }
-            u64 k0 = 0, k1 = 0;
-            if (a0) step_game<RANDOM>(e, g, m.x, SmemHands{&stage[s].hands[0][l]}, act & 0xFFu, r0, k0);
-            if (a1) step_game<RANDOM>(e, g + 1, m.y, SmemHands{&stage[s].hands[0][l + 1]}, act >> 8, r1, k1);
-            st2(e.meta + g, m.x, m.y);
-            st2(e.mask + g, k0, k1);
-        }
+        if (a0 || a1)
+            step_pair<RANDOM, -1>(e, g, m, a0, a1, SmemHands{&stage[s].hands[0][l]}, SmemHands{&stage[s].hands[0][l + 1]}, act, 0u);
         __syncthreads();                              // stage s may be refilled from the next iteration on
     }
 }

@@ -265,13 +265,15 @@ struct PlayResult {
 
 // CHECK = validate the card against the legal set (externally supplied actions); the in-kernel random
 // players pick from the legal set by construction and skip it.
-template <bool CHECK>
+// POS >= 0: the caller knows (and has checked) that the game is at position POS of its trick -- lock-step batches --
+// so the trick-position arithmetic and the trick-end branch fold at compile time; POS = -1 reads it from meta.
+template <bool CHECK, int POS = -1>
 __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talon, u64 talon_order,
                                          PlayResult& out) {
     out.trick_done = false; out.winner = 0; out.pile_bits = 0; out.talon_clear = 0;
     u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 contract = lo & 15u;
-    const u32 pos = (lo >> M_POS) & 3u;
+    const u32 pos = POS >= 0 ? (u32)POS : ((lo >> M_POS) & 3u);
     const u64 bit = card < 54 ? (1ull << card) : 0ull;
     if (CHECK) {
         u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));

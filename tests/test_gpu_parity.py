@@ -156,10 +156,11 @@ def test_deal_matches_oracle_and_is_shard_invariant(oracle):
     env.close()
 
 
+@pytest.mark.parametrize("gid0", [123456789, 2 ** 33 + 1000])      # odd / even: the Philox game-pair sharing depends on parity
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 18])
-def test_rollout_matches_oracle(oracle, mode):
+def test_rollout_matches_oracle(oracle, mode, gid0):
     """Whole deals with the Philox players: stepwise kernels == fused kernel == C oracle."""
-    n, seed, gid0 = 20011, 4242, 123456789
+    n, seed = 20011, 4242
     ref = oracle.rollout(seed, gid0, n, mode)
     env = _env(n, seed=seed, history=True)
     env.rollout(mode, first_game_id=gid0, fused=False)
