@@ -684,6 +684,29 @@ __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64
 // registers (one lane = one game).  Same device functions, same Philox draws, hence bit-identical to
 // the stepwise pipeline.  Not HBM-bound: 8 B/deal written.
 // ------------------------------------------------------------------------------------------------
+struct FusedGame { u64 h0, h1, h2, h3, p0, p1, p2, p3, talon, order, meta; };
+
+// One card play of the fused rollout at trick position J (compile-time: the loop over a trick is unrolled).
+template <int J>
+__device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, const Rng& rng, u64 gid, u32 trick, bool klop,
+                                           uint8_t* hist_row, u64 na) {
+    const u32 mover = (((u32)f.meta >> M_LEADER) + (u32)J) & 3u;
+    u64 hand = sel4(f.h0, f.h1, f.h2, f.h3, mover);
+    const u64 legal = legal_moves(hand, J != 0, (u32)(f.meta >> 32) & 63u, klop);
+    const u32 n = (u32)__popcll(legal);
+    const u32 card = nth_set_bit(legal, play_draw<J>(blk, rng, gid, trick * 4 + J, n));
+    PlayResult pr;
+    f.meta = play_card<false, J>(f.meta, hand, card, f.talon, f.order, pr);
+    if (hist_row) hist_row[(u64)J * na] = (uint8_t)((mover << 6) | card);
+    f.h0 = mover == 0 ? hand : f.h0; f.h1 = mover == 1 ? hand : f.h1; f.h2 = mover == 2 ? hand : f.h2; f.h3 = mover == 3 ? hand : f.h3;
+    if (J == 3) {
+        const u64 b = pr.pile_bits;
+        f.p0 |= pr.winner == 0 ? b : 0ull; f.p1 |= pr.winner == 1 ? b : 0ull;
+        f.p2 |= pr.winner == 2 ? b : 0ull; f.p3 |= pr.winner == 3 ? b : 0ull;
+        f.talon &= ~pr.talon_clear;
+    }
+}
+
 template <bool FROM_PERM>
 __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const uint8_t* __restrict__ perm,
                                                        const uint8_t* __restrict__ fc, const uint8_t* __restrict__ fd,
@@ -733,27 +756,17 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         }
         const u32 contract = mget(meta, M_CONTRACT, 4);
         const bool klop = klop_rules(contract);
-        for (u32 trick = 0; trick < 12 && mget(meta, M_PHASE, 2) == PH_PLAY; trick++) {
+        FusedGame fg{h0, h1, h2, h3, p0, p1, p2, p3, talon, order, meta};
+        for (u32 trick = 0; trick < 12 && mget(fg.meta, M_PHASE, 2) == PH_PLAY; trick++) {
             Words4 blk = play_block(e.rng, gid, trick);                // 4 plays = half of one Philox block
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                u32 mover = mover_of(meta);
-                u64 hand = sel4(h0, h1, h2, h3, mover);
-                u64 legal = legal_moves(hand, j != 0, mget(meta, M_TRICK, 6), klop);
-                u32 n = (u32)__popcll(legal);
-                u32 card = nth_set_bit(legal, play_draw(blk, e.rng, gid, trick * 4 + j, n));
-                PlayResult pr;
-                meta = play_card<false>(meta, hand, card, talon, order, pr);
-                if (e.hist && write_state) e.hist[(u64)(trick * 4 + j) * na + g] = (uint8_t)((mover << 6) | card);
-                h0 = mover == 0 ? hand : h0; h1 = mover == 1 ? hand : h1; h2 = mover == 2 ? hand : h2; h3 = mover == 3 ? hand : h3;
-                if (pr.trick_done) {
-                    u64 b = pr.pile_bits;
-                    p0 |= pr.winner == 0 ? b : 0ull; p1 |= pr.winner == 1 ? b : 0ull;
-                    p2 |= pr.winner == 2 ? b : 0ull; p3 |= pr.winner == 3 ? b : 0ull;
-                    talon &= ~pr.talon_clear;
-                }
-            }
+            uint8_t* hrow = (e.hist && write_state) ? e.hist + (u64)(trick * 4) * na + g : nullptr;
+            fused_play<0>(fg, blk, e.rng, gid, trick, klop, hrow, na);
+            fused_play<1>(fg, blk, e.rng, gid, trick, klop, hrow, na);
+            fused_play<2>(fg, blk, e.rng, gid, trick, klop, hrow, na);
+            fused_play<3>(fg, blk, e.rng, gid, trick, klop, hrow, na);
         }
+        h0 = fg.h0; h1 = fg.h1; h2 = fg.h2; h3 = fg.h3; p0 = fg.p0; p1 = fg.p1; p2 = fg.p2; p3 = fg.p3;
+        talon = fg.talon; meta = fg.meta;
         err = (meta >> M_ERR) & 1ull;
         if (!err && mget(meta, M_PHASE, 2) == PH_DONE) packed = score_game(meta, p0, p1, p2, p3, talon);
         if (out) out[g] = packed;
