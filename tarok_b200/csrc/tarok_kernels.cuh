@@ -126,9 +126,13 @@ __device__ __forceinline__ u64 order_from_lehmer(u64 talon, u32 L) {
 // compile time in the unrolled loop: every update is one predicated 32-bit OR.
 enum : u32 { ST_DEAL_RETRY = 7 };
 
+// The pile walk keeps CUMULATIVE state: T_j = free slots in piles 0..j and H_j = cards dealt to piles 0..j.  A draw r
+// picks pile s = min{j : r < T_j}, i.e. q_j = (r < T_j) holds exactly for j >= s, so the whole update is
+// H_j |= q_j ? bit : 0 and T_j -= q_j -- four compares, four predicated ORs, four predicated decrements per card;
+// the hands are recovered at the end as H_0, H_1^H_0, H_2^H_1, H_3^H_2 and the talon as ALL54 ^ H_3.
 __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
-    u32 lo[5] = {0, 0, 0, 0, 0}, hi[5] = {0, 0, 0, 0, 0};      // seats 0..3, talon
-    u32 c0 = 12, c1 = 12, c2 = 12, c3 = 12;
+    u32 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+    u32 t0 = 12, t1 = 24, t2 = 36, t3 = 48;
     u32 L = 0;
 #pragma unroll
     for (int blk = 0; blk < 7; blk++) {
@@ -143,15 +147,13 @@ __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
                 const u32 m = x * n;
                 u32 r = m >> 16;
                 if (__builtin_expect((m & 0xFFFFu) < (65536u % n), 0)) r = draw_loop(rng.seed, gid, ST_DEAL_RETRY, (u32)c, n, 0u);
-                const u32 a0 = c0, a1 = a0 + c1, a2 = a1 + c2, a3 = a2 + c3;
-                const bool p0 = r < a0, p1 = !p0 && r < a1, p2 = r >= a1 && r < a2, p3 = r >= a2 && r < a3, p4 = r >= a3;
+                const bool q0 = r < t0, q1 = r < t1, q2 = r < t2, q3 = r < t3;
                 const u32 bit = 1u << (c & 31);
                 u32* half = c < 32 ? lo : hi;
-                half[0] |= p0 ? bit : 0u; c0 -= p0 ? 1u : 0u;
-                half[1] |= p1 ? bit : 0u; c1 -= p1 ? 1u : 0u;
-                half[2] |= p2 ? bit : 0u; c2 -= p2 ? 1u : 0u;
-                half[3] |= p3 ? bit : 0u; c3 -= p3 ? 1u : 0u;
-                half[4] |= p4 ? bit : 0u;
+                half[0] |= q0 ? bit : 0u; t0 -= q0 ? 1u : 0u;
+                half[1] |= q1 ? bit : 0u; t1 -= q1 ? 1u : 0u;
+                half[2] |= q2 ? bit : 0u; t2 -= q2 ? 1u : 0u;
+                half[3] |= q3 ? bit : 0u; t3 -= q3 ? 1u : 0u;
             } else if (c == 55) {                               // word 27 whole: the talon order
                 const u64 m = (u64)word * 720u;
                 L = (u32)(m >> 32);
@@ -160,9 +162,10 @@ __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
         }
     }
     Dealt d;
-    d.h0 = ((u64)hi[0] << 32) | lo[0]; d.h1 = ((u64)hi[1] << 32) | lo[1];
-    d.h2 = ((u64)hi[2] << 32) | lo[2]; d.h3 = ((u64)hi[3] << 32) | lo[3];
-    d.talon = ((u64)hi[4] << 32) | lo[4];
+    const u64 H0 = ((u64)hi[0] << 32) | lo[0], H1 = ((u64)hi[1] << 32) | lo[1], H2 = ((u64)hi[2] << 32) | lo[2],
+              H3 = ((u64)hi[3] << 32) | lo[3];
+    d.h0 = H0; d.h1 = H1 ^ H0; d.h2 = H2 ^ H1; d.h3 = H3 ^ H2;
+    d.talon = ALL54 ^ H3;
     d.order = order_from_lehmer(d.talon, L);
     return d;
 }
@@ -339,11 +342,12 @@ __device__ __forceinline__ bool exchange_game(const Rng& rng, u64 gid, u32 rando
     u32 contract = mget(meta, M_CONTRACT, 4);
     u32 k = talon_k(contract);
     u32 ngroups = 6u / k;
+    u64 gb_synth = 0;
     if (SYNTH) {
         Words4 blk = philox_block(rng, gid, ST_EXCH, 0u);
         group = random_group ? draw_from_word(blk.w[0], rng, gid, ST_EXCH, 0u, ngroups) : 0u;   // Bot: group 0 (Igralec.py:162)
-        u64 gb = talon_group_bits(order, k, group);
-        u64 avail = (hand | gb) & DISCARDABLE;
+        gb_synth = talon_group_bits(order, k, group);
+        u64 avail = (hand | gb_synth) & DISCARDABLE;
         if ((u32)__popcll(avail) < k) return false;
         discard = 0;
         for (u32 j = 0; j < k; j++) {               // uniform k-subset = random.sample (Igralec.py:166)
@@ -354,7 +358,7 @@ __device__ __forceinline__ bool exchange_game(const Rng& rng, u64 gid, u32 rando
         }
     }
     if (group >= ngroups) return false;
-    u64 gb = talon_group_bits(order, k, group);
+    const u64 gb = SYNTH ? gb_synth : talon_group_bits(order, k, group);
     u64 full = hand | gb;
     if ((u32)__popcll(discard) != k || (discard & ~(full & DISCARDABLE))) return false;
     hand = full & ~discard;

@@ -245,8 +245,10 @@ __device__ __forceinline__ u64 begin_contract(u64 meta, u32 contract, u32 declar
 // ---- talon exchange -----------------------------------------------------------------------------
 // Group g of Navadna_igra.odpri_talon (Navadna_igra.py:36-44): consecutive slices of the ordered talon.
 __device__ __forceinline__ u64 talon_group_bits(u64 order, u32 k, u32 g) {
-    u64 b = 0;
-    for (u32 j = 0; j < k; j++) b |= 1ull << ((order >> (6 * (g * k + j))) & 63ull);
+    const u64 w = order >> (6u * g * k);                 // the group's ids are the next k six-bit fields
+    u64 b = 1ull << (w & 63ull);
+    if (k > 1) b |= 1ull << ((w >> 6) & 63ull);
+    if (k > 2) b |= 1ull << ((w >> 12) & 63ull);
     return b;
 }
 
