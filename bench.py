@@ -202,6 +202,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     n, mode, total = args.games, args.mode, args.games * world
     env = TarokEnv(n, seed=SEED, device=local_rank)
+    env.set_materialise(False)      # the rollout's outputs are scores + statistics (Tarok.rezultati); piles stay in the trick log
     auction = mode in (17, 18)
     flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     stats_ring = torch.zeros((args.warmup + args.steps + 1, 32), dtype=torch.int64, device=dev)

@@ -59,7 +59,8 @@ enum { TAROK_KLOP = 0, TAROK_TRI = 1, TAROK_DVE = 2, TAROK_ENA = 3, TAROK_SOLO_T
 #define TAROK_FLAG_HISTORY 1u          /* keep the play history (seat<<6|card per play) for observations */
 /* exportable fields */
 enum { TAROK_F_HANDS = 0,   /* uint64 [4, n_alloc]  hand bitboard of seat s        (Roka, Roka.py:4-13)      */
-       TAROK_F_PILES = 1,   /* uint64 [4, n_alloc]  won-cards pile of seat s       (Igralec.kupcek)          */
+       TAROK_F_PILES = 1,   /* uint64 [4, n_alloc]  won-cards pile of seat s (Igralec.kupcek): discards at once, won tricks
+                               (and the Klop talon in TAROK_F_TALON) are materialised from the trick log by tarok_score */
        TAROK_F_TALON = 2,   /* uint64 [n_alloc]     cards still in the talon                                 */
        TAROK_F_TALON_ORDER = 3, /* uint64 [n_alloc] the 6 talon ids in dealt order, 6 bits each (Igra.py:68) */
        TAROK_F_META = 4,    /* uint64 [n_alloc]     packed contract / trick state (layout in DESIGN.md)      */
@@ -82,6 +83,7 @@ const char* tarok_last_error(const tarok_t* h);/* h may be NULL: last error of a
 /* Tuning knobs.  TAROK_OPT_STEP_IMPL: 0 auto (default), 1 plain play_step kernel, 2 persistent TMA-staged kernel. */
 #define TAROK_OPT_STEP_IMPL 1
 #define TAROK_OPT_PDL 2        /* 1 (default): chain play_step launches with programmatic dependent launch */
+#define TAROK_OPT_MATERIALISE 4 /* 1 (default): tarok_score writes the full piles / Klop talon back; 0: scores + stats only */
 #define TAROK_OPT_LOCKSTEP 3   /* 1 (default): play_step variants specialised per trick position for lock-step batches */
 int tarok_set_option(tarok_t* h, int option, int64_t value);
 uint64_t tarok_n_games(const tarok_t* h);

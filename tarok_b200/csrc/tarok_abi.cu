@@ -23,6 +23,7 @@ struct tarok_env {
     int pdl;                                   // chain play_step launches with programmatic dependent launch
     int lockstep;                              // pass the lock-step hint to play_step (specialised per trick position)
     int lock_plays;                            // plays made by every live game since the last deal, -1 = unknown
+    int materialise;                           // tarok_score writes the materialised piles / talon back (default on)
     u32 flags;
     tk::Env e;
     // staging buffers of the host-buffer entry point
@@ -105,6 +106,7 @@ int tarok_set_option(tarok_t* h, int option, int64_t value) {
     if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 2) { h->step_impl = (int)value; return 0; }
     if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
     if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
+    if (option == TAROK_OPT_MATERIALISE && (value == 0 || value == 1)) { h->materialise = (int)value; return 0; }
     return fail(h, -1, "unknown option %d / value %lld", option, (long long)value);
 }
 
@@ -125,7 +127,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     tarok_env* h = new (std::nothrow) tarok_env();
     if (!h) return fail(nullptr, -4, "out of host memory");
     memset(&h->e, 0, sizeof(h->e));
-    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
+    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->materialise = 1; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;
@@ -147,6 +149,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     TK_ALLOC(h->e.mask, na * 8);
     TK_ALLOC(h->e.scores, na * 8);
     TK_ALLOC(h->e.stats, TAROK_STATS_LEN * 8);
+    TK_ALLOC(h->e.tricklog, 12 * na * 4);
     if (flags & TAROK_FLAG_HISTORY) {
         TK_ALLOC(h->e.hist, 48 * na);
         TK_ALLOC(h->e.hands0, 4 * na * 8);
@@ -179,7 +182,7 @@ int tarok_destroy(tarok_t* h) {
     if (h->exports.load() != 0) return fail(h, -5, "%d exported tensors still alive", h->exports.load());
     DeviceGuard dg(h->device);
     cudaFree(h->e.hands); cudaFree(h->e.piles); cudaFree(h->e.talon); cudaFree(h->e.torder);
-    cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats);
+    cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats); cudaFree(h->e.tricklog);
     cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist);
     if (h->st_perm) {
         cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down);
@@ -341,7 +344,8 @@ int tarok_score(tarok_t* h, int16_t* out_dev, void* stream) {
     DeviceGuard dg(h->device);
     u64* out = out_dev ? (u64*)out_dev : h->e.scores;
     u64 out_n = out_dev ? h->e.n : h->e.n_alloc;
-    tk::k_score<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, out, out_n);
+    if (h->materialise) tk::k_score<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, out, out_n);
+    else tk::k_score<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, out, out_n);
     TK_LAUNCH_OK(h);
     return 0;
 }
@@ -371,7 +375,8 @@ static int play_out_stepwise(tarok_t* h, uint32_t random_group, void* stream) {
         launch_step<true>(h, nullptr, S(stream));
         TK_LAUNCH_OK(h);
     }
-    tk::k_score<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
+    if (h->materialise) tk::k_score<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
+    else tk::k_score<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
     TK_LAUNCH_OK(h);
     return 0;
 }
@@ -398,7 +403,8 @@ int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game
         launch_step<true>(h, nullptr, S(stream));
         TK_LAUNCH_OK(h);
     }
-    tk::k_score<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
+    if (h->materialise) tk::k_score<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
+    else tk::k_score<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
     TK_LAUNCH_OK(h);
     return 0;
 }

@@ -22,6 +22,7 @@ constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane 
 struct Env {
     u64* hands; u64* piles; u64* talon; u64* torder; u64* meta; u64* mask; u64* scores;
     uint8_t* hist; u64* hands0; u64* discard; float* qmax_hist; long long* stats;
+    u32* tricklog;                         // [12][n_alloc]: trick k of game g = 4 cards (24 bit, play order) | winner << 24
     u64 n, n_alloc, first_gid;
     Rng rng;                               // seed + precomputed Philox round keys
 };
@@ -479,17 +480,13 @@ __device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const 
     u64 hand = hands.get(mover);
     const u32 contract = lo & 15u;
     const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
-    u64 talon = 0, order = 0;
-    if ((POS < 0 || POS == 3) && contract == C_KLOP) {
-        if (pos == 3 && ((lo >> M_TRICKS) & 15u) < 6) { talon = e.talon[g]; order = e.torder[g]; }
-    }
     if (RANDOM) {
         u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));
         u32 n = (u32)__popcll(legal);
         card = nth_set_bit(legal, play_draw<POS>(rnd, e.rng, e.first_gid + g, plays, n));
     }
     PlayResult pr;
-    meta = play_card<!RANDOM, POS>(meta, hand, card, talon, order, pr);
+    meta = play_card<!RANDOM, POS, false>(meta, hand, card, 0ull, 0ull, pr);
     next_mask = 0;
     if (!RANDOM && ((meta >> M_ERR) & 1ull)) {
         atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
@@ -498,9 +495,9 @@ __device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const 
     e.hands[mover * na + g] = hand;
     if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
     if ((POS < 0 || POS == 3) && pr.trick_done) {
-        u64* pp = e.piles + (pr.winner * na + g);
-        *pp |= pr.pile_bits;
-        if (pr.talon_clear) e.talon[g] = talon & ~pr.talon_clear;
+        // append-only trick log (4 B, coalesced) instead of a scattered read-modify-write of the winner's pile;
+        // k_score materialises the piles (and the Klop talon) from it
+        e.tricklog[(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
     }
     if (POS >= 0 && POS < 3) {                                   // same trick goes on: next seat follows the same lead
         next_mask = legal_moves(hands.get((mover + 1u) & 3u), true, (u32)(meta >> 32) & 63u, klop_rules(contract));
@@ -656,6 +653,59 @@ __global__ void __launch_bounds__(CTA) k_legal_mask(Env e, u64* __restrict__ out
 // score: Roka.prestej + the three start() epilogues; accumulates the statistics vector.
 // 56 B/deal algorithmic: R 4 piles 32 + talon 8 + meta 8, W int16[4] 8.
 // ------------------------------------------------------------------------------------------------
+// Piles are materialised here: pile[s] = what the exchange laid down (stored) | the tricks seat s won (trick log);
+// in Klop the talon loses the cards that went into tricks 1..6.  Idempotent.
+__device__ __forceinline__ void materialise(u64 meta, const uint2* log12, int which, u64 order,
+                                            u64& p0, u64& p1, u64& p2, u64& p3, u64& talon) {
+    const u32 tricks = mget(meta, M_TRICKS, 4);
+    const bool klop = mget(meta, M_CONTRACT, 4) == C_KLOP;
+#pragma unroll
+    for (u32 k = 0; k < 12; k++) {
+        if (k < tricks) {
+            const u32 entry = which ? log12[k].y : log12[k].x;
+            u64 tc;
+            const u64 b = trick_bits(entry, k, klop, order, tc);
+            const u32 w = entry >> 24;
+            p0 |= w == 0 ? b : 0ull; p1 |= w == 1 ? b : 0ull; p2 |= w == 2 ? b : 0ull; p3 |= w == 3 ? b : 0ull;
+            talon &= ~tc;
+        }
+    }
+}
+
+// MAT = write the materialised piles / talon back (the exported fields then hold the full piles); without it only the
+// scores and statistics are produced (pipelines that, like Tarok.paralel_start, only need the results).
+// Scores only (no per-seat piles): what each contract family's epilogue actually needs from the trick log.
+__device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int which, u64 order, u64 p0, u64 p1, u64 p2,
+                                              u64 p3, u64 talon) {
+    const u32 contract = mget(meta, M_CONTRACT, 4), decl = mget(meta, M_DECL, 2), tricks = mget(meta, M_TRICKS, 4);
+    if (is_navadna(contract)) {
+        const u32 team = mget(meta, M_TEAM, 4);
+        u64 pd = sel4(p0, p1, p2, p3, decl);              // stored piles hold only the declarer's discards so far
+        u64 tp = pd;
+#pragma unroll
+        for (u32 k = 0; k < 12; k++) {
+            if (k < tricks) {
+                const u32 entry = which ? log12[k].y : log12[k].x;
+                u64 tc;
+                const u64 b = trick_bits(entry, k, false, 0ull, tc);
+                const u32 w = entry >> 24;
+                tp |= ((team >> w) & 1u) ? b : 0ull;
+                pd |= w == decl ? b : 0ull;
+            }
+        }
+        return score_navadna(meta, tp, pd, talon);
+    }
+    if (is_berac(contract)) {
+        bool took = false;
+#pragma unroll
+        for (u32 k = 0; k < 12; k++) took |= k < tricks && ((which ? log12[k].y : log12[k].x) >> 24) == decl;
+        return score_berac(meta, took);
+    }
+    materialise(meta, log12, which, order, p0, p1, p2, p3, talon);
+    return contract == C_KLOP ? score_klop(p0, p1, p2, p3) : 0ull;
+}
+
+template <bool MAT>
 __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64 out_n) {
     u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
     const u64 na = e.n_alloc;
@@ -666,15 +716,32 @@ __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64
         ulonglong2 m = ld2(e.meta + g);
         ulonglong2 p0 = ld2(e.piles + g), p1 = ld2(e.piles + na + g), p2 = ld2(e.piles + 2 * na + g),
                    p3 = ld2(e.piles + 3 * na + g);
-        ulonglong2 t = ld2(e.talon + g);
+        ulonglong2 t = ld2(e.talon + g), o = ld2(e.torder + g);
+        const u32 most = max(mget(m.x, M_TRICKS, 4), mget(m.y, M_TRICKS, 4));
+        uint2 log12[12];
+#pragma unroll
+        for (u32 k = 0; k < 12; k++)
+            log12[k] = k < most ? *reinterpret_cast<const uint2*>(e.tricklog + k * na + g) : make_uint2(0u, 0u);
+        if (MAT) {
+            materialise(m.x, log12, 0, o.x, p0.x, p1.x, p2.x, p3.x, t.x);
+            materialise(m.y, log12, 1, o.y, p0.y, p1.y, p2.y, p3.y, t.y);
+            *reinterpret_cast<ulonglong2*>(e.piles + g) = p0; *reinterpret_cast<ulonglong2*>(e.piles + na + g) = p1;
+            *reinterpret_cast<ulonglong2*>(e.piles + 2 * na + g) = p2; *reinterpret_cast<ulonglong2*>(e.piles + 3 * na + g) = p3;
+            *reinterpret_cast<ulonglong2*>(e.talon + g) = t;
+        }
         e0 = ((m.x >> M_ERR) & 1ull) && g < e.n;
         e1 = ((m.y >> M_ERR) & 1ull) && g + 1 < e.n;
         f0 = mget(m.x, M_PHASE, 2) == PH_DONE && !((m.x >> M_ERR) & 1ull) && g < e.n;
         f1 = mget(m.y, M_PHASE, 2) == PH_DONE && !((m.y >> M_ERR) & 1ull) && g + 1 < e.n;
         c0 = mget(m.x, M_CONTRACT, 4); c1 = mget(m.y, M_CONTRACT, 4);
         pl0 = g < e.n ? mget(m.x, M_PLAYS, 6) : 0u; pl1 = g + 1 < e.n ? mget(m.y, M_PLAYS, 6) : 0u;
-        if (f0) s0 = score_game(m.x, p0.x, p1.x, p2.x, p3.x, t.x);
-        if (f1) s1 = score_game(m.y, p0.y, p1.y, p2.y, p3.y, t.y);
+        if (MAT) {
+            if (f0) s0 = score_game(m.x, p0.x, p1.x, p2.x, p3.x, t.x);
+            if (f1) s1 = score_game(m.y, p0.y, p1.y, p2.y, p3.y, t.y);
+        } else {
+            if (f0) s0 = score_from_log(m.x, log12, 0, o.x, p0.x, p1.x, p2.x, p3.x, t.x);
+            if (f1) s1 = score_from_log(m.y, log12, 1, o.y, p0.y, p1.y, p2.y, p3.y, t.y);
+        }
         if (g + 1 < out_n) st2(out + g, s0, s1);
         else if (g < out_n) out[g] = s0;
     }
@@ -693,7 +760,7 @@ struct FusedGame { u64 h0, h1, h2, h3, p0, p1, p2, p3, talon, order, meta; };
 // One card play of the fused rollout at trick position J (compile-time: the loop over a trick is unrolled).
 template <int J>
 __device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, const Rng& rng, u64 gid, u32 trick, bool klop,
-                                           uint8_t* hist_row, u64 na) {
+                                           uint8_t* hist_row, u64 na, u32* log_row = nullptr) {
     const u32 mover = (((u32)f.meta >> M_LEADER) + (u32)J) & 3u;
     u64 hand = sel4(f.h0, f.h1, f.h2, f.h3, mover);
     const u64 legal = legal_moves(hand, J != 0, (u32)(f.meta >> 32) & 63u, klop);
@@ -704,6 +771,7 @@ __device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, cons
     if (hist_row) hist_row[(u64)J * na] = (uint8_t)((mover << 6) | card);
     f.h0 = mover == 0 ? hand : f.h0; f.h1 = mover == 1 ? hand : f.h1; f.h2 = mover == 2 ? hand : f.h2; f.h3 = mover == 3 ? hand : f.h3;
     if (J == 3) {
+        if (log_row) *log_row = ((u32)(f.meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
         const u64 b = pr.pile_bits;
         f.p0 |= pr.winner == 0 ? b : 0ull; f.p1 |= pr.winner == 1 ? b : 0ull;
         f.p2 |= pr.winner == 2 ? b : 0ull; f.p3 |= pr.winner == 3 ? b : 0ull;
@@ -767,7 +835,7 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
             fused_play<0>(fg, blk, e.rng, gid, trick, klop, hrow, na);
             fused_play<1>(fg, blk, e.rng, gid, trick, klop, hrow, na);
             fused_play<2>(fg, blk, e.rng, gid, trick, klop, hrow, na);
-            fused_play<3>(fg, blk, e.rng, gid, trick, klop, hrow, na);
+            fused_play<3>(fg, blk, e.rng, gid, trick, klop, hrow, na, write_state ? e.tricklog + (u64)trick * na + g : nullptr);
         }
         h0 = fg.h0; h1 = fg.h1; h2 = fg.h2; h3 = fg.h3; p0 = fg.p0; p1 = fg.p1; p2 = fg.p2; p3 = fg.p3;
         talon = fg.talon; meta = fg.meta;

@@ -269,7 +269,9 @@ struct PlayResult {
 // players pick from the legal set by construction and skip it.
 // POS >= 0: the caller knows (and has checked) that the game is at position POS of its trick -- lock-step batches --
 // so the trick-position arithmetic and the trick-end branch fold at compile time; POS = -1 reads it from meta.
-template <bool CHECK, int POS = -1>
+// BITS = also produce the bitboard the winner collects (+ the Klop talon card); the stepwise kernels do not need it:
+// they append (cards, winner) to the trick log and the piles are materialised at scoring time (trick_bits below).
+template <bool CHECK, int POS = -1, bool BITS = true>
 __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talon, u64 talon_order,
                                          PlayResult& out) {
     out.trick_done = false; out.winner = 0; out.pile_bits = 0; out.talon_clear = 0;
@@ -294,19 +296,33 @@ __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talo
     // trick complete
     const u32 tricks = (lo >> M_TRICKS) & 15u;
     const u32 w = (((lo >> M_LEADER) & 3u) + trick_winner(tr)) & 3u;
-    u64 bits = (1ull << (tr & 63u)) | (1ull << ((tr >> 6) & 63u)) | (1ull << ((tr >> 12) & 63u)) | (1ull << (tr >> 18));
-    if (contract == C_KLOP && tricks < 6) {
-        u64 tc = 1ull << ((talon_order >> (6 * (5 - tricks))) & 63ull);
-        out.talon_clear = tc & talon;
-        bits |= out.talon_clear;
+    if (BITS) {
+        u64 bits = (1ull << (tr & 63u)) | (1ull << ((tr >> 6) & 63u)) | (1ull << ((tr >> 12) & 63u)) | (1ull << (tr >> 18));
+        if (contract == C_KLOP && tricks < 6) {
+            u64 tc = 1ull << ((talon_order >> (6 * (5 - tricks))) & 63ull);
+            out.talon_clear = tc & talon;
+            bits |= out.talon_clear;
+        }
+        out.pile_bits = bits;
     }
-    out.trick_done = true; out.winner = w; out.pile_bits = bits;
+    out.trick_done = true; out.winner = w;
     const bool fin = tricks == 11 || (is_berac(contract) && w == ((lo >> M_DECL) & 3u));
     constexpr u32 CLEAR = (3u << M_LEADER) | (3u << M_POS) | (15u << M_TRICKS) | (3u << M_WINNER) | (1u << M_TRICKDONE)
                         | (3u << M_PHASE);
     lo = (lo & ~CLEAR) | (w << M_LEADER) | ((tricks + 1u) << M_TRICKS) | (w << M_WINNER) | (1u << M_TRICKDONE)
        | ((fin ? (u32)PH_DONE : (u32)PH_PLAY) << M_PHASE);              // the finished trick stays visible in hi
     return ((u64)hi << 32) | lo;
+}
+
+// Trick-log entry: the four cards in play order (24 bits) | winner seat << 24.  The bitboard the winner collected in
+// trick k: its four cards, plus in Klop the talon card popped from the END of the ordered talon in tricks 1..6
+// (Klop.py:67-71, Q4), which is also returned in `talon_card`.
+__device__ __forceinline__ u64 trick_bits(u32 entry, u32 k, bool is_klop, u64 talon_order, u64& talon_card) {
+    u64 bits = (1ull << (entry & 63u)) | (1ull << ((entry >> 6) & 63u)) | (1ull << ((entry >> 12) & 63u))
+             | (1ull << ((entry >> 18) & 63u));
+    talon_card = 0;
+    if (is_klop && k < 6) { talon_card = 1ull << ((talon_order >> (6 * (5 - k))) & 63ull); bits |= talon_card; }
+    return bits;
 }
 
 // Legal mask of the seat to move given the (already updated) meta and that seat's hand.
@@ -320,35 +336,49 @@ __device__ __forceinline__ u32 mover_of(u64 meta) { const u32 lo = (u32)meta; re
 // ---- scoring --------------------------------------------------------------------------------------
 // Epilogues: Navadna_igra.start (Navadna_igra.py:80-113, Q6/Q7), Klop.start (Klop.py:36-45, Q5),
 // Berac.start (Berac.py:33-44).  Returns the four scores packed as int16 x4 (seat 0 in the low half).
+__device__ __forceinline__ u64 pack_scores(int s0, int s1, int s2, int s3) {
+    return (u64)(uint16_t)s0 | ((u64)(uint16_t)s1 << 16) | ((u64)(uint16_t)s2 << 32) | ((u64)(uint16_t)s3 << 48);
+}
+
+// Navadna_igra.start epilogue from the team's pile union `tp` and the declarer's own pile `pd` (Navadna_igra.py:80-113).
+__device__ __forceinline__ u64 score_navadna(u64 meta, u64 tp, u64 pd, u64 talon) {
+    const u32 contract = mget(meta, M_CONTRACT, 4), team = mget(meta, M_TEAM, 4), king = mget(meta, M_KING, 3);
+    const bool to_team = contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING
+                      && (pd & (1ull << ((king & 3u) * 8 + 7)));
+    if (to_team) tp |= talon;                             // leftover talon to a lone declarer who took the called king (Q7)
+    const int v = prestej(tp);
+    const int r = v - 35 + 2;                             // 5*round((v-35)/5): no ties for integers
+    const int q = (r >= 0 ? r / 5 : -((-r + 4) / 5)) * 5; // floor division
+    const int val = (v > 35 ? 10 * (int)contract : -10 * (int)contract) + q;
+    return pack_scores((team & 1u) ? val : 0, (team & 2u) ? val : 0, (team & 4u) ? val : 0, (team & 8u) ? val : 0);
+}
+
+// Klop.start epilogue (Klop.py:36-45): minus the own points; if anybody has more than 35 everybody writes 0 (Q5).
+__device__ __forceinline__ u64 score_klop(u64 p0, u64 p1, u64 p2, u64 p3) {
+    const int a = prestej(p0), b = prestej(p1), c = prestej(p2), d = prestej(p3);
+    const bool any = a > 35 || b > 35 || c > 35 || d > 35;
+    return pack_scores(any ? 0 : -a, any ? 0 : -b, any ? 0 : -c, any ? 0 : -d);
+}
+
+// Berac.start (Berac.py:33-44): -70/-90 as soon as the declarer took a trick, else +70/+90; the others 0.
+__device__ __forceinline__ u64 score_berac(u64 meta, bool declarer_took_a_trick) {
+    const u32 decl = mget(meta, M_DECL, 2);
+    const int v = mget(meta, M_CONTRACT, 4) == C_ODPRTI_BERAC ? 90 : 70;
+    const int x = declarer_took_a_trick ? -v : v;
+    return pack_scores(decl == 0 ? x : 0, decl == 1 ? x : 0, decl == 2 ? x : 0, decl == 3 ? x : 0);
+}
+
 __device__ __forceinline__ u64 score_game(u64 meta, u64 p0, u64 p1, u64 p2, u64 p3, u64 talon) {
-    u32 contract = mget(meta, M_CONTRACT, 4);
-    u32 decl = mget(meta, M_DECL, 2);
-    int s[4] = {0, 0, 0, 0};
+    const u32 contract = mget(meta, M_CONTRACT, 4);
+    const u32 decl = mget(meta, M_DECL, 2);
     if (is_navadna(contract)) {
-        u32 team = mget(meta, M_TEAM, 4);
-        u32 king = mget(meta, M_KING, 3);
-        u64 tp = ((team & 1u) ? p0 : 0) | ((team & 2u) ? p1 : 0) | ((team & 4u) ? p2 : 0) | ((team & 8u) ? p3 : 0);
-        u64 pd = sel4(p0, p1, p2, p3, decl);
-        bool to_team = contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING
-                    && (pd & (1ull << ((king & 3u) * 8 + 7)));
-        if (to_team) tp |= talon;
-        int v = prestej(tp);
-        int r = v - 35 + 2;                               // 5*round((v-35)/5): no ties for integers
-        int q = (r >= 0 ? r / 5 : -((-r + 4) / 5)) * 5;   // floor division
-        int val = (v > 35 ? 10 * (int)contract : -10 * (int)contract) + q;
-#pragma unroll
-        for (int i = 0; i < 4; i++) s[i] = ((team >> i) & 1u) ? val : 0;
-    } else if (contract == C_KLOP) {
-        int a = prestej(p0), b = prestej(p1), c = prestej(p2), d = prestej(p3);
-        bool any = a > 35 || b > 35 || c > 35 || d > 35;  // then everybody writes 0 (Klop.py:38-42, Q5)
-        s[0] = any ? 0 : -a; s[1] = any ? 0 : -b; s[2] = any ? 0 : -c; s[3] = any ? 0 : -d;
-    } else if (is_berac(contract)) {
-        int v = contract == C_ODPRTI_BERAC ? 90 : 70;
-        u64 pd = sel4(p0, p1, p2, p3, decl);              // no exchange in Berac: pile != 0 <=> took a trick
-#pragma unroll
-        for (int i = 0; i < 4; i++) s[i] = ((u32)i == decl) ? (pd ? -v : v) : 0;
+        const u32 team = mget(meta, M_TEAM, 4);
+        const u64 tp = ((team & 1u) ? p0 : 0) | ((team & 2u) ? p1 : 0) | ((team & 4u) ? p2 : 0) | ((team & 8u) ? p3 : 0);
+        return score_navadna(meta, tp, sel4(p0, p1, p2, p3, decl), talon);
     }
-    return (u64)(uint16_t)s[0] | ((u64)(uint16_t)s[1] << 16) | ((u64)(uint16_t)s[2] << 32) | ((u64)(uint16_t)s[3] << 48);
+    if (contract == C_KLOP) return score_klop(p0, p1, p2, p3);
+    if (is_berac(contract)) return score_berac(meta, sel4(p0, p1, p2, p3, decl) != 0);   // no exchange in Berac
+    return 0;
 }
 
 }  // namespace tk

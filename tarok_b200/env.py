@@ -127,6 +127,10 @@ class TarokEnv:
         """0 auto, 1 plain play_step kernel, 2 persistent TMA-staged kernel (A/B measurements)."""
         self._check(self._lib.tarok_set_option(self._h, 1, int(impl)))
 
+    def set_materialise(self, on: bool):
+        """Whether ``score()`` writes the full piles / Klop talon back (default) or only produces scores + statistics."""
+        self._check(self._lib.tarok_set_option(self._h, 4, 1 if on else 0))
+
     def set_lockstep(self, on: bool):
         """Trick-position-specialised play_step for lock-step batches (default on; the kernel verifies the hint)."""
         self._check(self._lib.tarok_set_option(self._h, 3, 1 if on else 0))

@@ -435,6 +435,7 @@ class Tarok:
         in the kernels; only the 32-entry statistics vector comes back."""
         seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
         env = E.TarokEnv(st_iger, seed=seed, device=self.device)
+        env.set_materialise(False)                       # only the result sums are needed (Tarok.py:59-61)
         env.rollout(E.MODE_AUCTION_BOT, first_game_id=0, fused=False)
         st = env.stats()
         self.statistika = st

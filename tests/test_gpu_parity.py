@@ -348,3 +348,17 @@ def test_config5_size_properties():
     assert (env.stats()[:21] == st[:21]).all()
     del hands, meta, err, berac, allc, plays        # zero-copy views must be dropped before the handle can be destroyed
     env.close()
+
+
+@pytest.mark.parametrize("mode", [0, 7, 9, 16, 17, 18])
+def test_scores_only_path_matches_oracle(oracle, mode):
+    """tarok_score without pile materialisation (TAROK_OPT_MATERIALISE = 0): same scores and statistics."""
+    n, seed = 30001, 808
+    ref = oracle.rollout(seed, 64, n, mode, full=False)
+    env = _env(n, seed=seed)
+    env.set_materialise(False)
+    env.rollout(mode, first_game_id=64)
+    assert (env.scores[:n].cpu().numpy() == ref["scores"]).all()
+    st = env.stats()
+    assert (st[0:8] == ref["stats"][0:8]).all() and st[19] == ref["stats"][8]
+    env.close()

@@ -27,5 +27,8 @@ if __name__ == "__main__":
     print("setup+48steps %8.1f us" % timed(steps))
     env.setup_synth(mode, 0); env.step_random(48)
     print("score         %8.1f us" % timed(lambda: env.score()))
+    env.set_materialise(False)
+    print("score (no mat)%8.1f us" % timed(lambda: env.score()))
+    env.set_materialise(True)
     print("fused rollout %8.1f us" % timed(lambda: env.rollout(mode, 0, fused=True)))
     print("stepwise roll %8.1f us" % timed(lambda: env.rollout(mode, 0, fused=False)))
