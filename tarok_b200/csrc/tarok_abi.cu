@@ -150,6 +150,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     TK_ALLOC(h->e.scores, na * 8);
     TK_ALLOC(h->e.stats, TAROK_STATS_LEN * 8);
     TK_ALLOC(h->e.tricklog, 12 * na * 4);
+    cudaMemset(h->e.tricklog, 0, 12 * na * 4);
     if (flags & TAROK_FLAG_HISTORY) {
         TK_ALLOC(h->e.hist, 48 * na);
         TK_ALLOC(h->e.hands0, 4 * na * 8);

@@ -717,11 +717,9 @@ __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64
         ulonglong2 p0 = ld2(e.piles + g), p1 = ld2(e.piles + na + g), p2 = ld2(e.piles + 2 * na + g),
                    p3 = ld2(e.piles + 3 * na + g);
         ulonglong2 t = ld2(e.talon + g), o = ld2(e.torder + g);
-        const u32 most = max(mget(m.x, M_TRICKS, 4), mget(m.y, M_TRICKS, 4));
-        uint2 log12[12];
-#pragma unroll
-        for (u32 k = 0; k < 12; k++)
-            log12[k] = k < most ? *reinterpret_cast<const uint2*>(e.tricklog + k * na + g) : make_uint2(0u, 0u);
+        uint2 log12[12];                                  // all twelve entries are fetched up front (one memory phase);
+#pragma unroll                                            // entries past the tricks played are stale and never looked at
+        for (u32 k = 0; k < 12; k++) log12[k] = *reinterpret_cast<const uint2*>(e.tricklog + k * na + g);
         if (MAT) {
             materialise(m.x, log12, 0, o.x, p0.x, p1.x, p2.x, p3.x, t.x);
             materialise(m.y, log12, 1, o.y, p0.y, p1.y, p2.y, p3.y, t.y);
