@@ -460,6 +460,12 @@ __global__ void __launch_bounds__(CTA) k_setup_synth(Env e, u32 mode) {
     if (e.discard) e.discard[g] = dout;
 }
 
+// The two card ids of a lane's game pair.  The caller's array holds exactly n_games bytes: never read past it.
+__device__ __forceinline__ u32 load_actions(const uint8_t* __restrict__ action, u32 g, u64 n) {
+    if ((u64)g + 1 < n) return *reinterpret_cast<const unsigned short*>(action + g);
+    return (u64)g < n ? (u32)action[g] | 0xFF00u : 0xFFFFu;
+}
+
 // Programmatic dependent launch (PDL): consecutive play_step launches are chained so that the CTAs of step
 // t+1 are scheduled while the tail of step t drains; they park at griddepcontrol.wait until step t has
 // completed and its writes are visible.  This removes the launch ramp / tail bubble between the 48 steps.
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restric
     ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + (na + g)), h2 = ld2(e.hands + (2 * na + g)),
                h3 = ld2(e.hands + (3 * na + g));
     u32 act = 0;
-    if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
+    if (!RANDOM) act = load_actions(action, g, e.n);
     const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
     const u32 p0 = ((u32)(m.x >> 32) >> (M_PLAYS - 32)) & 63u, p1 = ((u32)(m.y >> 32) >> (M_PLAYS - 32)) & 63u;
     const bool in_step = (!a0 || p0 == (u32)hint) && (!a1 || p1 == (u32)hint);
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __res
         if (threadIdx.x == 0 && tile + gridDim.x < tiles) fetch(tile + gridDim.x, s ^ 1u);
         const u32 g = tile * TILE + l;
         u32 act = 0;
-        if (!RANDOM) act = *reinterpret_cast<const unsigned short*>(action + g);
+        if (!RANDOM) act = load_actions(action, g, e.n);
         mbar_wait(&full[s], (it >> 1) & 1u);
         ulonglong2 m = *reinterpret_cast<const ulonglong2*>(&stage[s].meta[l]);
         const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;

@@ -200,14 +200,10 @@ class TarokEnv:
     def step(self, cards):
         """One card per live game (``igraj_karto``); cards: uint8 [n] card ids."""
         if isinstance(cards, torch.Tensor) and cards.dtype == torch.uint8 and cards.device == self.torch_device \
-                and cards.is_contiguous() and cards.numel() == self.n_alloc:
-            x = cards                    # already padded to the kernel tile (e.g. from select_action)
+                and cards.is_contiguous() and cards.numel() in (self.n, self.n_alloc):
+            x = cards                    # used in place (the kernel reads the first n_games bytes only)
         else:
             x = self._dev_u8(cards, (self.n,))
-        if x.numel() != self.n_alloc:    # kernel reads two actions per lane
-            pad = torch.zeros(self.n_alloc, dtype=torch.uint8, device=self.torch_device)
-            pad[: self.n] = x
-            x = pad
         self._check(self._lib.tarok_step(self._h, C.c_void_p(x.data_ptr()), self._stream()))
 
     def step_random(self, count: int = 1):
