@@ -362,3 +362,25 @@ def test_scores_only_path_matches_oracle(oracle, mode):
     st = env.stats()
     assert (st[0:8] == ref["stats"][0:8]).all() and st[19] == ref["stats"][8]
     env.close()
+
+
+@pytest.mark.parametrize("impl,pdl,lock", [(1, False, False), (1, True, False), (1, False, True), (2, True, False), (2, False, False)])
+def test_every_play_step_variant_matches_oracle(oracle, impl, pdl, lock):
+    """The selectable play_step implementations (plain / TMA-staged, PDL on/off, lock-step specialisation on/off)
+    all produce the oracle's games; the default (plain + PDL + lock-step) is what the other tests run."""
+    n, seed = 70001, 31
+    for mode in (17, 0):
+        ref = oracle.rollout(seed, 10, n, mode)
+        env = _env(n, seed=seed, history=True)
+        env.set_step_impl(impl); env.set_pdl(pdl); env.set_lockstep(lock)
+        env.rollout(mode, first_game_id=10)
+        assert (env.scores[:n].cpu().numpy() == ref["scores"]).all()
+        hist = env.hist[:, :n].cpu().numpy().T
+        played = ref["cards"] != 0xFF
+        assert ((hist & 63)[played] == ref["cards"][played]).all()
+        # externally supplied actions through the same variant: replay the oracle's cards
+        env.setup_synth(mode, 10)
+        for t in range(48):
+            env.step(ref["cards"][:, t])
+        assert (env.score().cpu().numpy() == ref["scores"]).all() and env.errors() == int(ref["err"].sum())
+        env.close()
