@@ -361,6 +361,8 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(mode, n),
                        "games_per_gpu": n, "mode": mode, "seed": hex(SEED),
+                       "outputs": "per-deal scores (int16 x4) + the all-reduced statistics vector = Tarok.rezultati; won-card piles stay "
+                                  "in the 4-byte-per-trick log (TAROK_OPT_MATERIALISE=0), as Tarok.paralel_start never returns them",
                        "l2": "160 MiB flush write between iterations (inside the timed region); within one iteration the 48 "
                              "play_steps revisit the %d MB state as the workload prescribes" % (n * 104 >> 20)},
             "deals_per_sec": deals / (ms * 1e-3), "env_steps": env_steps, "deals": deals, "error_games": errors,
