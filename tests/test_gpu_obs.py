@@ -140,3 +140,33 @@ def test_hand_and_exchange_observations_and_exchange_decision(golden):
     assert env2.errors() <= 2                            # only hands with fewer than k discardable cards (Q19)
     assert len(torch.unique(gr)) >= 2
     env.close(); env2.close()
+
+
+def test_observation_invariants_at_config4_size():
+    """65,536 envs, random play: structural invariants of the expanded observations at every 7th decision."""
+    import torch
+    from tarok_b200.env import TarokEnv
+    n = 65536
+    env = TarokEnv(n, seed=9, history=True)
+    env.setup_synth(17)                                   # all contracts
+    for t in range(48):
+        if t % 7 == 3:
+            kinds, rows = env.obs_shape()
+            live = kinds != 255
+            key = kinds.to(torch.int32) * 64 + rows.to(torch.int32)
+            for k in torch.unique(key[live]).tolist():
+                kind, T = k // 64, k % 64
+                sel = torch.nonzero(key == k).flatten().to(torch.int32)
+                arrs, ok = env.obs_expand(kind, T, sel)
+                assert bool(ok.all())
+                opp, hand, mozne = arrs[0], arrs[2] if kind == 1 else arrs[1], arrs[-1]
+                assert bool((opp.sum(dim=(2, 3)) <= 1).all())                    # at most one card per row
+                own_rows = hand.sum(dim=2) > 0
+                assert bool(((opp.sum(dim=(2, 3)) > 0) & own_rows).sum() == 0)    # a row is an opponent's play or mine
+                assert bool(((opp.sum(dim=(2, 3)) > 0) | own_rows).sum(dim=1).eq(t).all())   # t plays so far
+                assert bool((hand.sum(dim=2)[own_rows] <= 12).all())
+                legal = env.mask[:n][sel.long()]
+                bits = ((legal.unsqueeze(1) >> torch.arange(54, device="cuda")) & 1).float()
+                assert bool((mozne == bits).all())
+        env.step_random(1)
+    env.close()
