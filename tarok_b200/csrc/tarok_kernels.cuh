@@ -3,7 +3,8 @@
 // HBM layout (structure of arrays, one 64-bit word per game per field, n_alloc = n rounded up to
 // the 512-game CTA tile, every array 256-byte aligned):
 //   hands[4][n_alloc]  piles[4][n_alloc]  talon[n_alloc]  torder[n_alloc]  meta[n_alloc]
-//   mask[n_alloc]  scores[n_alloc] (int16 x4)  hist[48][n_alloc] (uint8, optional)
+//   mask[n_alloc]  scores[n_alloc] (int16 x4)  tricklog[12][n_alloc] (uint32)
+//   optional (TAROK_FLAG_HISTORY): hist[48][n_alloc] (uint8)  hands0[4][n_alloc]  discard[n_alloc]  qmax_hist[48][n_alloc] (float)
 // The stepwise kernels give each lane TWO consecutive games so that every per-field access is one
 // 128-bit load/store (ld.global.v2.u64): a warp covers a 64-game tile = 512 contiguous bytes per
 // field.  Per-game logic is branch-light integer code (popc / shifts / selects, tarok_rules.cuh).
@@ -405,7 +406,8 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
 // ------------------------------------------------------------------------------------------------
 // play_step: one card per live game per launch -- THE hot kernel (48 launches per deal).
 // Algorithmic traffic per env-step: R meta 8 + hands 16 + action 1, W hand 8 + meta 8
-// + mask 8, per trick /4: pile RW 16 (+ Klop talon) = 64 B.
+// + mask 8, per trick /4: pile RW 16 (+ Klop talon) = 64 B.  What this kernel moves: R meta 8 + all four hands 32
+// (coalesced, instead of gathering two), W hand 8 + meta 8 + mask 8, per trick /4: a 4-byte trick-log entry.
 // ------------------------------------------------------------------------------------------------
 // Where a lane finds the four hands of its game: registers (plain kernel) or the TMA-staged tile in shared
 // memory, where picking the mover's hand is ONE indexed 64-bit LDS instead of a select chain.
