@@ -67,9 +67,13 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise TarokLibraryError(
-            "%s is missing: build it with `python -m tarok_b200.build` (nvcc, sm_100a). "
-            "tarok_b200 has no CPU fallback." % LIB_PATH)
+        try:                                   # build the product in-tree (nvcc, sm_100a); this is not a fallback
+            from .build import build_library
+            build_library()
+        except Exception as ex:
+            raise TarokLibraryError(
+                "%s is missing and could not be built (%s): run `python -m tarok_b200.build` (nvcc, sm_100a). "
+                "tarok_b200 has no CPU fallback." % (LIB_PATH, str(ex)[:200]))
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

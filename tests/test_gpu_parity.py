@@ -384,3 +384,41 @@ def test_every_play_step_variant_matches_oracle(oracle, impl, pdl, lock):
             env.step(ref["cards"][:, t])
         assert (env.score().cpu().numpy() == ref["scores"]).all() and env.errors() == int(ref["err"].sum())
         env.close()
+
+
+def test_error_paths_are_loud():
+    """Bad arguments and bad inputs come back as error codes / error bits with a message, never silently."""
+    import torch
+    from tarok_b200 import _lib
+    from tarok_b200.env import TarokEnv
+    with pytest.raises(_lib.TarokLibraryError, match="n_games"):
+        TarokEnv(0)
+    env = _env(600, history=False)
+    with pytest.raises(_lib.TarokLibraryError, match="bad contract mode"):
+        env.force_contract_synth(12)
+    with pytest.raises(_lib.TarokLibraryError, match="bad auction mode"):
+        env.auction_synth(3)
+    with pytest.raises(_lib.TarokLibraryError, match="HISTORY"):
+        env.view(7)                                              # hist was not requested
+    with pytest.raises(ValueError):
+        env.set_deals(np.zeros((599, 54), np.uint8))             # wrong shape
+    # a deal that is not a permutation of the 54 cards is flagged per game and never played
+    perm = np.tile(np.arange(54, dtype=np.uint8), (600, 1))
+    perm[7, 3] = perm[7, 4]                                       # duplicate card
+    perm[9, 0] = 77                                               # out of range
+    env.set_deals(perm)
+    env.force_contract_synth(0)
+    m = _meta(env)
+    assert m["err"].nonzero()[0].tolist() == [7, 9] and (m["phase"][[7, 9]] == 3).all()
+    env.step_random(48)
+    sc = env.score().cpu().numpy()
+    assert (sc[[7, 9]] == 0).all()
+    st = env.stats()
+    assert st[20] == 2 and st[18] == 598
+    # a handle cannot be destroyed under a live zero-copy view
+    view = env.meta
+    env._views.clear()
+    with pytest.raises(_lib.TarokLibraryError, match="exported tensors still alive"):
+        env._check(env._lib.tarok_destroy(env._h))
+    del view, m
+    env.close()
