@@ -206,3 +206,35 @@ def test_host_side_bots_through_the_callback_path():
     t.paralel_start()
     assert all(isinstance(v, int) for v in t.rezultati.values())
     assert all(len(b.roka[i]) == 0 for b in bots for i in range(32))     # Bot bids never reach Berac: all 48 cards played
+
+
+def test_reference_exceptions_are_reproduced():
+    """Illegal card -> the reference's exception text (Navadna_igra.py:125-126); four distinct names required (Tarok.py:9)."""
+    from tarok_b200 import Bot_igralec, Igra, Karta, Tarok
+
+    class Goljuf(Bot_igralec):
+        device_policy = None
+
+        def igraj_karto(self, karte_na_mizi, mozne, zgodovina, id_igre):
+            held = {k.v_id() for k in self.roka[id_igre]}
+            return Karta.iz_id(next(i for i in range(54) if i not in held))      # a card the player does not hold
+
+    class Tih(Bot_igralec):
+        device_policy = None
+
+        def licitiram(self, min_igra, id_igre, obvezno=None, prednost=False):
+            from tarok_b200 import Igralec, Tip_igre
+            return Igralec.licitiram(self, Tip_igre.Naprej, min_igra, id_igre, obvezno, prednost)
+
+    players = [Goljuf(), Tih(), Tih(), Tih()]
+    with pytest.raises(Exception, match="Karte ne mores igarti"):
+        list(Igra(players).start())
+    same = [Bot_igralec(ime="a"), Bot_igralec(ime="a"), Bot_igralec(ime="b"), Bot_igralec(ime="c")]
+    with pytest.raises(AssertionError):
+        Tarok(same, 4)
+    # everybody passes -> forehand must play Klop (Igra.py:92-94)
+    quiet = [Tih() for _ in range(4)]
+    t = Tarok(quiet, 8)
+    t.izpis = False
+    t.paralel_start()
+    assert all(v <= 0 for v in t.rezultati.values())                 # Klop scores are never positive (Klop.py:36-42)
