@@ -149,7 +149,15 @@ def cpu_port_rate(mode, target_seconds, threads_note=True):
     t = time.perf_counter()
     st = O.rollout_stats_only(SEED, 0, n, mode)
     dt = time.perf_counter() - t
-    return {"steps_per_s": float(st[8]) / dt, "deals_per_s": n / dt, "cores": cores, "deals": n, "seconds": dt}
+    out = {"steps_per_s": float(st[8]) / dt, "deals_per_s": n / dt, "cores": cores, "deals": n, "seconds": dt}
+    O.set_threads(1)                                   # P = 1 beside P = all
+    n1 = max(int(n / dt / cores * 2.0), 10000)
+    t = time.perf_counter()
+    st1 = O.rollout_stats_only(SEED, 0, n1, mode)
+    dt1 = time.perf_counter() - t
+    O.use_all_threads()
+    out["single_core_steps_per_s"] = float(st1[8]) / dt1
+    return out
 
 
 def run_reference(args, rank):
@@ -353,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
         r = cpu_port_rate(mode, 12.0)
         cpu = {"value": r["steps_per_s"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
                "sample": "%d deals of the same workload (%.1f s, OpenMP over %d threads)" % (r["deals"], r["seconds"], r["cores"]),
-               "deals_per_sec": r["deals_per_s"]}
+               "deals_per_sec": r["deals_per_s"], "single_core_value": r["single_core_steps_per_s"]}
 
     if rank == 0:
         out = {

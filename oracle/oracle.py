@@ -157,3 +157,8 @@ def use_all_threads():
         n = os.cpu_count() or 1
     lib().syn_set_threads(C.c_int(n))
     return int(lib().syn_max_threads())
+
+
+def set_threads(n: int) -> int:
+    lib().syn_set_threads(C.c_int(int(n)))
+    return int(lib().syn_max_threads())
