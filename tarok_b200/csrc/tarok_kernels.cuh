@@ -172,7 +172,7 @@ __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
     return d;
 }
 
-__global__ void __launch_bounds__(CTA) k_deal(Env e) {
+__global__ void __launch_bounds__(CTA, 4) k_deal(Env e) {
     u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
     if (g >= e.n_alloc) return;
     const u64 na = e.n_alloc;
