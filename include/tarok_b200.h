@@ -136,6 +136,12 @@ int tarok_score(tarok_t* h, int16_t* out_dev /* [n_games,4] or NULL */, void* st
 int tarok_reset_stats(tarok_t* h, void* stream);
 int tarok_read_stats(tarok_t* h, int64_t* out_host /* [32] */, void* stream); /* synchronises stream */
 
+/* ---- multi-GPU: the only exchange on the path ------------------------------------ */
+/* Sums the statistics vector over all ranks of `nccl_comm` (an ncclComm_t passed as void*) into out_dev (int64 [32]
+   on this device): one ncclAllReduce(ncclSum, ncclInt64) on the caller's stream, i.e. Tarok.rezultati (Tarok.py:59-61)
+   for game shards spread over several GPUs.  The handle's own vector is left untouched.  libnccl is dlopen'ed. */
+int tarok_allreduce_stats(tarok_t* h, void* nccl_comm, int64_t* out_dev, void* stream);
+
 /* ---- whole deals ----------------------------------------------------------------------------- */
 /* deal + contract(mode) + talon exchange with device-side (Philox) decisions in ONE launch; the state it
    leaves is bit-identical to tarok_deal + tarok_auction_synth/tarok_force_contract_synth + tarok_exchange_synth. */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "tarok_score": (_I, [_VP, _VP, _VP]),
     "tarok_reset_stats": (_I, [_VP, _VP]),
     "tarok_read_stats": (_I, [_VP, _VP, _VP]),
+    "tarok_allreduce_stats": (_I, [_VP, _VP, _VP, _VP]),
     "tarok_setup_synth": (_I, [_VP, _U32, _U64, _VP]),
     "tarok_rollout_stepwise": (_I, [_VP, _U32, _U64, _VP]),
     "tarok_rollout_fused": (_I, [_VP, _U32, _U64, _VP]),

@@ -2,6 +2,8 @@
 // No torch, no C++ types across the boundary.  Every launch goes to the caller's stream.
 #include "../../include/tarok_b200.h"
 
+#include <dlfcn.h>
+
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -364,6 +366,29 @@ int tarok_read_stats(tarok_t* h, int64_t* out_host, void* stream) {
     DeviceGuard dg(h->device);
     TK_CUDA(h, cudaMemcpyAsync(out_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, S(stream)));
     TK_CUDA(h, cudaStreamSynchronize(S(stream)));
+    return 0;
+}
+
+// ---- the one collective: all-reduce of the statistics vector (NCCL over NVLink / NVSwitch) ------------------------
+// libnccl is resolved at run time (the process that owns the communicator has it loaded already), so the library
+// itself carries no link-time dependency on NCCL.
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+
+int tarok_allreduce_stats(tarok_t* h, void* nccl_comm, int64_t* out_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!nccl_comm || !out_dev) return fail(h, -1, "nccl_comm/out_dev is null");
+    static nccl_allreduce_fn fn = nullptr;
+    if (!fn) {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+        if (!lib) return fail(h, -6, "libnccl.so.2 not found: %s", dlerror());
+        fn = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+        if (!fn) return fail(h, -6, "ncclAllReduce not found in libnccl");
+    }
+    DeviceGuard dg(h->device);
+    const int rc = fn(h->e.stats, out_dev, TAROK_STATS_LEN, /*ncclInt64*/ 4, /*ncclSum*/ 0, nccl_comm, S(stream));
+    if (rc != 0) return fail(h, -6, "ncclAllReduce failed with code %d", rc);
     return 0;
 }
 

@@ -48,6 +48,45 @@ def allreduce_stats(stats: torch.Tensor) -> torch.Tensor:
     return stats
 
 
+class NcclComm:
+    """A raw NCCL communicator (ncclComm_t) for ``tarok_allreduce_stats``, bootstrapped over an initialised
+    ``torch.distributed`` group: rank 0's ncclUniqueId is broadcast, every rank calls ncclCommInitRank.  ctypes only."""
+
+    def __init__(self, device: int):
+        import ctypes as C
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_byte * 128)]
+
+        self._C, self._nccl = C, C.CDLL("libnccl.so.2")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = UniqueId()
+        if rank == 0:
+            self._ok(self._nccl.ncclGetUniqueId(C.byref(uid)))
+        buf = torch.tensor(list(bytes(uid.internal)), dtype=torch.uint8, device=torch.device("cuda", device))
+        dist.broadcast(buf, src=0)
+        C.memmove(C.byref(uid), bytes(buf.cpu().tolist()), 128)
+        self.comm = C.c_void_p()
+        torch.cuda.set_device(device)
+        self._nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        self._ok(self._nccl.ncclCommInitRank(C.byref(self.comm), world, uid, rank))
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise RuntimeError("NCCL error %d" % rc)
+
+    def allreduce_stats(self, env) -> torch.Tensor:
+        """Sum of ``env``'s statistics vector over all ranks (int64 [32] on the device), via the C ABI."""
+        out = torch.empty(32, dtype=torch.int64, device=env.torch_device)
+        env._check(env._lib.tarok_allreduce_stats(env._h, self.comm, self._C.c_void_p(out.data_ptr()), env._stream()))
+        return out
+
+    def close(self):
+        if self.comm:
+            self._nccl.ncclCommDestroy(self.comm)
+            self.comm = self._C.c_void_p()
+
+
 class ShardedTarok:
     """This rank's shard of a ``total_games`` batch on its own GPU (one process per GPU)."""
 
