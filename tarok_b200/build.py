@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libtarok_b200.so")
 SOURCES = [os.path.join(CSRC, "tarok_abi.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("tarok_kernels.cuh", "tarok_rules.cuh", "philox.cuh")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("tarok_kernels.cuh", "tarok_obs.cuh", "tarok_rules.cuh", "philox.cuh")] + [
     os.path.join(ROOT, "include", "tarok_b200.h")]
 
 NVCC_FLAGS = [
