@@ -45,3 +45,29 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("the oracle", "").replace("oracle's", "") or f == "README.md", \
                     "%s mentions the oracle" % f
+
+
+def test_c_consumer_compiles_against_the_header():
+    """A plain-C program builds against include/tarok_b200.h and links the shared library (no GPU needed to link)."""
+    import subprocess
+    import tempfile
+    import __graft_entry__ as G
+    G.build()
+    exe = os.path.join(tempfile.mkdtemp(), "c_abi_demo")
+    cmd = ["/usr/bin/gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe, "-L" + os.path.join(ROOT, "tarok_b200"),
+           "-ltarok_b200", "-Wl,-rpath," + os.path.join(ROOT, "tarok_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    out = subprocess.run([exe, "200000"], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert 199900 <= int(out.stdout.split()[1]) <= 200000 and "kernel launches: 50" in out.stdout
+    else:       # no GPU here: the program must fail loudly, not fall back
+        assert out.returncode == 1 and "no CUDA device" in out.stderr
+
+
+@pytest.mark.gpu
+def test_c_consumer_runs_on_the_gpu():
+    test_c_consumer_compiles_against_the_header()
