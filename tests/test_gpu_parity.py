@@ -422,3 +422,52 @@ def test_error_paths_are_loud():
         env._check(env._lib.tarok_destroy(env._h))
     del view, m
     env.close()
+
+
+def test_device_randomness_is_uniform():
+    """Chi-square checks of the Philox deal / talon order / random-play draws (the oracle shares the generator, so
+    parity alone would not reveal a biased one)."""
+    import torch
+    n = 1 << 21
+    env = _env(n, seed=123456789)
+    env.deal(0)
+    hands = env.hands[:, :n]
+    talon = env.talon[:n]
+    # 1. every card lands in each hand with probability 12/54 and in the talon with 6/54
+    chi = 0.0
+    for c in range(54):
+        obs = [float(((hands[s] >> c) & 1).sum().item()) for s in range(4)] + [float(((talon >> c) & 1).sum().item())]
+        exp = [n * 12 / 54] * 4 + [n * 6 / 54]
+        chi += sum((o - e) ** 2 / e for o, e in zip(obs, exp))
+    assert chi < 54 * 4 + 6 * (2 * 54 * 4) ** 0.5, chi          # 216 degrees of freedom, ~6 sigma
+    # 2. the talon order is a uniform permutation: rank pattern of the six ids -> 720 classes
+    order = env.talon_order[:n]
+    ids = torch.stack([(order >> (6 * i)) & 63 for i in range(6)], dim=1)
+    ranks = ids.argsort(dim=1).argsort(dim=1)
+    code = (ranks * torch.tensor([7 ** i for i in range(6)], device="cuda")).sum(dim=1)
+    counts = torch.unique(code, return_counts=True)[1].double()
+    assert counts.numel() == 720
+    chi = float(((counts - n / 720) ** 2 / (n / 720)).sum().item())
+    assert chi < 719 + 6 * (2 * 719) ** 0.5, chi
+    # 3. the first card of a Klop deal is uniform over the legal set (12 cards, or 11 when the pagat is held)
+    env.force_contract_synth(0)
+    mask = env.mask[:n].clone()
+    nleg = torch.zeros(n, dtype=torch.int64, device="cuda")
+    for c in range(54):
+        nleg += (mask >> c) & 1
+    env.step_random(1)
+    played = mask & ~env.hands[0, :n]                               # the card that left seat 0's hand
+    below = torch.zeros(n, dtype=torch.int64, device="cuda")        # index of the played card inside the legal set
+    seen = torch.zeros(n, dtype=torch.bool, device="cuda")
+    for c in range(54):
+        is_c = ((played >> c) & 1).bool()
+        seen |= is_c
+        below += (((mask >> c) & 1).bool() & ~seen).long()
+    for k in (11, 12):
+        sel = nleg == k
+        cnt = torch.bincount(below[sel], minlength=k).double()
+        m = float(sel.sum().item())
+        chi = float(((cnt - m / k) ** 2 / (m / k)).sum().item())
+        assert chi < (k - 1) + 6 * (2 * (k - 1)) ** 0.5, (k, chi)
+    del hands, talon, order, mask
+    env.close()
