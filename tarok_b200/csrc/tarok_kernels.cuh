@@ -486,10 +486,9 @@ __device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const 
     const u32 pos = POS >= 0 ? (u32)POS : ((lo >> M_POS) & 3u);
     const u32 mover = ((lo >> M_LEADER) + pos) & 3u;
     u64 hand = hands.get(mover);
-    const u32 contract = lo & 15u;
     const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
     if (RANDOM) {
-        u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));
+        u64 legal = legal_moves(hand, pos != 0, hi & 63u, (lo >> M_KLOPFAM) & 1u);
         u32 n = (u32)__popcll(legal);
         card = nth_set_bit(legal, play_draw<POS>(rnd, e.rng, e.first_gid + g, plays, n));
     }
@@ -508,7 +507,7 @@ __device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const 
         e.tricklog[(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
     }
     if (POS >= 0 && POS < 3) {                                   // same trick goes on: next seat follows the same lead
-        next_mask = legal_moves(hands.get((mover + 1u) & 3u), true, (u32)(meta >> 32) & 63u, klop_rules(contract));
+        next_mask = legal_moves(hands.get((mover + 1u) & 3u), true, (u32)(meta >> 32) & 63u, (lo >> M_KLOPFAM) & 1u);
     } else {
         const u32 nx = mover_of(meta);
         next_mask = mask_for_mover(meta, nx == mover ? hand : hands.get(nx));
@@ -552,8 +551,9 @@ __global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restric
     u32 act = 0;
     if (!RANDOM) act = load_actions(action, g, e.n);
     const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
-    const u32 p0 = ((u32)(m.x >> 32) >> (M_PLAYS - 32)) & 63u, p1 = ((u32)(m.y >> 32) >> (M_PLAYS - 32)) & 63u;
-    const bool in_step = (!a0 || p0 == (u32)hint) && (!a1 || p1 == (u32)hint);
+    // plays sit in the top byte of the high word and the bits above them are clear for every live game
+    const bool in_step = (!a0 || ((u32)(m.x >> 32) >> (M_PLAYS - 32)) == (u32)hint)
+                      && (!a1 || ((u32)(m.y >> 32) >> (M_PLAYS - 32)) == (u32)hint);
     const bool lock = hint >= 0 && __all_sync(0xFFFFFFFFu, in_step);
     if (!a0 && !a1) return;
     const RegHands hx{h0.x, h1.x, h2.x, h3.x}, hy{h0.y, h1.y, h2.y, h3.y};

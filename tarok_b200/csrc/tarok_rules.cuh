@@ -46,9 +46,10 @@ __device__ __forceinline__ u32 talon_k(u32 c) {
 //             13-14 leader (zacne)   15-16 pos = cards in the current trick   17-20 tricks completed
 //             21-22 last trick winner   23 trick-just-completed   24-25 phase (0 dealt 1 await-exchange
 //             2 playing 3 finished)   26 error   27-29 chosen talon group (7 none)
+//             30 Klop-family rules (Klop / Berac / Odprti_berac: pagat restriction), cached from the contract code
 //  high word: 32-55 trick cards, 6 bits each, play order   56-61 plays made (0..48)   62 scored/pad
 constexpr int M_CONTRACT = 0, M_DECL = 4, M_KING = 6, M_TEAM = 9, M_LEADER = 13, M_POS = 15,
-              M_TRICKS = 17, M_WINNER = 21, M_TRICKDONE = 23, M_PHASE = 24, M_ERR = 26, M_GROUP = 27,
+              M_TRICKS = 17, M_WINNER = 21, M_TRICKDONE = 23, M_PHASE = 24, M_ERR = 26, M_GROUP = 27, M_KLOPFAM = 30,
               M_TRICK = 32, M_PLAYS = 56, M_SCORED = 62;
 enum : u32 { PH_DEALT = 0, PH_EXCHANGE = 1, PH_PLAY = 2, PH_DONE = 3 };
 
@@ -238,6 +239,7 @@ __device__ __forceinline__ u64 begin_contract(u64 meta, u32 contract, u32 declar
     meta = mset(meta, M_TEAM, 4, team);
     meta = mset(meta, M_LEADER, 2, leader);
     meta = mset(meta, M_PHASE, 2, bad ? (u32)PH_DONE : phase);
+    meta = mset(meta, M_KLOPFAM, 1, (!bad && klop_rules(contract)) ? 1u : 0u);
     if (bad) meta |= 1ull << M_ERR;
     return meta;
 }
@@ -278,9 +280,9 @@ __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talo
     u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 contract = lo & 15u;
     const u32 pos = POS >= 0 ? (u32)POS : ((lo >> M_POS) & 3u);
-    const u64 bit = card < 54 ? (1ull << card) : 0ull;
+    const u64 bit = (!CHECK || card < 54) ? (1ull << (card & 63u)) : 0ull;   // in-kernel picks are in range by construction
     if (CHECK) {
-        u64 legal = legal_moves(hand, pos != 0, hi & 63u, klop_rules(contract));
+        u64 legal = legal_moves(hand, pos != 0, hi & 63u, (lo >> M_KLOPFAM) & 1u);
         if (!(legal & bit)) {                             // 'Karte ne mores igarti' (Navadna_igra.py:125-126)
             lo |= (1u << M_ERR) | (PH_DONE << M_PHASE);
             return ((u64)hi << 32) | lo;
@@ -329,7 +331,7 @@ __device__ __forceinline__ u64 trick_bits(u32 entry, u32 k, bool is_klop, u64 ta
 __device__ __forceinline__ u64 mask_for_mover(u64 meta, u64 hand) {
     if (mget(meta, M_PHASE, 2) != PH_PLAY) return 0ull;
     u32 pos = mget(meta, M_POS, 2);
-    return legal_moves(hand, pos != 0, mget(meta, M_TRICK, 6), klop_rules(mget(meta, M_CONTRACT, 4)));
+    return legal_moves(hand, pos != 0, mget(meta, M_TRICK, 6), ((u32)meta >> M_KLOPFAM) & 1u);
 }
 __device__ __forceinline__ u32 mover_of(u64 meta) { const u32 lo = (u32)meta; return ((lo >> M_LEADER) + (lo >> M_POS)) & 3u; }
 

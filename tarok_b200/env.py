@@ -35,7 +35,7 @@ S_SEAT, S_PLAYER, S_CONTRACT, S_FINISHED, S_STEPS, S_ERRORS, S_ERR_EVENTS = 0, 4
 
 # meta word layout (tarok_b200/csrc/tarok_rules.cuh)
 M_CONTRACT, M_DECL, M_KING, M_TEAM, M_LEADER, M_POS, M_TRICKS, M_WINNER, M_TRICKDONE = 0, 4, 6, 9, 13, 15, 17, 21, 23
-M_PHASE, M_ERR, M_GROUP, M_TRICK, M_PLAYS = 24, 26, 27, 32, 56
+M_PHASE, M_ERR, M_GROUP, M_KLOPFAM, M_TRICK, M_PLAYS = 24, 26, 27, 30, 32, 56
 PH_DEALT, PH_EXCHANGE, PH_PLAY, PH_DONE = 0, 1, 2, 3
 
 _DLTENSOR = b"dltensor"
