@@ -200,7 +200,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from tarok_b200.env import TarokEnv, MODE_AUCTION_UNIFORM, S_STEPS, S_FINISHED, S_ERRORS
+    from tarok_b200.env import TarokEnv, pack_records, MODE_AUCTION_UNIFORM, S_STEPS, S_FINISHED, S_ERRORS
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -310,9 +310,13 @@ def run_ours(args, rank, world, local_rank):
     k_h = torch.from_numpy(rng.integers(0, 4, n, dtype=np.uint8)).pin_memory()
     sc_h = torch.empty((n, 4), dtype=torch.int16).pin_memory()
     st_h = torch.zeros(32, dtype=torch.int64).pin_memory()
-    def e2e_run(fused):
+    rec_h, _ = pack_records(perm_h, c_h, d_h, k_h)           # the same deals + contracts as 24-byte records (pinned)
+    def e2e_run(fused, records=False):
         def once(i):
-            env.rollout_host(perm_h, c_h, d_h, k_h, sc_h, st_h, first_game_id=i * total + rank * n, fused=fused)
+            if records:
+                env.rollout_records(rec_h, sc_h, st_h, first_game_id=i * total + rank * n)
+            else:
+                env.rollout_host(perm_h, c_h, d_h, k_h, sc_h, st_h, first_game_id=i * total + rank * n, fused=fused)
             torch.cuda.current_stream().synchronize()                     # the host reads the result
             return int(st_h[S_STEPS])
         for i in range(args.warmup):
@@ -334,6 +338,7 @@ def run_ours(args, rank, world, local_rank):
 
     e2e_value, e2e_ms = e2e_run(True)          # fused kernel behind an 8-chunk upload/compute/download pipeline
     e2e_sw_value, e2e_sw_ms = e2e_run(False)   # stepwise kernels, serial upload -> 52 launches -> download
+    e2e_rec_value, e2e_rec_ms = e2e_run(True, records=True)   # same pipeline, 24-byte deal records instead of 57-byte rows
 
     # ---- HBM-bound regime: the same step kernel on a state 8x larger than L2 (informational)
     big = None
@@ -381,7 +386,10 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": world * (n * 8 + 256), "ms_per_step": e2e_ms,
                     "api": "tarok_rollout_host (TarokEnv.rollout_host): pinned host deals+contracts in, scores+stats out; fused "
                            "kernel behind an 8-chunk upload/compute/download pipeline",
-                    "stepwise_kernels": {"value": e2e_sw_value, "ms_per_step": e2e_sw_ms}},
+                    "stepwise_kernels": {"value": e2e_sw_value, "ms_per_step": e2e_sw_ms},
+                    "deal_records": {"value": e2e_rec_value, "ms_per_step": e2e_rec_ms, "h2d_bytes_per_step": world * n * 24,
+                                     "api": "tarok_rollout_records: the same deals and contracts serialised as 24-byte records "
+                                            "(packed on the host before the timed region, like the rows are dealt before it)"}},
             "gpu_launches": launches * world,
             "roofline": roofline, "roofline_large": big,
             "fused_rollout": {"ms_per_rollout": fused_ms, "env_steps_per_sec_per_gpu": env_steps / args.steps / world / (fused_ms * 1e-3),

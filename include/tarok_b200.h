@@ -160,6 +160,22 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
                        uint64_t first_global_game_id, int fused,
                        int16_t* scores_host, int64_t* stats_host, void* stream);
 
+/* Deal records: the same inputs as tarok_rollout_host in 24 instead of 57 bytes per deal (the host-buffer path is
+   PCIe-bound, so the bytes are the cost).  One record = three little-endian uint64 words w0,w1,w2:
+     bits 0..53 of w0/w1/w2 = bit planes 0/1/2 of each card's owner code (bit i = card id i; code 0-3 = seat whose
+                              twelve cards of Igra.razdeli (Igra.py:65-73) hold the card, 4 = talon, 5-7 invalid);
+     w0 bits 54..62, w1 bits 54..62 = positions 0..5 within the ordered talon (karte[48:54]) of its six cards taken in
+                              ascending card id, 3 bits each (cards 0-2 in w0, 3-5 in w1);
+     w2 bits 54..57 contract code, 58..59 declarer seat, 60..62 king suit (7 = none): the arguments of tarok_force_contract.
+   tarok_pack_records is the host-side serialiser (plain CPU code; returns the number of rows that are not permutations
+   or carry an out-of-range contract/declarer -- those become records that decode to error games -- or -1 on NULL). */
+#define TAROK_RECORD_BYTES 24
+int64_t tarok_pack_records(const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
+                           const uint8_t* king_host /* or NULL */, uint64_t n, uint64_t* records_host /* [n,3] */);
+/* tarok_rollout_host(fused = 1) fed with deal records; same outputs, bit-identical scores. */
+int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t first_global_game_id,
+                          int16_t* scores_host, int64_t* stats_host, void* stream);
+
 /* ---- observations: Nevronski_igralec.stanje_v_vektor_rek_navadna (Igralec.py:453-533) --------- */
 /* Needs TAROK_FLAG_HISTORY.  net_type follows Nevronski_igralec.Tipi_NN: 0 Klop, 1 Navadna_igra (Tri/Dve/Ena),
    2 Solo (Solo_*), 3 Berac.  tarok_obs_shape gives, per game, the net type of its contract (255 = not waiting

@@ -42,6 +42,8 @@ SIGNATURES = {
     "tarok_rollout_stepwise": (_I, [_VP, _U32, _U64, _VP]),
     "tarok_rollout_fused": (_I, [_VP, _U32, _U64, _VP]),
     "tarok_rollout_host": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _I, _VP, _VP, _VP]),
+    "tarok_pack_records": (C.c_int64, [_VP, _VP, _VP, _VP, _U64, _VP]),
+    "tarok_rollout_records": (_I, [_VP, _VP, _U64, _VP, _VP, _VP]),
     "tarok_obs_shape": (_I, [_VP, _VP, _VP, _VP]),
     "tarok_obs_expand": (_I, [_VP, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tarok_obs_expand_at": (_I, [_VP, _I, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -443,9 +443,71 @@ int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id
     h->lock_plays = 0;
     h->e.first_gid = first_global_game_id;
     clear_hist(h, stream);
-    tk::k_rollout_fused<false><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr, nullptr,
+    tk::k_rollout_fused<tk::DEALS_PHILOX><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr, nullptr,
                                                                            h->e.scores, 1, 0ull);
     TK_LAUNCH_OK(h);
+    return 0;
+}
+
+// Lazily created: the copy streams, events and device staging buffers of the host-buffer entries.
+static int ensure_staging(tarok_t* h) {
+    if (h->st_perm) return 0;
+    TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+    TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    for (int c = 0; c < TK_MAX_CHUNKS; c++) {
+        TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[c], cudaEventDisableTiming));
+        TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[c], cudaEventDisableTiming));
+    }
+    TK_CUDA(h, cudaMalloc((void**)&h->st_perm, h->e.n_alloc * 54));
+    TK_CUDA(h, cudaMalloc((void**)&h->st_contract, h->e.n_alloc));
+    TK_CUDA(h, cudaMalloc((void**)&h->st_declarer, h->e.n_alloc));
+    TK_CUDA(h, cudaMalloc((void**)&h->st_king, h->e.n_alloc));
+    return 0;
+}
+
+// Chunked pipeline shared by the two host-buffer entries: upload chunk c+1 (copy stream) while chunk c plays (caller's
+// stream) and chunk c-1's scores go back (download stream).  `row` = bytes per deal of the input format (54: permutation
+// rows + three 1-byte arrays; 24: deal records, which carry the contract themselves).
+static int rollout_host_fused(tarok_t* h, const uint8_t* deals_host, size_t row, const uint8_t* contract_host,
+                              const uint8_t* declarer_host, const uint8_t* king_host, int16_t* scores_host,
+                              int64_t* stats_host, cudaStream_t s) {
+    const u64 n = h->e.n;
+    const u64 chunk = (n >= (1ull << 18)) ? (((n + 7) / 8 + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
+    TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));
+    TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_fork, 0));
+    for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
+        const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
+        TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * row, deals_host + b * row, len * row, cudaMemcpyHostToDevice, h->s_up));
+        if (c == 0 && contract_host) {   // the three 1-byte-per-game inputs go up whole, right behind the first chunk of deals
+            TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, h->s_up));
+            TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, h->s_up));
+            if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, h->s_up));
+        }
+        TK_CUDA(h, cudaEventRecord(h->ev_up[c], h->s_up));
+        TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_up[c], 0));
+        tk::Env ev = h->e;
+        ev.n = e_;
+        const unsigned grid = (unsigned)((len + tk::CTA - 1) / tk::CTA);
+        if (row == 54)
+            tk::k_rollout_fused<tk::DEALS_PERM><<<grid, tk::CTA, tk::CTA * 54, s>>>(
+                ev, 0u, h->st_perm, h->st_contract, h->st_declarer, king_host ? h->st_king : nullptr, h->e.scores, 0, b);
+        else
+            tk::k_rollout_fused<tk::DEALS_RECORD><<<grid, tk::CTA, 0, s>>>(ev, 0u, h->st_perm, nullptr, nullptr, nullptr,
+                                                                          h->e.scores, 0, b);
+        TK_LAUNCH_OK(h);
+        if (scores_host) {
+            TK_CUDA(h, cudaEventRecord(h->ev_done[c], s));
+            TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_done[c], 0));
+            TK_CUDA(h, cudaMemcpyAsync((uint64_t*)scores_host + b, h->e.scores + b, len * 8, cudaMemcpyDeviceToHost, h->s_down));
+        }
+    }
+    TK_CUDA(h, cudaEventRecord(h->ev_join, h->s_down));
+    TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
     return 0;
 }
 
@@ -456,77 +518,76 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
     if (!perm_host || !contract_host || !declarer_host) return fail(h, -1, "perm/contract/declarer host pointers are required");
     DeviceGuard dg(h->device);
     const u64 n = h->e.n;
-    if (!h->st_perm) {
-        TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
-        TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
-        TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        for (int c = 0; c < TK_MAX_CHUNKS; c++) {
-            TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_up[c], cudaEventDisableTiming));
-            TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[c], cudaEventDisableTiming));
-        }
-        TK_CUDA(h, cudaMalloc((void**)&h->st_perm, h->e.n_alloc * 54));
-        TK_CUDA(h, cudaMalloc((void**)&h->st_contract, h->e.n_alloc));
-        TK_CUDA(h, cudaMalloc((void**)&h->st_declarer, h->e.n_alloc));
-        TK_CUDA(h, cudaMalloc((void**)&h->st_king, h->e.n_alloc));
-    }
+    if (int rc = ensure_staging(h)) return rc;
     cudaStream_t s = S(stream);
     TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
     h->lock_plays = 0;
     h->e.first_gid = first_global_game_id;
-    if (!fused) {
-        TK_CUDA(h, cudaMemcpyAsync(h->st_perm, perm_host, n * 54, cudaMemcpyHostToDevice, s));
-        TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, s));
-        TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, s));
-        if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, s));
-    }
-    if (fused) {
-        // chunked pipeline: upload chunk c+1 (copy stream) while chunk c plays (caller's stream) and chunk c-1's
-        // scores go back (download stream).  The four per-game inputs are uploaded per chunk.
-        const u64 chunk = (n >= (1ull << 18)) ? (((n + 7) / 8 + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
-        const int nchunks = (int)((n + chunk - 1) / chunk);
-        TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
-        TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));
-        TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_fork, 0));
-        for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
-            const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
-            TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * 54, perm_host + b * 54, len * 54, cudaMemcpyHostToDevice, h->s_up));
-            if (c == 0) {   // the three 1-byte-per-game inputs go up whole, right behind the first chunk of deals
-                TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, h->s_up));
-                TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, h->s_up));
-                if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, h->s_up));
-            }
-            TK_CUDA(h, cudaEventRecord(h->ev_up[c], h->s_up));
-            TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_up[c], 0));
-            tk::Env ev = h->e;
-            ev.n = e_;
-            const unsigned grid = (unsigned)((len + tk::CTA - 1) / tk::CTA);
-            tk::k_rollout_fused<true><<<grid, tk::CTA, tk::CTA * 54, s>>>(
-                ev, 0u, h->st_perm, h->st_contract, h->st_declarer, king_host ? h->st_king : nullptr, h->e.scores, 0, b);
-            TK_LAUNCH_OK(h);
-            if (scores_host) {
-                TK_CUDA(h, cudaEventRecord(h->ev_done[c], s));
-                TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_done[c], 0));
-                TK_CUDA(h, cudaMemcpyAsync((uint64_t*)scores_host + b, h->e.scores + b, len * 8, cudaMemcpyDeviceToHost, h->s_down));
-            }
-        }
-        TK_CUDA(h, cudaEventRecord(h->ev_join, h->s_down));
-        TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
-        if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
-        return 0;
-    } else {
-        clear_hist(h, stream);
-        tk::k_set_deals<<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, h->st_perm);
-        TK_LAUNCH_OK(h);
-        tk::k_begin<tk::SRC_FORCED><<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, 0u, h->st_contract, h->st_declarer,
-                                                                             king_host ? h->st_king : nullptr);
-        TK_LAUNCH_OK(h);
-        int rc = play_out_stepwise(h, 0u, stream);
-        if (rc) return rc;
-    }
+    if (fused) return rollout_host_fused(h, perm_host, 54, contract_host, declarer_host, king_host, scores_host, stats_host, s);
+    TK_CUDA(h, cudaMemcpyAsync(h->st_perm, perm_host, n * 54, cudaMemcpyHostToDevice, s));
+    TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, s));
+    TK_CUDA(h, cudaMemcpyAsync(h->st_declarer, declarer_host, n, cudaMemcpyHostToDevice, s));
+    if (king_host) TK_CUDA(h, cudaMemcpyAsync(h->st_king, king_host, n, cudaMemcpyHostToDevice, s));
+    clear_hist(h, stream);
+    tk::k_set_deals<<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, h->st_perm);
+    TK_LAUNCH_OK(h);
+    tk::k_begin<tk::SRC_FORCED><<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, 0u, h->st_contract, h->st_declarer,
+                                                                         king_host ? h->st_king : nullptr);
+    TK_LAUNCH_OK(h);
+    if (int rc = play_out_stepwise(h, 0u, stream)) return rc;
     if (scores_host) TK_CUDA(h, cudaMemcpyAsync(scores_host, h->e.scores, n * 8, cudaMemcpyDeviceToHost, s));
     if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
     return 0;
+}
+
+int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t first_global_game_id, int16_t* scores_host,
+                          int64_t* stats_host, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!records_host) return fail(h, -1, "records_host is null");
+    DeviceGuard dg(h->device);
+    if (int rc = ensure_staging(h)) return rc;
+    cudaStream_t s = S(stream);
+    TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
+    h->lock_plays = 0;
+    h->e.first_gid = first_global_game_id;
+    return rollout_host_fused(h, (const uint8_t*)records_host, TAROK_RECORD_BYTES, nullptr, nullptr, nullptr, scores_host,
+                              stats_host, s);
+}
+
+// Host-side serialiser (plain CPU code, no device work): permutation rows + forced contracts -> deal records.
+int64_t tarok_pack_records(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king,
+                           uint64_t n, uint64_t* records) {
+    if (!perm || !contract || !declarer || !records) return -1;
+    int64_t bad = 0;
+    for (uint64_t g = 0; g < n; g++) {
+        const uint8_t* row = perm + g * 54;
+        uint64_t w[3] = {0, 0, 0}, seen = 0, talon = 0;
+        for (int i = 0; i < 54; i++) {
+            const unsigned c = row[i], code = i < 48 ? (unsigned)i / 12u : 4u;
+            if (c >= 54) continue;
+            seen |= 1ull << c;
+            if (i >= 48) talon |= 1ull << c;
+            for (int p = 0; p < 3; p++) w[p] |= (uint64_t)((code >> p) & 1u) << c;
+        }
+        uint64_t ranks = 0;                                // position in the talon of its cards taken in ascending id
+        for (int i = 48; i < 54; i++) {
+            const unsigned c = row[i];
+            if (c >= 54) continue;
+            const int below = __builtin_popcountll(talon & ((1ull << c) - 1));
+            ranks |= (uint64_t)(i - 48) << (3 * below);
+        }
+        const unsigned k = (king && king[g] < 7u) ? king[g] : 7u;
+        if (seen != ((1ull << 54) - 1) || contract[g] > 15u || declarer[g] > 3u) {
+            // not a permutation / out-of-range contract: emit a record that decodes to an error game, like the row would
+            bad++;
+            w[0] = w[1] = w[2] = (1ull << 54) - 1;
+        }
+        w[0] |= (ranks & 0x1FF) << 54;
+        w[1] |= ((ranks >> 9) & 0x1FF) << 54;
+        w[2] |= (uint64_t)(contract[g] & 15u) << 54 | (uint64_t)(declarer[g] & 3u) << 58 | (uint64_t)(k & 7u) << 60;
+        records[g * 3] = w[0]; records[g * 3 + 1] = w[1]; records[g * 3 + 2] = w[2];
+    }
+    return bad;
 }
 
 // ---- observations ------------------------------------------------------------------------

@@ -237,6 +237,32 @@ __global__ void __launch_bounds__(CTA) k_set_deals(Env e, const uint8_t* __restr
     if (e.discard) e.discard[g] = 0;
 }
 
+// Compact deal record (24 B = three u64 words; include/tarok_b200.h "deal records"): three bit planes over the 54 card
+// ids give each card's owner code (0-3 seat, 4 talon), the ten spare bits of each word carry the talon order and the
+// forced contract.  Decoding is a handful of bitwise ops, no per-card loop except the six talon cards.
+struct DealRecord { u32 contract, declarer, king; };
+__device__ __forceinline__ Dealt deal_from_record(u64 w0, u64 w1, u64 w2, DealRecord& r, bool& ok) {
+    const u64 p0 = w0 & ALL54, p1 = w1 & ALL54, p2 = w2 & ALL54;
+    Dealt d;
+    d.h0 = ALL54 & ~(p0 | p1 | p2); d.h1 = p0 & ~p1 & ~p2; d.h2 = p1 & ~p0 & ~p2; d.h3 = p0 & p1 & ~p2;
+    d.talon = p2; d.order = 0;
+    ok = !(p2 & (p0 | p1)) && __popcll(d.h0) == 12 && __popcll(d.h1) == 12 && __popcll(d.h2) == 12 && __popcll(d.h3) == 12;
+    const u32 ranks = ((u32)(w0 >> 54) & 0x1FFu) | (((u32)(w1 >> 54) & 0x1FFu) << 9);
+    u64 t = p2;
+    u32 seen = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {                         // talon cards in ascending id, each with its position 0..5
+        const u32 c = t ? (u32)__ffsll((long long)t) - 1u : 0u;
+        t &= t - 1;
+        const u32 pos = (ranks >> (3 * i)) & 7u;
+        seen |= 1u << pos;
+        d.order |= (u64)c << (6u * (pos < 6u ? pos : 0u));
+    }
+    ok = ok && seen == 0x3Fu;                              // (12,12,12,12) + six distinct positions => exactly six talon cards
+    r.contract = (u32)(w2 >> 54) & 15u; r.declarer = (u32)(w2 >> 58) & 3u; r.king = (u32)(w2 >> 60) & 7u;
+    return d;
+}
+
 // Current deal -> the permutation Igra.razdeli would have consumed (hands ascending, ordered talon).
 __global__ void __launch_bounds__(CTA) k_export_perm(Env e, uint8_t* __restrict__ out) {
     __shared__ uint8_t sh[CTA * 54];
@@ -785,7 +811,9 @@ __device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, cons
     }
 }
 
-template <bool FROM_PERM>
+enum : int { DEALS_PHILOX = 0, DEALS_PERM = 1, DEALS_RECORD = 2 };
+
+template <int DEALS>
 __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const uint8_t* __restrict__ perm,
                                                        const uint8_t* __restrict__ fc, const uint8_t* __restrict__ fd,
                                                        const uint8_t* __restrict__ fk, u64* __restrict__ out, int write_state,
@@ -795,7 +823,7 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
     u64 g = base + threadIdx.x;
     const u64 na = e.n_alloc;
     const u64 gid = e.first_gid + g;
-    if (FROM_PERM) {
+    if (DEALS == DEALS_PERM) {
         const u64 total = e.n * 54ull, off = base * 54ull;
         const bool vec_ok = (((uintptr_t)perm) & 15u) == 0;
         for (u32 v = threadIdx.x; v < CTA * 54 / 16; v += CTA) {
@@ -811,14 +839,19 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
     if (live) {
         Dealt d;
         bool ok = true;
-        if (FROM_PERM) d = deal_from_perm(shp + threadIdx.x * 54, ok);
-        else d = deal_philox(e.rng, gid);
+        DealRecord rec = {0u, 0u, NO_KING};
+        if (DEALS == DEALS_PERM) d = deal_from_perm(shp + threadIdx.x * 54, ok);
+        else if (DEALS == DEALS_RECORD) {
+            const u64* w = reinterpret_cast<const u64*>(perm) + g * 3;
+            d = deal_from_record(w[0], w[1], w[2], rec, ok);
+        } else d = deal_philox(e.rng, gid);
         h0 = d.h0; h1 = d.h1; h2 = d.h2; h3 = d.h3; talon = d.talon; order = d.order;
         meta = meta_fresh();
         if (!ok) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
         else {
             u32 contract, declarer, king;
-            if (fc) resolve_contract<SRC_FORCED>(e.rng, gid, mode, fc, fd, fk, g, contract, declarer, king);
+            if (DEALS == DEALS_RECORD) { contract = rec.contract; declarer = rec.declarer; king = rec.king; }
+            else if (fc) resolve_contract<SRC_FORCED>(e.rng, gid, mode, fc, fd, fk, g, contract, declarer, king);
             else resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, contract, declarer, king);
             meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
         }

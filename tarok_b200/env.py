@@ -48,6 +48,30 @@ def meta_field(meta, shift, bits):
     return (meta >> shift) & ((1 << bits) - 1)
 
 
+def _host_ptr(a):
+    """Address of a contiguous HOST buffer (numpy array or CPU torch tensor), or None."""
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        assert a.device.type == "cpu" and a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pack_records(perm, contract, declarer, king=None, out=None):
+    """Serialises permutation rows (uint8 [n,54], ``Igra.razdeli`` order) + forced contracts (uint8 [n] each) into
+    24-byte deal records (uint64 [n,3]) on the host.  Returns (records, number of invalid rows)."""
+    n = int(perm.shape[0])
+    if out is None:
+        out = torch.empty((n, 3), dtype=torch.int64).pin_memory() if torch.cuda.is_available() else torch.empty((n, 3), dtype=torch.int64)
+    bad = _lib.load().tarok_pack_records(_host_ptr(perm), _host_ptr(contract), _host_ptr(declarer), _host_ptr(king), n,
+                                         _host_ptr(out))
+    if bad < 0:
+        raise ValueError("pack_records: perm, contract and declarer are required")
+    return out, int(bad)
+
+
 class TarokEnv:
     def __init__(self, n_games: int, seed: int = DEFAULT_SEED, device: int = 0, history: bool = False):
         self._lib = _lib.load()
@@ -244,17 +268,17 @@ class TarokEnv:
         Uploads the injected deals + forced contracts, plays them with uniform-random players and
         downloads ``scores_out`` (int16 [n,4]) and ``stats_out`` (int64 [32]).  Asynchronous on the
         current stream when the buffers are pinned; the caller synchronises."""
-        def hp(a):
-            if a is None:
-                return None
-            if isinstance(a, torch.Tensor):
-                assert a.device.type == "cpu" and a.is_contiguous()
-                return C.c_void_p(a.data_ptr())
-            assert a.flags["C_CONTIGUOUS"]
-            return a.ctypes.data_as(C.c_void_p)
+        hp = _host_ptr
         self._check(self._lib.tarok_rollout_host(
             self._h, hp(perm), hp(contract), hp(declarer), hp(king), int(first_game_id), 1 if fused else 0,
             hp(scores_out), hp(stats_out), self._stream()))
+
+    def rollout_records(self, records, scores_out, stats_out, first_game_id: int = 0):
+        """``rollout_host(fused=True)`` fed with 24-byte deal records (``pack_records``; layout in include/tarok_b200.h):
+        the same deals, contracts and scores for 2.4x fewer bytes over PCIe."""
+        hp = _host_ptr
+        self._check(self._lib.tarok_rollout_records(self._h, hp(records), int(first_game_id), hp(scores_out),
+                                                    hp(stats_out), self._stream()))
 
     # ------------------------------------------------------------------ observations (Igralec.py:453-533)
     def obs_shape(self):

@@ -71,3 +71,34 @@ def test_c_consumer_compiles_against_the_header():
 @pytest.mark.gpu
 def test_c_consumer_runs_on_the_gpu():
     test_c_consumer_compiles_against_the_header()
+
+
+def test_pack_records_is_the_documented_layout():
+    """Host-side serialiser (CPU code in the library): decode the bit planes in numpy and compare with the rows."""
+    import numpy as np
+    from tarok_b200.env import pack_records
+    rng = np.random.default_rng(3)
+    n = 2000
+    perm = np.stack([rng.permutation(54) for _ in range(n)]).astype(np.uint8)
+    contract = rng.integers(0, 10, n).astype(np.uint8)
+    declarer = rng.integers(0, 4, n).astype(np.uint8)
+    king = rng.integers(0, 4, n).astype(np.uint8)
+    rec, bad = pack_records(perm, contract, declarer, king)
+    assert bad == 0
+    w = rec.numpy().view(np.uint64)
+    for g in range(n):
+        code = [int((w[g, 0] >> np.uint64(c)) & np.uint64(1)) | int((w[g, 1] >> np.uint64(c)) & np.uint64(1)) << 1
+                | int((w[g, 2] >> np.uint64(c)) & np.uint64(1)) << 2 for c in range(54)]
+        for s in range(4):
+            assert sorted(c for c in range(54) if code[c] == s) == sorted(perm[g, 12 * s:12 * s + 12].tolist())
+        talon = [c for c in range(54) if code[c] == 4]
+        ranks = (int(w[g, 0] >> np.uint64(54)) & 0x1FF) | (int(w[g, 1] >> np.uint64(54)) & 0x1FF) << 9
+        order = [None] * 6
+        for i, c in enumerate(talon):
+            order[(ranks >> (3 * i)) & 7] = c
+        assert order == perm[g, 48:].tolist()
+        assert int(w[g, 2] >> np.uint64(54)) & 15 == contract[g]
+        assert int(w[g, 2] >> np.uint64(58)) & 3 == declarer[g]
+        assert int(w[g, 2] >> np.uint64(60)) & 7 == king[g]
+    perm[0, 0] = perm[0, 1]
+    assert pack_records(perm, contract, declarer, None)[1] == 1

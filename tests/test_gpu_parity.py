@@ -294,6 +294,69 @@ def test_host_buffer_entry_matches_device_path(oracle):
         env.close()
 
 
+@pytest.mark.parametrize("mode", [0, 16, 17])
+def test_deal_records_match_permutation_rows(oracle, mode):
+    """24-byte deal records carry the same deal (incl. the ORDER of the talon, which Klop consumes card by card) and the same
+    forced contract as the 57-byte row format: identical scores, and both agree with the oracle."""
+    import torch
+    from tarok_b200.env import pack_records
+    n = 300001                                                       # ragged: not a multiple of the chunk or the CTA
+    ref = oracle.rollout(77, 0, n, mode)
+    rec, bad = pack_records(ref["perm"], ref["contract"], ref["declarer"], ref["king"])
+    assert bad == 0 and rec.shape == (n, 3)
+    out = []
+    for records in (False, True):
+        env = _env(n, seed=77)
+        scores = torch.empty((n, 4), dtype=torch.int16).pin_memory()
+        stats = torch.zeros(32, dtype=torch.int64).pin_memory()
+        if records:
+            env.rollout_records(rec, scores, stats)
+        else:
+            env.rollout_host(ref["perm"], ref["contract"], ref["declarer"], ref["king"], scores, stats, fused=True)
+        torch.cuda.synchronize()
+        out.append((scores.numpy().copy(), stats.numpy().copy()))
+        env.close()
+    assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
+    if mode != 17:        # the host entries always take talon group 0 (Bot_igralec, Igralec.py:162); mode 17 of the oracle draws it
+        assert (out[1][0] == ref["scores"]).all()
+        assert out[1][1][19] == ref["stats"][8] and (out[1][1][0:8] == ref["stats"][0:8]).all()
+    else:
+        assert len(set(ref["contract"].tolist())) >= 9          # every contract family went through both formats
+
+
+def test_deal_records_reject_what_the_rows_reject():
+    """Rows that are not permutations / out-of-range contracts become error games in both formats."""
+    import torch
+    from tarok_b200.env import pack_records
+    n = 4096
+    rng = np.random.default_rng(5)
+    perm = np.stack([rng.permutation(54) for _ in range(n)]).astype(np.uint8)
+    contract = np.full(n, 3, np.uint8); declarer = (np.arange(n) % 4).astype(np.uint8); king = (np.arange(n) % 4).astype(np.uint8)
+    perm[10, 5] = perm[10, 6]                    # duplicate card in seat 0 (the missing card would default to seat 0)
+    perm[11, 50] = 54                            # out-of-range id in the talon
+    contract[12] = 11                            # no such contract
+    declarer[13] = 4
+    king[14] = 5                                 # king game with no valid suit
+    rec, bad = pack_records(perm, contract, declarer, king)
+    assert bad == 3                              # rows 10, 11, 13; rows 12 and 14 are well-formed records of an invalid call
+    out = {}
+    for name in ("rows", "records"):
+        env = _env(n, seed=1)
+        scores = torch.empty((n, 4), dtype=torch.int16).pin_memory()
+        stats = torch.zeros(32, dtype=torch.int64).pin_memory()
+        if name == "rows":
+            env.rollout_host(perm, contract, declarer, king, scores, stats, fused=True)
+        else:
+            env.rollout_records(rec, scores, stats)
+        torch.cuda.synchronize()
+        out[name] = (scores.numpy().copy(), stats.numpy().copy())
+        env.close()
+    assert (out["rows"][0] == out["records"][0]).all()
+    assert (out["rows"][1] == out["records"][1]).all()
+    assert out["rows"][1][20] == 5 and out["rows"][1][18] == n - 5          # error games / finished games
+    assert (out["rows"][0][10:15] == 0).all()
+
+
 def test_no_cpu_fallback_symbols_loaded():
     """The product path is the CUDA library: it must be loaded in-process and have launched kernels."""
     env = _env(1000)
