@@ -58,7 +58,10 @@ enum { TAROK_KLOP = 0, TAROK_TRI = 1, TAROK_DVE = 2, TAROK_ENA = 3, TAROK_SOLO_T
 /* flags for tarok_create */
 #define TAROK_FLAG_HISTORY 1u          /* keep the play history (seat<<6|card per play) for observations */
 /* exportable fields */
-enum { TAROK_F_HANDS = 0,   /* uint64 [4, n_alloc]  hand bitboard of seat s        (Roka, Roka.py:4-13)      */
+enum { TAROK_F_HANDS = 0,   /* uint64 [4, n_alloc]  hand bitboards (Roka, Roka.py:4-13) in LEADER-RELATIVE slots: row j is
+                               the hand of seat (leader + j) & 3, leader = bits 13-14 of the game's meta word (0 from
+                               the deal until a contract or a trick moves it), so the seat to move is always row `pos`;
+                               tarok_hands_by_seat copies them out indexed by seat */
        TAROK_F_PILES = 1,   /* uint64 [4, n_alloc]  won-cards pile of seat s (Igralec.kupcek): discards at once, won tricks
                                (and the Klop talon in TAROK_F_TALON) are materialised from the trick log by tarok_score */
        TAROK_F_TALON = 2,   /* uint64 [n_alloc]     cards still in the talon                                 */
@@ -126,6 +129,8 @@ int tarok_exchange_synth(tarok_t* h, uint32_t random_group, void* stream);
         Klop.py:47-79), pobere_stih/primerjaj_karti (Navadna_igra.py:143-156), Berac.start
         (Berac.py:13-44) --------------------------------------------------------------------------- */
 int tarok_legal_mask(tarok_t* h, uint64_t* out_dev, void* stream);   /* recomputed from the state */
+/* The four hands of every game indexed by SEAT (uint64 [4, n_alloc] on the device): TAROK_F_HANDS un-rotated. */
+int tarok_hands_by_seat(tarok_t* h, uint64_t* out_dev, void* stream);
 int tarok_step(tarok_t* h, const uint8_t* card_dev, void* stream);   /* one card per live game */
 int tarok_step_random(tarok_t* h, void* stream);                     /* uniform-random legal card */
 int tarok_steps_random(tarok_t* h, uint32_t count, void* stream);    /* `count` back-to-back random steps */

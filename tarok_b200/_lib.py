@@ -31,6 +31,7 @@ SIGNATURES = {
     "tarok_exchange": (_I, [_VP, _VP, _VP, _VP]),
     "tarok_exchange_synth": (_I, [_VP, _U32, _VP]),
     "tarok_legal_mask": (_I, [_VP, _VP, _VP]),
+    "tarok_hands_by_seat": (_I, [_VP, _VP, _VP]),
     "tarok_step": (_I, [_VP, _VP, _VP]),
     "tarok_step_random": (_I, [_VP, _VP]),
     "tarok_steps_random": (_I, [_VP, _U32, _VP]),

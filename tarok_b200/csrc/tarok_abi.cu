@@ -95,7 +95,16 @@ static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (tma) cudaLaunchKernelEx(&cfg, tk::k_step_tma<RANDOM>, h->e, action);
-    else cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM>, h->e, action, h->lockstep ? h->lock_plays : -1);
+    else {
+        const int hint = h->lockstep ? h->lock_plays : -1;
+        switch (hint >= 0 ? (hint & 3) : 4) {
+            case 0: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 0>, h->e, action, hint); break;
+            case 1: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 1>, h->e, action, hint); break;
+            case 2: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 2>, h->e, action, hint); break;
+            case 3: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 3>, h->e, action, hint); break;
+            default: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, -1>, h->e, action, hint); break;
+        }
+    }
     // lock-step bookkeeping (only a hint to the kernel, which verifies it per warp): every live game has made
     // `lock_plays` plays since the last deal; one more after this launch
     if (h->lock_plays >= 0) h->lock_plays = h->lock_plays < 47 ? h->lock_plays + 1 : -1;
@@ -307,6 +316,15 @@ int tarok_legal_mask(tarok_t* h, uint64_t* out_dev, void* stream) {
     if (((uintptr_t)out_dev) & 15u) return fail(h, -1, "out_dev must be 16-byte aligned");
     DeviceGuard dg(h->device);
     tk::k_legal_mask<<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, (u64*)out_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_hands_by_seat(tarok_t* h, uint64_t* out_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!out_dev) return fail(h, -1, "out_dev is null");
+    DeviceGuard dg(h->device);
+    tk::k_hands_by_seat<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, (u64*)out_dev);
     TK_LAUNCH_OK(h);
     return 0;
 }

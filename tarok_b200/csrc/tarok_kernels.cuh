@@ -99,6 +99,23 @@ __device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, 
 // ------------------------------------------------------------------------------------------------
 struct Dealt { u64 h0, h1, h2, h3, talon, order; };
 
+// ---- hand slots -------------------------------------------------------------------------------------------------
+// hands[j * n_alloc + g] holds the hand of seat (leader + j) & 3, where leader is the M_LEADER field of the game's meta
+// word (the seat that opens the current trick; 0 from the deal until a contract or a trick says otherwise).  The seat to
+// move is therefore always in slot `pos`, the same slot for every game of a lock-step batch: play_step reads and writes
+// ONE coalesced slot (plus the next seat's for its legal mask) instead of gathering from four seat-indexed arrays and
+// scattering 8-byte writes; when a trick ends the four hands are re-written rotated to the winner.  Everything that
+// changes the leader goes through these helpers.  tarok_hands_by_seat / TarokEnv.hands give the seat-indexed view.
+__device__ __forceinline__ void rotate4(u64& a, u64& b, u64& c, u64& d, u32 r) {        // out[j] = in[(j + r) & 3]
+    const u64 x0 = sel4(a, b, c, d, r), x1 = sel4(a, b, c, d, (r + 1u) & 3u), x2 = sel4(a, b, c, d, (r + 2u) & 3u),
+              x3 = sel4(a, b, c, d, (r + 3u) & 3u);
+    a = x0; b = x1; c = x2; d = x3;
+}
+__device__ __forceinline__ void seats_to_slots(u64& a, u64& b, u64& c, u64& d, u32 leader) { rotate4(a, b, c, d, leader & 3u); }
+__device__ __forceinline__ void slots_to_seats(u64& a, u64& b, u64& c, u64& d, u32 leader) { rotate4(a, b, c, d, (4u - leader) & 3u); }
+__device__ __forceinline__ u32 slot_of(u32 seat, u32 leader) { return (seat - leader) & 3u; }
+__device__ __forceinline__ u32 leader_of(u64 meta) { return ((u32)meta >> M_LEADER) & 3u; }
+
 __device__ __forceinline__ u64 order_from_lehmer(u64 talon, u32 L) {
     u64 rem = 0;                                   // the six talon ids ascending, 6 bits each
 #pragma unroll
@@ -272,8 +289,9 @@ __global__ void __launch_bounds__(CTA) k_export_perm(Env e, uint8_t* __restrict_
         uint8_t* row = sh + threadIdx.x * 54;
         const u64 na = e.n_alloc;
         int k = 0;
+        const u32 leader = leader_of(e.meta[g]);
         for (int s = 0; s < 4; s++) {
-            u64 h = e.hands[s * na + g];
+            u64 h = e.hands[slot_of((u32)s, leader) * na + g];
             for (int i = 0; i < 12; i++) {
                 u32 c = h ? (u32)__ffsll((long long)h) - 1u : 0xFFu;
                 h &= h - 1;
@@ -353,10 +371,15 @@ __global__ void __launch_bounds__(CTA) k_begin(Env e, u32 mode, const uint8_t* _
     u64 h0 = e.hands[g], h1 = e.hands[na + g], h2 = e.hands[2 * na + g], h3 = e.hands[3 * na + g];
     u32 contract, declarer, king;
     resolve_contract<SRC>(e.rng, e.first_gid + g, mode, a, b, c, g, contract, declarer, king);
+    slots_to_seats(h0, h1, h2, h3, leader_of(meta));             // identity in practice: a dealt game has leader 0
     meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
     if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
     e.meta[g] = meta;
     e.mask[g] = mask_for_mover(meta, sel4(h0, h1, h2, h3, mover_of(meta)));
+    if (leader_of(meta) != 0u) {                                  // Berac: the declarer opens -> re-seat the slots
+        seats_to_slots(h0, h1, h2, h3, leader_of(meta));
+        e.hands[g] = h0; e.hands[na + g] = h1; e.hands[2 * na + g] = h2; e.hands[3 * na + g] = h3;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,6 +431,8 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
     const u64 na = e.n_alloc;
     u32 decl = mget(meta, M_DECL, 2);
     u64 h0 = e.hands[g], h1 = e.hands[na + g], h2 = e.hands[2 * na + g], h3 = e.hands[3 * na + g];
+    const u32 leader = leader_of(meta);
+    slots_to_seats(h0, h1, h2, h3, leader);
     u64 hand = sel4(h0, h1, h2, h3, decl);
     u64 pile = e.piles[decl * na + g];
     u64 talon = e.talon[g], order = e.torder[g], dout = 0;
@@ -420,7 +445,7 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
         e.mask[g] = 0;
         return;
     }
-    e.hands[decl * na + g] = hand;
+    e.hands[slot_of(decl, leader) * na + g] = hand;
     e.piles[decl * na + g] = pile;
     e.talon[g] = talon;
     e.meta[g] = meta;
@@ -432,20 +457,10 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
 // ------------------------------------------------------------------------------------------------
 // play_step: one card per live game per launch -- THE hot kernel (48 launches per deal).
 // Algorithmic traffic per env-step: R meta 8 + hands 16 + action 1, W hand 8 + meta 8
-// + mask 8, per trick /4: pile RW 16 (+ Klop talon) = 64 B.  What this kernel moves: R meta 8 + all four hands 32
-// (coalesced, instead of gathering two), W hand 8 + meta 8 + mask 8, per trick /4: a 4-byte trick-log entry.
+// + mask 8, per trick /4: pile RW 16 (+ Klop talon) = 64 B.  What a lock-step batch moves: R meta 8 + the mover's and
+// the next seat's slot 16, W slot 8 + meta 8 + mask 8; the trick-closing step reads and re-writes all four slots
+// (rotation to the winner) and appends a 4-byte trick-log entry: 59 B on average.
 // ------------------------------------------------------------------------------------------------
-// Where a lane finds the four hands of its game: registers (plain kernel) or the TMA-staged tile in shared
-// memory, where picking the mover's hand is ONE indexed 64-bit LDS instead of a select chain.
-struct RegHands {
-    u64 h0, h1, h2, h3;
-    __device__ __forceinline__ u64 get(u32 seat) const { return sel4(h0, h1, h2, h3, seat); }
-};
-struct SmemHands {
-    const u64* base;                       // &stage.hands[0][game]; seat stride = TILE words
-    __device__ __forceinline__ u64 get(u32 seat) const { return base[seat * TILE]; }
-};
-
 // ------------------------------------------------------------------------------------------------
 // setup: deal -> contract (synthetic mode) -> talon exchange fused into ONE launch for pipelines whose
 // pre-play decisions are all made on the device (uniform-random / Bot players).  Same device functions and
@@ -480,6 +495,7 @@ __global__ void __launch_bounds__(CTA) k_setup_synth(Env e, u32 mode) {
         }
         if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
         mask = mask_for_mover(meta, sel4(d.h0, d.h1, d.h2, d.h3, mover_of(meta)));
+        seats_to_slots(d.h0, d.h1, d.h2, d.h3, leader_of(meta));
     }
     e.hands[g] = d.h0; e.hands[na + g] = d.h1; e.hands[2 * na + g] = d.h2; e.hands[3 * na + g] = d.h3;
     e.piles[g] = p0; e.piles[na + g] = p1; e.piles[2 * na + g] = p2; e.piles[3 * na + g] = p3;
@@ -502,96 +518,165 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // Game indices are 32-bit inside the step kernels (n_alloc <= 2^29, enforced by tarok_create): one IMAD.WIDE
 // per address instead of 64-bit multiply chains.
-// POS >= 0 = lock-step specialisation: every live game of the warp is at play `plays` (position POS = plays & 3 of its
-// trick), checked by the caller, so position-dependent work folds at compile time; POS = -1 is the general path.
-template <bool RANDOM, int POS, class Hands>
-__device__ __forceinline__ void step_game(const Env& e, u32 g, u64& meta, const Hands& hands, u32 card,
-                                          const Words4& rnd, u64& next_mask) {
+
+// ---- general path: any mix of trick positions; the four slots of the game are in registers ----------------------
+template <bool RANDOM>
+__device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u64 s0, u64 s1, u64 s2, u64 s3, u32 card,
+                                              const Words4& rnd, u64& next_mask) {
     const u32 na = (u32)e.n_alloc;
     const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
-    const u32 pos = POS >= 0 ? (u32)POS : ((lo >> M_POS) & 3u);
-    const u32 mover = ((lo >> M_LEADER) + pos) & 3u;
-    u64 hand = hands.get(mover);
+    const u32 pos = (lo >> M_POS) & 3u, leader = (lo >> M_LEADER) & 3u, kf = (lo >> M_KLOPFAM) & 1u;
+    const u32 mover = (leader + pos) & 3u;
     const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
+    u64 hand = sel4(s0, s1, s2, s3, pos);                          // the seat to move sits in slot `pos`
     if (RANDOM) {
-        u64 legal = legal_moves(hand, pos != 0, hi & 63u, (lo >> M_KLOPFAM) & 1u);
-        u32 n = (u32)__popcll(legal);
-        card = nth_set_bit(legal, play_draw<POS>(rnd, e.rng, e.first_gid + g, plays, n));
+        const u64 legal = legal_moves(hand, pos != 0, hi & 63u, kf);
+        card = nth_set_bit(legal, play_draw<-1>(rnd, e.rng, e.first_gid + g, plays, (u32)__popcll(legal)));
     }
     PlayResult pr;
-    meta = play_card<!RANDOM, POS, false>(meta, hand, card, 0ull, 0ull, pr);
+    meta = play_card<!RANDOM, -1, false>(meta, hand, card, 0ull, 0ull, pr);
     next_mask = 0;
     if (!RANDOM && ((meta >> M_ERR) & 1ull)) {
         atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
         return;
     }
-    e.hands[mover * na + g] = hand;
     if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
-    if ((POS < 0 || POS == 3) && pr.trick_done) {
+    if (!pr.trick_done) {                                          // same trick goes on: next slot follows the same lead
+        e.hands[pos * na + g] = hand;
+        next_mask = legal_moves(sel4(s0, s1, s2, s3, (pos + 1u) & 3u), true, (u32)(meta >> 32) & 63u, kf);
+    } else {
         // append-only trick log (4 B, coalesced) instead of a scattered read-modify-write of the winner's pile;
         // k_score materialises the piles (and the Klop talon) from it
         e.tricklog[(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
-    }
-    if (POS >= 0 && POS < 3) {                                   // same trick goes on: next seat follows the same lead
-        next_mask = legal_moves(hands.get((mover + 1u) & 3u), true, (u32)(meta >> 32) & 63u, (lo >> M_KLOPFAM) & 1u);
-    } else {
-        const u32 nx = mover_of(meta);
-        next_mask = mask_for_mover(meta, nx == mover ? hand : hands.get(nx));
+        s3 = hand;                                                 // the trick closes from slot 3
+        const u32 w = (pr.winner - leader) & 3u;                   // the winner's slot = its index in the trick
+        if (w == 0u) {
+            e.hands[3 * na + g] = s3;                              // the leader stays: only the mover's slot changed
+        } else {
+            rotate4(s0, s1, s2, s3, w);
+            e.hands[g] = s0; e.hands[na + g] = s1; e.hands[2 * na + g] = s2; e.hands[3 * na + g] = s3;
+        }
+        next_mask = mask_for_mover(meta, s0);
     }
 }
 
-// Philox block(s) + the two games of a lane + the two 128-bit stores.
-template <bool RANDOM, int POS, class H0, class H1>
-__device__ __forceinline__ void step_pair(const Env& e, u32 g, ulonglong2& m, bool a0, bool a1, const H0& hx, const H1& hy,
-                                          u32 act, u32 lock_trick) {
+// Philox block(s) for the two games of a lane: one block serves both (same pair, same trick) in the common case.
+__device__ __forceinline__ void pair_blocks(const Env& e, u32 g, u32 t0, u32 t1, bool a1, Words4& r0, Words4& r1) {
+    const u64 gid = e.first_gid + g;
+    r0 = play_block(e.rng, gid, t0);
+    r1 = r0;
+    if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
+}
+
+template <bool RANDOM>
+__device__ __forceinline__ void step_pair_any(const Env& e, u32 g, ulonglong2& m, bool a0, bool a1, ulonglong2 s0,
+                                              ulonglong2 s1, ulonglong2 s2, ulonglong2 s3, u32 act) {
     Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
-    if (RANDOM) {
-        // one Philox block serves both games of the lane (same pair, same trick) in the common case.  In the lock-step
-        // path the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used.
-        const u64 gid = e.first_gid + g;
-        const u32 t0 = POS >= 0 ? lock_trick : ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u;
-        const u32 t1 = POS >= 0 ? lock_trick : ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u;
-        r0 = play_block(e.rng, gid, t0);
-        r1 = r0;
-        if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
-    }
+    if (RANDOM) pair_blocks(e, g, ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u, ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u, a1, r0, r1);
     u64 k0 = 0, k1 = 0;
-    if (a0) step_game<RANDOM, POS>(e, g, m.x, hx, act & 0xFFu, r0, k0);
-    if (a1) step_game<RANDOM, POS>(e, g + 1, m.y, hy, act >> 8, r1, k1);
+    if (a0) step_game_any<RANDOM>(e, g, m.x, s0.x, s1.x, s2.x, s3.x, act & 0xFFu, r0, k0);
+    if (a1) step_game_any<RANDOM>(e, g + 1, m.y, s0.y, s1.y, s2.y, s3.y, act >> 8, r1, k1);
     st2(e.meta + g, m.x, m.y);
     st2(e.mask + g, k0, k1);
 }
 
-// `hint` = the number of plays every live game has made so far (lock-step pipelines know it on the host), or -1.
-// It is only a hint: each warp votes whether all its live games really are at `hint` and otherwise takes the general path.
-template <bool RANDOM>
-__global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restrict__ action, int hint) {
-    pdl_launch_dependents();
+// General path for a lane pair.  HAVE = the trick position whose slots the caller has loaded already (a lock-step kernel
+// whose warp vote failed: slot HAVE in `hm`, slot HAVE + 1 in `n0`, for HAVE == 3 also slots 1, 2 in `n1`, `n2`), or -1.
+// Using them here also keeps those loads above the vote: one memory round trip on the lock-step side.
+template <bool RANDOM, int HAVE>
+__device__ __forceinline__ void step_pair_general(const Env& e, u32 g, ulonglong2 m, bool a0, bool a1, u32 act,
+                                                  ulonglong2 hm, ulonglong2 n0, ulonglong2 n1, ulonglong2 n2) {
+    const u32 na = (u32)e.n_alloc;
+    ulonglong2 s0, s1, s2, s3;
+    if (HAVE == 0) { s0 = hm; s1 = n0; s2 = ld2(e.hands + (2 * na + g)); s3 = ld2(e.hands + (3 * na + g)); }
+    else if (HAVE == 1) { s1 = hm; s2 = n0; s0 = ld2(e.hands + g); s3 = ld2(e.hands + (3 * na + g)); }
+    else if (HAVE == 2) { s2 = hm; s3 = n0; s0 = ld2(e.hands + g); s1 = ld2(e.hands + (na + g)); }
+    else if (HAVE == 3) { s3 = hm; s0 = n0; s1 = n1; s2 = n2; }
+    else { s0 = ld2(e.hands + g); s1 = ld2(e.hands + (na + g)); s2 = ld2(e.hands + (2 * na + g)); s3 = ld2(e.hands + (3 * na + g)); }
+    step_pair_any<RANDOM>(e, g, m, a0, a1, s0, s1, s2, s3, act);
+}
+
+// ---- lock-step path: every live game of the warp has made `hint` plays, so the trick position POS = hint & 3 is a
+// compile-time constant: the mover is slot POS for everybody, the trick-position arithmetic and the trick-end branch fold.
+// hm = slot POS (the mover's hand); POS < 3: n0 = slot POS + 1 (the next seat); POS == 3: n0, n1, n2 = slots 0, 1, 2.
+template <bool RANDOM, int POS>
+__device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u64& hm, u64& n0, u64& n1, u64& n2, u32 card,
+                                               const Words4& rnd, u64& next_mask) {
+    const u32 na = (u32)e.n_alloc;
+    const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
+    const u32 leader = (lo >> M_LEADER) & 3u, kf = (lo >> M_KLOPFAM) & 1u;
+    const u32 mover = (leader + (u32)POS) & 3u;
+    const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
+    if (RANDOM) {
+        const u64 legal = legal_moves(hm, POS != 0, hi & 63u, kf);
+        card = nth_set_bit(legal, play_draw<POS>(rnd, e.rng, e.first_gid + g, plays, (u32)__popcll(legal)));
+    }
+    PlayResult pr;
+    meta = play_card<!RANDOM, POS, false>(meta, hm, card, 0ull, 0ull, pr);
+    next_mask = 0;
+    if (!RANDOM && ((meta >> M_ERR) & 1ull)) {                     // the hand is untouched; the caller stores it back as is
+        atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
+        return;
+    }
+    if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
+    if (POS < 3) {
+        next_mask = legal_moves(n0, true, (u32)(meta >> 32) & 63u, kf);
+    } else {
+        e.tricklog[(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
+        const u32 w = (pr.winner - leader) & 3u;
+        rotate4(n0, n1, n2, hm, w);                                // slots 0..3 re-seated from the winner
+        next_mask = mask_for_mover(meta, n0);
+    }
+}
+
+template <bool RANDOM, int POS>
+__device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restrict__ action, int hint) {
     const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
     const u32 na = (u32)e.n_alloc;                 // the grid covers n_alloc exactly: no partial warps
     pdl_wait();                                    // the previous step's writes are visible from here on
-    // all five 128-bit loads are issued before the first use: one memory round trip per step
+    // every load is issued before the first use: one memory round trip per step
     ulonglong2 m = ld2(e.meta + g);
-    ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + (na + g)), h2 = ld2(e.hands + (2 * na + g)),
-               h3 = ld2(e.hands + (3 * na + g));
+    ulonglong2 hm = ld2(e.hands + (POS * na + g));
+    ulonglong2 n0 = ld2(e.hands + (((POS + 1) & 3) * na + g)), n1 = {0, 0}, n2 = {0, 0};
+    if (POS == 3) { n1 = ld2(e.hands + (na + g)); n2 = ld2(e.hands + (2 * na + g)); }
     u32 act = 0;
     if (!RANDOM) act = load_actions(action, g, e.n);
     const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
     // plays sit in the top byte of the high word and the bits above them are clear for every live game
     const bool in_step = (!a0 || ((u32)(m.x >> 32) >> (M_PLAYS - 32)) == (u32)hint)
                       && (!a1 || ((u32)(m.y >> 32) >> (M_PLAYS - 32)) == (u32)hint);
-    const bool lock = hint >= 0 && __all_sync(0xFFFFFFFFu, in_step);
+    const bool lock = __all_sync(0xFFFFFFFFu, in_step);            // the hint is only a hint: each warp checks it
     if (!a0 && !a1) return;
-    const RegHands hx{h0.x, h1.x, h2.x, h3.x}, hy{h0.y, h1.y, h2.y, h3.y};
-    if (lock) {
-        switch (hint & 3) {
-            case 0: step_pair<RANDOM, 0>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
-            case 1: step_pair<RANDOM, 1>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
-            case 2: step_pair<RANDOM, 2>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
-            default: step_pair<RANDOM, 3>(e, g, m, a0, a1, hx, hy, act, (u32)hint >> 2); break;
-        }
+    if (!lock) { step_pair_general<RANDOM, POS>(e, g, m, a0, a1, act, hm, n0, n1, n2); return; }
+    Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
+    // the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used
+    if (RANDOM) pair_blocks(e, g, (u32)hint >> 2, (u32)hint >> 2, a1, r0, r1);
+    u64 k0 = 0, k1 = 0;
+    if (a0) step_game_lock<RANDOM, POS>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, r0, k0);
+    if (a1) step_game_lock<RANDOM, POS>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, r1, k1);
+    st2(e.hands + (POS * na + g), hm.x, hm.y);     // a game that did not move gets its slot back unchanged
+    if (POS == 3) {
+        st2(e.hands + g, n0.x, n0.y); st2(e.hands + (na + g), n1.x, n1.y); st2(e.hands + (2 * na + g), n2.x, n2.y);
+    }
+    st2(e.meta + g, m.x, m.y);
+    st2(e.mask + g, k0, k1);
+}
+
+// `hint` = the number of plays every live game has made so far (lock-step pipelines know it on the host); POS = hint & 3
+// is compiled in (one kernel per trick position, each with its own register allocation); POS = -1: no hint.
+template <bool RANDOM, int POS>
+__global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restrict__ action, int hint) {
+    pdl_launch_dependents();
+    if constexpr (POS >= 0) {
+        step_lock<RANDOM, POS>(e, action, hint);
     } else {
-        step_pair<RANDOM, -1>(e, g, m, a0, a1, hx, hy, act, 0u);
+        const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
+        pdl_wait();
+        const ulonglong2 m = ld2(e.meta + g), z = {0, 0};
+        u32 act = 0;
+        if (!RANDOM) act = load_actions(action, g, e.n);
+        const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
+        if (a0 || a1) step_pair_general<RANDOM, -1>(e, g, m, a0, a1, act, z, z, z, z);
     }
 }
 
@@ -663,10 +748,25 @@ __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __res
         mbar_wait(&full[s], (it >> 1) & 1u);
         ulonglong2 m = *reinterpret_cast<const ulonglong2*>(&stage[s].meta[l]);
         const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
-        if (a0 || a1)
-            step_pair<RANDOM, -1>(e, g, m, a0, a1, SmemHands{&stage[s].hands[0][l]}, SmemHands{&stage[s].hands[0][l + 1]}, act, 0u);
+        if (a0 || a1) {
+            const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(&stage[s].hands[0][l]),
+                             s1 = *reinterpret_cast<const ulonglong2*>(&stage[s].hands[1][l]),
+                             s2 = *reinterpret_cast<const ulonglong2*>(&stage[s].hands[2][l]),
+                             s3 = *reinterpret_cast<const ulonglong2*>(&stage[s].hands[3][l]);
+            step_pair_any<RANDOM>(e, g, m, a0, a1, s0, s1, s2, s3, act);
+        }
         __syncthreads();                              // stage s may be refilled from the next iteration on
     }
+}
+
+// Seat-indexed copy of the hand slots (for callers that want Roka by seat rather than by trick position).
+__global__ void __launch_bounds__(CTA) k_hands_by_seat(Env e, u64* __restrict__ out) {
+    const u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
+    const u64 na = e.n_alloc;
+    if (g >= na) return;
+    u64 a = e.hands[g], b = e.hands[na + g], c = e.hands[2 * na + g], d = e.hands[3 * na + g];
+    slots_to_seats(a, b, c, d, leader_of(e.meta[g]));
+    out[g] = a; out[na + g] = b; out[2 * na + g] = c; out[3 * na + g] = d;
 }
 
 // Standalone legal mask, recomputed from hands + meta (24 B/env-step algorithmic).
@@ -677,8 +777,9 @@ __global__ void __launch_bounds__(CTA) k_legal_mask(Env e, u64* __restrict__ out
     ulonglong2 m = ld2(e.meta + g);
     ulonglong2 h0 = ld2(e.hands + g), h1 = ld2(e.hands + na + g), h2 = ld2(e.hands + 2 * na + g),
                h3 = ld2(e.hands + 3 * na + g);
-    u64 k0 = mask_for_mover(m.x, sel4(h0.x, h1.x, h2.x, h3.x, mover_of(m.x)));
-    u64 k1 = mask_for_mover(m.y, sel4(h0.y, h1.y, h2.y, h3.y, mover_of(m.y)));
+    // the seat to move sits in slot `pos`
+    u64 k0 = mask_for_mover(m.x, sel4(h0.x, h1.x, h2.x, h3.x, mget(m.x, M_POS, 2)));
+    u64 k1 = mask_for_mover(m.y, sel4(h0.y, h1.y, h2.y, h3.y, mget(m.y, M_POS, 2)));
     if (g + 1 < e.n) st2(out + g, k0, k1);
     else if (g < e.n) out[g] = k0;
 }
@@ -883,6 +984,7 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         if (out) out[g] = packed;
     }
     if (write_state && g < na) {
+        seats_to_slots(h0, h1, h2, h3, leader_of(meta));
         e.hands[g] = h0; e.hands[na + g] = h1; e.hands[2 * na + g] = h2; e.hands[3 * na + g] = h3;
         e.piles[g] = p0; e.piles[na + g] = p1; e.piles[2 * na + g] = p2; e.piles[3 * na + g] = p3;
         e.talon[g] = talon; e.torder[g] = order; e.meta[g] = meta; e.mask[g] = 0;

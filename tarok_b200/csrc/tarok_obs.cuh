@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __res
     const u64 legal = e.mask[g];
     const u32 self = mover_of(meta);
     const u32 pos = mget(meta, M_POS, 2), lead = mget(meta, M_TRICK, 6);
-    const u64 hand = e.hands[self * na + g];
+    const u64 hand = e.hands[pos * na + g];                        // hand slots are leader-relative: the mover sits in slot pos
     // is `mozne` one of the player's own suit lists (list order) or the sorted union (id order)?
     bool list_order = false;
     if (pos != 0) list_order = (hand & suit_mask_of(lead)) != 0 || (hand & TAROKS) != 0;
@@ -237,8 +237,9 @@ __global__ void __launch_bounds__(CTA) k_obs_hands(Env e, float* __restrict__ ou
     const u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
     if (g >= e.n) return;
     const u64 na = e.n_alloc;
+    const u32 leader = leader_of(e.meta[g]);
 #pragma unroll
-    for (int s = 0; s < 4; s++) warp_bits(out + (g * 4 + s) * 54u, e.hands[s * na + g], lane);
+    for (int s = 0; s < 4; s++) warp_bits(out + (g * 4 + s) * 54u, e.hands[slot_of((u32)s, leader) * na + g], lane);
 }
 
 __global__ void __launch_bounds__(CTA) k_obs_exchange(Env e, const int* __restrict__ sel, u64 n_sel, float* __restrict__ hand,
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(CTA) k_obs_exchange(Env e, const int* __restri
     if (!match) return;
     const u32 contract = mget(meta, M_CONTRACT, 4), decl = mget(meta, M_DECL, 2), king = mget(meta, M_KING, 3);
     const u32 k = talon_k(contract);
-    warp_bits(hand + i * 54u, e.hands[decl * na + g], lane);
+    warp_bits(hand + i * 54u, e.hands[slot_of(decl, leader_of(meta)) * na + g], lane);
     const u64 order = e.torder[g];
     if (lane < 6) talon[i * 324u + ((order >> (6 * lane)) & 63ull) * 6u + lane / k] = 1.f;
     if (lane == 0) game[i * 15u + (is_king_game(contract) ? (contract - C_TRI) * 4u + king : 12u + (contract - C_SOLO_TRI))] = 1.f;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(CTA) k_select_exchange(Env e, const float* __r
     Words4 rnd = philox_block(e.rng, gid, ST_EXPLORE, 50u);                       // same words on every lane
     if (explore_threshold && rnd.w[0] < explore_threshold) group = draw_from_word(rnd.w[1], e.rng, gid, ST_EXPLORE, 201u, groups);
     const u64 order = e.torder[g];
-    const u64 hand = e.hands[decl * na + g];
+    const u64 hand = e.hands[slot_of(decl, leader_of(meta)) * na + g];
     const u64 gb = talon_group_bits(order, k, group);
     u64 avail = (hand | gb) & DISCARDABLE;
     u64 discard = 0;

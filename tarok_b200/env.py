@@ -134,7 +134,14 @@ class TarokEnv:
         return t
 
     # zero-copy state
-    hands = property(lambda self: self.view(F_HANDS))            # int64 [4, n_alloc]
+    hand_slots = property(lambda self: self.view(F_HANDS))       # int64 [4, n_alloc], row j = seat (leader + j) & 3 (zero-copy)
+
+    @property
+    def hands(self):
+        """Hand bitboards by SEAT, int64 [4, n_alloc]: a fresh copy (the device keeps them in leader-relative slots)."""
+        out = torch.empty((4, self.n_alloc), dtype=torch.int64, device=self.torch_device)
+        self._check(self._lib.tarok_hands_by_seat(self._h, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
     piles = property(lambda self: self.view(F_PILES))            # int64 [4, n_alloc]
     talon = property(lambda self: self.view(F_TALON))            # int64 [n_alloc]
     talon_order = property(lambda self: self.view(F_TALON_ORDER))
