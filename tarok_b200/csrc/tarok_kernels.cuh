@@ -107,9 +107,9 @@ struct Dealt { u64 h0, h1, h2, h3, talon, order; };
 // scattering 8-byte writes; when a trick ends the four hands are re-written rotated to the winner.  Everything that
 // changes the leader goes through these helpers.  tarok_hands_by_seat / TarokEnv.hands give the seat-indexed view.
 __device__ __forceinline__ void rotate4(u64& a, u64& b, u64& c, u64& d, u32 r) {        // out[j] = in[(j + r) & 3]
-    const u64 x0 = sel4(a, b, c, d, r), x1 = sel4(a, b, c, d, (r + 1u) & 3u), x2 = sel4(a, b, c, d, (r + 2u) & 3u),
-              x3 = sel4(a, b, c, d, (r + 3u) & 3u);
-    a = x0; b = x1; c = x2; d = x3;
+    const bool by1 = r & 1u, by2 = r & 2u;                 // two conditional stages: by one, then by two
+    const u64 a1 = by1 ? b : a, b1 = by1 ? c : b, c1 = by1 ? d : c, d1 = by1 ? a : d;
+    a = by2 ? c1 : a1; b = by2 ? d1 : b1; c = by2 ? a1 : c1; d = by2 ? b1 : d1;
 }
 __device__ __forceinline__ void seats_to_slots(u64& a, u64& b, u64& c, u64& d, u32 leader) { rotate4(a, b, c, d, leader & 3u); }
 __device__ __forceinline__ void slots_to_seats(u64& a, u64& b, u64& c, u64& d, u32 leader) { rotate4(a, b, c, d, (4u - leader) & 3u); }
@@ -549,7 +549,7 @@ __device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u6
         // k_score materialises the piles (and the Klop talon) from it
         e.tricklog[(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
         s3 = hand;                                                 // the trick closes from slot 3
-        const u32 w = (pr.winner - leader) & 3u;                   // the winner's slot = its index in the trick
+        const u32 w = pr.winner_rel;                               // the winner's slot = its index in the trick
         if (w == 0u) {
             e.hands[3 * na + g] = s3;                              // the leader stays: only the mover's slot changed
         } else {
@@ -601,7 +601,7 @@ __device__ __forceinline__ void step_pair_general(const Env& e, u32 g, ulonglong
 // hm = slot POS (the mover's hand); POS < 3: n0 = slot POS + 1 (the next seat); POS == 3: n0, n1, n2 = slots 0, 1, 2.
 template <bool RANDOM, int POS>
 __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u64& hm, u64& n0, u64& n1, u64& n2, u32 card,
-                                               const Words4& rnd, u64& next_mask) {
+                                               const Words4& rnd, u64& next_mask, u32& log_entry) {
     const u32 na = (u32)e.n_alloc;
     const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 leader = (lo >> M_LEADER) & 3u, kf = (lo >> M_KLOPFAM) & 1u;
@@ -622,10 +622,10 @@ __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u
     if (POS < 3) {
         next_mask = legal_moves(n0, true, (u32)(meta >> 32) & 63u, kf);
     } else {
-        e.tricklog[(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
-        const u32 w = (pr.winner - leader) & 3u;
-        rotate4(n0, n1, n2, hm, w);                                // slots 0..3 re-seated from the winner
-        next_mask = mask_for_mover(meta, n0);
+        log_entry = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
+        rotate4(n0, n1, n2, hm, pr.winner_rel);                    // slots 0..3 re-seated from the winner
+        // the winner opens the next trick: everything it holds (minus the Klop-family pagat rule), nothing once finished
+        next_mask = (((u32)meta >> M_PHASE) & 3u) == PH_PLAY ? legal_moves(n0, false, 0u, kf) : 0ull;
     }
 }
 
@@ -652,11 +652,18 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     // the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used
     if (RANDOM) pair_blocks(e, g, (u32)hint >> 2, (u32)hint >> 2, a1, r0, r1);
     u64 k0 = 0, k1 = 0;
-    if (a0) step_game_lock<RANDOM, POS>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, r0, k0);
-    if (a1) step_game_lock<RANDOM, POS>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, r1, k1);
+    u32 l0 = 0, l1 = 0;                            // trick-log entries (POS == 3); 0 = nothing to append
+    if (a0) step_game_lock<RANDOM, POS>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, r0, k0, l0);
+    if (a1) step_game_lock<RANDOM, POS>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, r1, k1, l1);
     st2(e.hands + (POS * na + g), hm.x, hm.y);     // a game that did not move gets its slot back unchanged
     if (POS == 3) {
         st2(e.hands + g, n0.x, n0.y); st2(e.hands + (na + g), n1.x, n1.y); st2(e.hands + (2 * na + g), n2.x, n2.y);
+        // append-only trick log (4 B per game, coalesced) instead of a scattered read-modify-write of the winner's pile;
+        // the trick index is the uniform hint.  (A game that refused an illegal card gets a 0 entry nobody reads.)
+        u32* row = e.tricklog + ((u32)hint >> 2) * na + g;
+        if (a0 && a1) *reinterpret_cast<uint2*>(row) = make_uint2(l0, l1);
+        else if (a0) row[0] = l0;
+        else row[1] = l1;
     }
     st2(e.meta + g, m.x, m.y);
     st2(e.mask + g, k0, k1);

@@ -108,16 +108,21 @@ __device__ __forceinline__ u64 legal_moves(u64 hand, bool has_lead, u32 lead, bo
 
 // pobere_stih / primerjaj_karti (Navadna_igra.py:143-156, Klop.py:81-94): scan cards 1..3 against the
 // current best: same suit and higher rank, or a tarok over a non-tarok.  No trula/pagat rule (Q3).
+// Branch-free form: only a tarok or a card of the led suit can ever be "best", and among those the larger id wins
+// (taroks are ids 32..53, above every suit card; within a suit a larger id is a higher rank), so the winner is the arg-max
+// of key_i = eligible_i ? ((c_i + 1) << 2 | i) : 0.  Same suit as the lead <=> (c ^ lead) < 8 for a suit lead; for a tarok
+// lead that test only ever adds taroks.  Checked against the sequential scan on all 54*53*52*51 ordered tricks
+// (tests/test_oracle_golden.py::test_trick_winner_closed_form).
 __device__ __forceinline__ u32 trick_winner(u32 t24) {
-    u32 best = t24 & 63u, w = 0;
+    const u32 lead = t24 & 63u;
+    u32 m = ((lead + 1u) << 2);
 #pragma unroll
-    for (int i = 1; i < 4; i++) {
-        u32 c = (t24 >> (6 * i)) & 63u;
-        u32 sb = best >= 32 ? 4u : (best >> 3), sc = c >= 32 ? 4u : (c >> 3);
-        bool beats = (sb == sc) ? (c > best) : (sc == 4u);
-        if (beats) { best = c; w = i; }
+    for (u32 i = 1; i < 4; i++) {
+        const u32 c = (t24 >> (6u * i)) & 63u;
+        const bool eligible = c >= 32u || (c ^ lead) < 8u;
+        m = max(m, eligible ? (((c + 1u) << 2) | i) : 0u);
     }
-    return w;
+    return m & 3u;
 }
 
 // Roka.prestej (Roka.py:55-98): groups of three, sum-2; a remainder of one or two cards, sum-1 (Q10).
@@ -262,6 +267,7 @@ __device__ __forceinline__ u64 talon_group_bits(u64 order, u32 k, u32 g) {
 // (Berac.py:33-39, Q12).
 struct PlayResult {
     bool trick_done;
+    u32 winner_rel;   // the winner's index in the trick's play order (= its hand slot)
     u32 winner;       // absolute seat
     u64 pile_bits;    // cards the winner collects
     u64 talon_clear;  // Klop: talon bit consumed
@@ -276,7 +282,7 @@ struct PlayResult {
 template <bool CHECK, int POS = -1, bool BITS = true>
 __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talon, u64 talon_order,
                                          PlayResult& out) {
-    out.trick_done = false; out.winner = 0; out.pile_bits = 0; out.talon_clear = 0;
+    out.trick_done = false; out.winner = 0; out.winner_rel = 0; out.pile_bits = 0; out.talon_clear = 0;
     u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 contract = lo & 15u;
     const u32 pos = POS >= 0 ? (u32)POS : ((lo >> M_POS) & 3u);
@@ -297,7 +303,9 @@ __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talo
     }
     // trick complete
     const u32 tricks = (lo >> M_TRICKS) & 15u;
-    const u32 w = (((lo >> M_LEADER) & 3u) + trick_winner(tr)) & 3u;
+    const u32 wr = trick_winner(tr);
+    const u32 w = (((lo >> M_LEADER) & 3u) + wr) & 3u;
+    out.winner_rel = wr;
     if (BITS) {
         u64 bits = (1ull << (tr & 63u)) | (1ull << ((tr >> 6) & 63u)) | (1ull << ((tr >> 12) & 63u)) | (1ull << (tr >> 18));
         if (contract == C_KLOP && tricks < 6) {
@@ -308,7 +316,8 @@ __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talo
         out.pile_bits = bits;
     }
     out.trick_done = true; out.winner = w;
-    const bool fin = tricks == 11 || (is_berac(contract) && w == ((lo >> M_DECL) & 3u));
+    // Berac (the Klop-family contracts other than Klop itself) stops when the declarer takes a trick
+    const bool fin = tricks == 11 || (((lo >> M_KLOPFAM) & 1u) && contract != C_KLOP && w == ((lo >> M_DECL) & 3u));
     constexpr u32 CLEAR = (3u << M_LEADER) | (3u << M_POS) | (15u << M_TRICKS) | (3u << M_WINNER) | (1u << M_TRICKDONE)
                         | (3u << M_PHASE);
     lo = (lo & ~CLEAR) | (w << M_LEADER) | ((tricks + 1u) << M_TRICKS) | (w << M_WINNER) | (1u << M_TRICKDONE)
