@@ -145,17 +145,21 @@ __device__ __forceinline__ u64 order_from_lehmer(u64 talon, u32 L) {
 // compile time in the unrolled loop: every update is one predicated 32-bit OR.
 enum : u32 { ST_DEAL_RETRY = 7 };
 
-// The pile walk keeps CUMULATIVE state: T_j = free slots in piles 0..j and H_j = cards dealt to piles 0..j.  A draw r
-// picks pile s = min{j : r < T_j}, i.e. q_j = (r < T_j) holds exactly for j >= s, so the whole update is
-// H_j |= q_j ? bit : 0 and T_j -= q_j -- four compares, four predicated ORs, four predicated decrements per card;
-// the hands are recovered at the end as H_0, H_1^H_0, H_2^H_1, H_3^H_2 and the talon as ALL54 ^ H_3.
+// The pile walk keeps CUMULATIVE state: T_j = free slots in piles 0..j.  A draw r picks pile s = min{j : r < T_j}, i.e.
+// q_j = (r < T_j) holds exactly for j >= s, and the update is T_j -= q_j.  The four T_j (<= 54) live in the four bytes of
+// ONE register with bit 7 of every byte set, so that a single subtraction compares all four at once (bit 7 of byte j of
+// T - (r + 1) * 0x01010101 survives iff r < T_j; no borrow can cross a byte); the four q_j of the eight cards of a Philox
+// block are shifted into one accumulator (byte j = the block's eight q_j bits) and transposed into the cumulative
+// bitboards H_j = cards in piles 0..j with byte permutes once per block group: 6 integer instructions per card after the
+// draw.  The hands are H_0, H_1^H_0, H_2^H_1, H_3^H_2 and the talon ALL54 ^ H_3.
 __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
-    u32 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
-    u32 t0 = 12, t1 = 24, t2 = 36, t3 = 48;
+    u32 T = 0x80808080u | 12u | (24u << 8) | (36u << 16) | (48u << 24);
+    u32 rev[7];
     u32 L = 0;
 #pragma unroll
     for (int blk = 0; blk < 7; blk++) {
         Words4 b = philox_block(rng, gid, ST_DEAL, (u32)blk);
+        u32 acc = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int c = blk * 8 + j;
@@ -166,25 +170,36 @@ __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
                 const u32 m = x * n;
                 u32 r = m >> 16;
                 if (__builtin_expect((m & 0xFFFFu) < (65536u % n), 0)) r = draw_loop(rng.seed, gid, ST_DEAL_RETRY, (u32)c, n, 0u);
-                const bool q0 = r < t0, q1 = r < t1, q2 = r < t2, q3 = r < t3;
-                const u32 bit = 1u << (c & 31);
-                u32* half = c < 32 ? lo : hi;
-                half[0] |= q0 ? bit : 0u; t0 -= q0 ? 1u : 0u;
-                half[1] |= q1 ? bit : 0u; t1 -= q1 ? 1u : 0u;
-                half[2] |= q2 ? bit : 0u; t2 -= q2 ? 1u : 0u;
-                half[3] |= q3 ? bit : 0u; t3 -= q3 ? 1u : 0u;
-            } else if (c == 55) {                               // word 27 whole: the talon order
-                const u64 m = (u64)word * 720u;
-                L = (u32)(m >> 32);
-                if (__builtin_expect((u32)m < 256u, 0)) L = draw_loop(rng.seed, gid, ST_DEAL_RETRY, 54u, 720u, 0u);   // 2^32 % 720 = 256
+                const u32 q = ((T - (r * 0x01010101u + 0x01010101u)) >> 7) & 0x01010101u;   // byte j = (r < T_j)
+                T -= q;
+                acc = acc * 2u + q;
+            } else {
+                acc *= 2u;                                       // pad: keeps card j of the block at bit 7 - j
+                if (c == 55) {                                   // word 27 whole: the talon order
+                    const u64 m = (u64)word * 720u;
+                    L = (u32)(m >> 32);
+                    if (__builtin_expect((u32)m < 256u, 0)) L = draw_loop(rng.seed, gid, ST_DEAL_RETRY, 54u, 720u, 0u);   // 2^32 % 720 = 256
+                }
             }
         }
+        rev[blk] = __brev(acc);                                  // byte 3 - j: bit jj = q_j of card 8 * blk + jj
+    }
+    // 4 x 4 byte transposes: H_j.lo = byte (3 - j) of rev[0..3], H_j.hi = byte (3 - j) of rev[4..6]
+    u64 H[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const u32 k = 3u - (u32)j;                               // source byte
+        const u32 lo01 = __byte_perm(rev[0], rev[1], k | ((4u + k) << 4));            // bytes: [rev0.k, rev1.k, x, x]
+        const u32 lo23 = __byte_perm(rev[2], rev[3], k | ((4u + k) << 4));
+        const u32 lo = __byte_perm(lo01, lo23, 0x5410);                               // [lo01.0, lo01.1, lo23.0, lo23.1]
+        const u32 hi45 = __byte_perm(rev[4], rev[5], k | ((4u + k) << 4));
+        const u32 hi6 = (rev[6] >> (8u * k)) & 0xFFu;
+        const u32 hi = (hi45 & 0xFFFFu) | (hi6 << 16);
+        H[j] = ((u64)hi << 32) | lo;
     }
     Dealt d;
-    const u64 H0 = ((u64)hi[0] << 32) | lo[0], H1 = ((u64)hi[1] << 32) | lo[1], H2 = ((u64)hi[2] << 32) | lo[2],
-              H3 = ((u64)hi[3] << 32) | lo[3];
-    d.h0 = H0; d.h1 = H1 ^ H0; d.h2 = H2 ^ H1; d.h3 = H3 ^ H2;
-    d.talon = ALL54 ^ H3;
+    d.h0 = H[0]; d.h1 = H[1] ^ H[0]; d.h2 = H[2] ^ H[1]; d.h3 = H[3] ^ H[2];
+    d.talon = ALL54 ^ H[3];
     d.order = order_from_lehmer(d.talon, L);
     return d;
 }
