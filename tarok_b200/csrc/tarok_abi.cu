@@ -16,7 +16,7 @@
 using tk::u64;
 using tk::u32;
 
-#define TK_MAX_CHUNKS 8
+#define TK_MAX_CHUNKS 32
 
 struct tarok_env {
     int device;
@@ -26,6 +26,7 @@ struct tarok_env {
     int lockstep;                              // pass the lock-step hint to play_step (specialised per trick position)
     int lock_plays;                            // plays made by every live game since the last deal, -1 = unknown
     int materialise;                           // tarok_score writes the materialised piles / talon back (default on)
+    int chunks;                                // upload/compute/download pipeline depth of the host-buffer entries
     u32 flags;
     tk::Env e;
     // staging buffers of the host-buffer entry point
@@ -118,6 +119,7 @@ int tarok_set_option(tarok_t* h, int option, int64_t value) {
     if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
     if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
     if (option == TAROK_OPT_MATERIALISE && (value == 0 || value == 1)) { h->materialise = (int)value; return 0; }
+    if (option == TAROK_OPT_CHUNKS && value >= 1 && value <= TK_MAX_CHUNKS) { h->chunks = (int)value; return 0; }
     return fail(h, -1, "unknown option %d / value %lld", option, (long long)value);
 }
 
@@ -138,7 +140,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     tarok_env* h = new (std::nothrow) tarok_env();
     if (!h) return fail(nullptr, -4, "out of host memory");
     memset(&h->e, 0, sizeof(h->e));
-    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->materialise = 1; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
+    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->materialise = 1; h->chunks = 8; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;
@@ -492,7 +494,8 @@ static int rollout_host_fused(tarok_t* h, const uint8_t* deals_host, size_t row,
                               const uint8_t* declarer_host, const uint8_t* king_host, int16_t* scores_host,
                               int64_t* stats_host, cudaStream_t s) {
     const u64 n = h->e.n;
-    const u64 chunk = (n >= (1ull << 18)) ? (((n + 7) / 8 + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
+    const u64 want = (u64)h->chunks;
+    const u64 chunk = (n >= (1ull << 18)) ? (((n + want - 1) / want + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
     const int nchunks = (int)((n + chunk - 1) / chunk);
     TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
     TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));

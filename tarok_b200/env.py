@@ -158,6 +158,10 @@ class TarokEnv:
         """0 auto, 1 plain play_step kernel, 2 persistent TMA-staged kernel (A/B measurements)."""
         self._check(self._lib.tarok_set_option(self._h, 1, int(impl)))
 
+    def set_chunks(self, chunks: int):
+        """Pipeline depth (1..32, default 8) of the host-buffer entries ``rollout_host(fused=True)`` / ``rollout_records``."""
+        self._check(self._lib.tarok_set_option(self._h, 5, int(chunks)))
+
     def set_materialise(self, on: bool):
         """Whether ``score()`` writes the full piles / Klop talon back (default) or only produces scores + statistics."""
         self._check(self._lib.tarok_set_option(self._h, 4, 1 if on else 0))
