@@ -449,6 +449,35 @@ def test_every_play_step_variant_matches_oracle(oracle, impl, pdl, lock):
         env.close()
 
 
+@pytest.mark.parametrize("lock", [True, False])
+def test_hand_slots_follow_the_trick_leader(lock):
+    """TAROK_F_HANDS is kept in leader-relative slots (row j = seat (leader + j) & 3): check the invariant against the
+    seat-indexed copy at every play of a mixed-contract batch (Berac: the declarer leads from the start), with the lock-step
+    kernels and with the general path, and that the legal mask is cut from the mover's hand (= row `pos`)."""
+    import torch
+    import tarok_b200.env as E
+    n = 20000
+    env = _env(n, seed=99)
+    env.set_lockstep(lock)
+    env.setup_synth(E.MODE_AUCTION_UNIFORM, 0)
+    idx = torch.arange(n, device="cuda")
+    for t in range(48):
+        meta = env.meta[:n]
+        leader = (meta >> E.M_LEADER) & 3
+        pos = (meta >> E.M_POS) & 3
+        live = ((meta >> E.M_PHASE) & 3) == E.PH_PLAY
+        seats = env.hands[:, :n]
+        slots = env.hand_slots[:, :n]
+        for j in range(4):
+            assert bool((slots[j] == seats[(leader + j) & 3, idx]).all()), (t, j)
+        mask = env.mask[:n]
+        assert bool(((mask & ~slots[pos, idx]) == 0)[live].all()), t
+        assert bool((mask[live] != 0).all()) and bool((mask[~live] == 0).all()), t
+        del meta, slots, mask
+        env.step_random(1)
+    env.close()
+
+
 def test_error_paths_are_loud():
     """Bad arguments and bad inputs come back as error codes / error bits with a message, never silently."""
     import torch
