@@ -112,7 +112,7 @@ __device__ __forceinline__ u64 legal_moves(u64 hand, bool has_lead, u32 lead, bo
 // (taroks are ids 32..53, above every suit card; within a suit a larger id is a higher rank), so the winner is the arg-max
 // of key_i = eligible_i ? ((c_i + 1) << 2 | i) : 0.  Same suit as the lead <=> (c ^ lead) < 8 for a suit lead; for a tarok
 // lead that test only ever adds taroks.  Checked against the sequential scan on all 54*53*52*51 ordered tricks
-// (tests/test_oracle_golden.py::test_trick_winner_closed_form).
+// (tests/test_closed_forms.py).
 __device__ __forceinline__ u32 trick_winner(u32 t24) {
     const u32 lead = t24 & 63u;
     u32 m = ((lead + 1u) << 2);
