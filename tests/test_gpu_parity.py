@@ -194,6 +194,34 @@ def test_rollout_matches_oracle(oracle, mode, gid0):
     env.close()
 
 
+def test_desynchronised_batch_takes_the_general_path(oracle):
+    """Games that start playing at different times (here: the contracts without a talon exchange play three cards before
+    the others have exchanged) break the lock-step hint inside most warps; the per-warp vote must then send them through
+    the general path, with the same games as a result (the Philox draws depend on the game and its own play index only)."""
+    import tarok_b200.env as E
+    n, seed, gid0 = 40001, 777, 5
+    ref = oracle.rollout(seed, gid0, n, E.MODE_AUCTION_UNIFORM)
+    env = _env(n, seed=seed, history=True)
+    env.deal(gid0)
+    env.auction_synth(E.MODE_AUCTION_UNIFORM)
+    waiting = (_meta(env)["phase"] == E.PH_EXCHANGE)
+    assert 0.05 < waiting.mean() < 0.95                      # a real mix inside every warp
+    env.step_random(3)                                       # only Klop / Berac / Solo_brez games move
+    m = _meta(env)
+    assert (m["plays"][waiting] == 0).all() and (m["plays"][~waiting & (ref["err"] == 0)] == 3).all()
+    env.exchange_synth(True)
+    env.step_random(48)                                      # 45 more for the early starters, 48 for the rest
+    sc = env.score().cpu().numpy()
+    assert (sc == ref["scores"]).all()
+    assert (_meta(env)["plays"] == ref["plays"]).all()
+    hist = env.hist[:, :n].cpu().numpy().T
+    played = ref["cards"] != 0xFF
+    assert ((hist & 63)[played] == ref["cards"][played]).all()
+    st = env.stats()
+    assert (st[0:8] == ref["stats"][0:8]).all() and st[19] == ref["stats"][8] and st[20] == ref["stats"][9]
+    env.close()
+
+
 def test_fused_setup_equals_separate_kernels():
     import tarok_b200.env as E
     n = 70001
