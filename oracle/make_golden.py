@@ -81,7 +81,8 @@ def _pack(recs, extra=None):
     return a
 
 
-def gen_traces(per_contract=150, seed=20261018):
+def build_traces(per_contract, seed):
+    """Forced-contract games played by the real reference with seeded random decisions -> packed arrays."""
     rng = random.Random(seed)
     recs = []
     for c in range(10):
@@ -95,11 +96,16 @@ def gen_traces(per_contract=150, seed=20261018):
                 recs.append(H.run_forced(perm, c, d, k, pol))
             except ValueError:      # random.sample: fewer than k discardable cards (Q19)
                 continue
-    np.savez_compressed(os.path.join(OUT, "traces_forced.npz"), **_pack(recs))
-    print("traces_forced.npz", len(recs))
+    return _pack(recs)
 
 
-def gen_full(n=400, seed=7):
+def gen_traces(per_contract=150, seed=20261018):
+    a = build_traces(per_contract, seed)
+    np.savez_compressed(os.path.join(OUT, "traces_forced.npz"), **a)
+    print("traces_forced.npz", len(a["contract"]))
+
+
+def build_full(n, seed):
     """Whole Igra.start(): fixed-intent auction (Nevronski model) + king call + dispatch + play."""
     rng = random.Random(seed)
     recs, intents = [], []
@@ -116,9 +122,13 @@ def gen_full(n=400, seed=7):
         except ValueError:
             continue
         intents.append(idx)
-    np.savez_compressed(os.path.join(OUT, "traces_full.npz"),
-                        **_pack(recs, dict(intent=np.array(intents, np.uint8))))
-    print("traces_full.npz", len(recs), np.bincount([r.contract for r, _ in recs], minlength=10))
+    return _pack(recs, dict(intent=np.array(intents, np.uint8)))
+
+
+def gen_full(n=400, seed=7):
+    a = build_full(n, seed)
+    np.savez_compressed(os.path.join(OUT, "traces_full.npz"), **a)
+    print("traces_full.npz", len(a["contract"]), np.bincount(a["contract"], minlength=10))
 
 
 def gen_auction():
