@@ -7,7 +7,8 @@ One "step" = one pass of the hot path over one batch: deal -> contract -> talon 
 48 x play_step (uniform-random legal-move players) -> score, for G concurrent deals per GPU
 (default: BASELINE config 2 = 1,048,576 Navadna deals on one B200).  Prints ONE JSON line.
 
-* value      whole-job env-steps/s, inputs resident in HBM (Philox deals generated on device)
+* value      whole-job env-steps/s, inputs resident in HBM (Philox deals generated on device); each of the K steps
+             is bracketed by its own CUDA-event pair, a 160 MiB L2-flush write runs between the pairs
 * e2e        same metric through the host-buffer C-ABI entry (tarok_rollout_host): pinned host deals
              + contracts uploaded, scores + stats downloaded, inside the timed region
 * roofline   the dominant kernel k_step<random>: 64 B/env-step x live games per
@@ -217,10 +218,14 @@ def run_ours(args, rank, world, local_rank):
     pending = []
     step_events = []
 
-    def rollout(i, timed):
+    iter_events = []
+
+    def rollout(i, timed, last=False):
         gid0 = i * total + rank * n
         if not args.no_flush:
-            flush.zero_()                                                  # L2 flush between iterations
+            flush.zero_()                                                  # L2 flush between iterations (not timed)
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
         env.setup_synth(mode, gid0)                                        # deal + contract + exchange, one launch
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -232,8 +237,13 @@ def run_ours(args, rank, world, local_rank):
             # the one collective: returns/statistics, 256 B over NCCL/NVLink; asynchronous so that the next
             # rollout's deal overlaps it (waited for before the timed region closes)
             pending.append(dist.all_reduce(stats_ring[i], async_op=True))
+        if last:
+            for w in pending:                                              # every all-reduce lands inside a timed interval
+                w.wait()
+        i1.record()
         if timed:
             step_events.append((a, b))
+            iter_events.append((i0, i1))
 
     def barrier():
         if world > 1:
@@ -252,13 +262,13 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t0.record()
     for i in range(args.steps):
-        rollout(args.warmup + i, True)
-    for w in pending:
-        w.wait()
+        rollout(args.warmup + i, True, last=(i == args.steps - 1))
     t1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    # K steps, each timed by its own CUDA-event pair on the launching stream (the L2-flush writes run between the pairs)
+    region_ms = t0.elapsed_time(t1)
+    ms = torch.tensor([sum(x.elapsed_time(y) for x, y in iter_events)], dtype=torch.float64, device=dev)
     step_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in step_events) / (48 * len(step_events))],
                            dtype=torch.float64, device=dev)
     if world > 1:
@@ -382,8 +392,12 @@ def run_ours(args, rank, world, local_rank):
                                   "in the 4-byte-per-trick log (TAROK_OPT_MATERIALISE=0), as Tarok.paralel_start never returns them",
                        "l2": ("no flush: every iteration regenerates and revisits its own %d MB state (> 126 MB L2)" % (n * 152 >> 20))
                              if args.no_flush else
-                             ("160 MiB flush write between iterations (inside the timed region); within one iteration the 48 "
-                              "play_steps revisit the %d MB state as the workload prescribes" % (n * 152 >> 20))},
+                             ("160 MiB flush write between iterations, outside the per-iteration event pairs (and every iteration "
+                              "regenerates its own %d MB state, larger than L2); within one iteration the 48 play_steps revisit "
+                              "that state as the workload prescribes" % (n * 152 >> 20)),
+                       "timing": "each of the K steps bracketed by its own CUDA-event pair; ms_per_step = their mean, max over ranks; "
+                                 "region_ms_incl_flush = first event to last event including the flush writes"},
+            "region_ms_incl_flush": region_ms,
             "deals_per_sec": deals / (ms * 1e-3), "env_steps": env_steps, "deals": deals, "error_games": errors,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": world * n * 57,
                     "d2h_bytes_per_step": world * (n * 8 + 256), "ms_per_step": e2e_ms,
