@@ -76,14 +76,13 @@ struct DeviceGuard {
     ~DeviceGuard() { if (ok) cudaSetDevice(prev); }
 };
 
-// play_step launcher: persistent TMA-staged kernel (one CTA per resident slot, 4 per SM) once the batch has
-// more tiles than resident CTAs; the plain one-tile-per-CTA kernel for small batches.
+// play_step launcher.  Default: the plain kernel, one 512-game tile per CTA, compiled per trick position for lock-step
+// batches (the hint) with programmatic dependent launch; TAROK_OPT_STEP_IMPL=2 selects the persistent TMA-staged variant
+// (one CTA per resident slot, 4 per SM), which measures slower on B200 and is kept for comparison (tools/step_ab.py).
 template <bool RANDOM>
 static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     const unsigned tiles = grid2(h->e.n_alloc);
     const unsigned resident = (unsigned)h->sm_count * 4u;
-    // measured on B200 (tools/step_ab.py, profiles/r01): the kernel is bound by integer-ALU issue, not by load
-    // latency, so the plain kernel wins; "auto" therefore picks it and the staged one stays selectable.
     const bool tma = h->step_impl == 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tma ? (tiles < resident ? tiles : resident) : tiles);
