@@ -2,7 +2,8 @@
 //
 // HBM layout (structure of arrays, one 64-bit word per game per field, n_alloc = n rounded up to
 // the 512-game CTA tile, every array 256-byte aligned):
-//   hands[4][n_alloc]  piles[4][n_alloc]  talon[n_alloc]  torder[n_alloc]  meta[n_alloc]
+//   hands[4][n_alloc] (leader-relative slots, see "hand slots" below; everything else is indexed by seat)
+//   piles[4][n_alloc]  talon[n_alloc]  torder[n_alloc]  meta[n_alloc]
 //   mask[n_alloc]  scores[n_alloc] (int16 x4)  tricklog[12][n_alloc] (uint32)
 //   optional (TAROK_FLAG_HISTORY): hist[48][n_alloc] (uint8)  hands0[4][n_alloc]  discard[n_alloc]  qmax_hist[48][n_alloc] (float)
 // The stepwise kernels give each lane TWO consecutive games so that every per-field access is one
