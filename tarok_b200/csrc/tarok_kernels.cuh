@@ -563,7 +563,7 @@ __device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u6
     } else {
         // append-only trick log (4 B, coalesced) instead of a scattered read-modify-write of the winner's pile;
         // k_score materialises the piles (and the Klop talon) from it
-        e.tricklog[(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
+        e.tricklog[(u64)(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);   // 12 rows: 64-bit index
         s3 = hand;                                                 // the trick closes from slot 3
         const u32 w = pr.winner_rel;                               // the winner's slot = its index in the trick
         if (w == 0u) {
@@ -676,7 +676,7 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
         st2(e.hands + g, n0.x, n0.y); st2(e.hands + (na + g), n1.x, n1.y); st2(e.hands + (2 * na + g), n2.x, n2.y);
         // append-only trick log (4 B per game, coalesced) instead of a scattered read-modify-write of the winner's pile;
         // the trick index is the uniform hint.  (A game that refused an illegal card gets a 0 entry nobody reads.)
-        u32* row = e.tricklog + ((u32)hint >> 2) * na + g;
+        u32* row = e.tricklog + (u64)((u32)hint >> 2) * na + g;   // 12 rows of n_alloc <= 2^29 entries: 64-bit index
         if (a0 && a1) *reinterpret_cast<uint2*>(row) = make_uint2(l0, l1);
         else if (a0) row[0] = l0;
         else row[1] = l1;
