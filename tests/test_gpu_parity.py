@@ -441,6 +441,26 @@ def test_config5_size_properties():
     env.close()
 
 
+def test_near_maximum_batch_uses_64_bit_indices():
+    """400 M concurrent deals (61 GB of state; the handle takes up to 2^29): row offsets into the 12-row trick log and the
+    48-row history exceed 2^32 there.  Stepwise (trick log -> k_score) and fused (registers) must still agree."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90 << 30:
+        pytest.skip("needs 90 GB of free device memory")
+    n = 400_000_000
+    env = _env(n, seed=7)
+    env.set_materialise(False)
+    env.rollout(17, first_game_id=0, fused=False)
+    a = env.stats().copy()
+    env.reset_stats()
+    env.rollout(17, first_game_id=0, fused=True)
+    b = env.stats().copy()
+    env.close()
+    assert (a[:21] == b[:21]).all()
+    assert a[18] + a[20] == n and a[20] < n // 10000
+
+
 @pytest.mark.parametrize("mode", [0, 7, 9, 16, 17, 18])
 def test_scores_only_path_matches_oracle(oracle, mode):
     """tarok_score without pile materialisation (TAROK_OPT_MATERIALISE = 0): same scores and statistics."""
