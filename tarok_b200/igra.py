@@ -28,7 +28,7 @@ import torch
 
 from . import env as E
 from .igralec import Igralec
-from .karte import Barva, Karta, Roka, Tip_igre, karte_iz_maske, maska_iz_kart
+from .karte import Barva, Karta, Roka, Tip_igre, maska_iz_kart
 
 #: Deal-injection hook with the reference's semantics: when set to a callable it is applied to
 #: ``list(range(54))`` exactly like ``random.shuffle`` at Igra.py:66-67 and the result is dealt

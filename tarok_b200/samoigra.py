@@ -18,7 +18,6 @@ from __future__ import annotations
 import os
 from typing import Dict, Optional
 
-import numpy as np
 import torch
 
 from . import env as E

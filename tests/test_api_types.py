@@ -1,10 +1,9 @@
 """CPU: the reference-API value types and host logic (tarok_b200.karte / igralec / Partije.licitiraj)
 against vectors frozen from the real reference (tests/golden/units.npz, auction_*.npz)."""
-import numpy as np
 import pytest
 
 from tarok_b200 import Barva, Bot_igralec, Igralec, Karta, Roka, Tip_igre
-from tarok_b200.karte import karte_iz_maske, maska_iz_kart
+from tarok_b200.karte import maska_iz_kart
 
 
 def test_karta_tables(golden):
