@@ -380,6 +380,12 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": r["steps_per_s"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
                "sample": "%d deals of the same workload (%.1f s, OpenMP over %d threads)" % (r["deals"], r["seconds"], r["cores"]),
                "deals_per_sec": r["deals_per_s"], "single_core_value": r["single_core_steps_per_s"]}
+        try:    # the Python reference itself, timed where it exists (build container; static file, not measured here)
+            rj = json.load(open(os.path.join(ROOT, "profiles", "r01", "reference_cpu_container.json")))
+            cpu["python_reference_in_build_container"] = [
+                {k: x[k] for k in ("workload", "processes", "deals", "deals_per_sec", "env_steps_per_sec")} for x in rj["results"]]
+        except Exception:
+            pass
 
     if rank == 0:
         out = {
