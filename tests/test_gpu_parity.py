@@ -289,6 +289,31 @@ def test_illegal_action_sets_error_bit_and_stops_the_game():
     assert (m["phase"][bad] == 3).all() and (m["phase"][~bad] == 2).all()
     assert env.stats()[21] == bad.sum()
     assert (u64(env.hands[0, :n])[bad] == hands0[bad]).all()      # state untouched
+    # the survivors play on; at the trick-closing position (the launch that re-seats the hand slots) some of them send a
+    # card they do not hold and some an id that is no card at all
+    def lowest_legal():
+        mk = u64(env.mask[:n])
+        return np.array([max(int(x & -x).bit_length() - 1, 0) for x in mk.astype(object)], np.uint8)
+    env.step(lowest_legal())
+    env.step(lowest_legal())
+    cards = lowest_legal()
+    before = u64(env.hands[:, :n]).copy()
+    live = ~bad
+    bad2 = live & (np.arange(n) % 5 == 0)
+    bad3 = live & ~bad2 & (np.arange(n) % 11 == 0)
+    mover = (_meta(env)["leader"] + _meta(env)["pos"]) & 3
+    for i in np.nonzero(bad2)[0]:
+        cards[i] = next(c for c in range(54) if not (int(before[mover[i], i]) >> c) & 1)
+    cards[bad3] = 200
+    env.step(cards)
+    m = _meta(env)
+    assert (m["err"] == (bad | bad2 | bad3)).all()
+    assert (m["tricks"][live & ~bad2 & ~bad3] == 1).all() and (m["tricks"][bad2 | bad3] == 0).all()
+    after = u64(env.hands[:, :n])
+    assert (after[:, bad2 | bad3] == before[:, bad2 | bad3]).all()          # refused: nothing moved, nothing re-seated
+    assert env.stats()[21] == bad.sum() + bad2.sum() + bad3.sum()
+    ok = live & ~bad2 & ~bad3
+    assert ((np.bitwise_count(before[:, ok]).sum(axis=0) - np.bitwise_count(after[:, ok]).sum(axis=0)) == 1).all()
     env.close()
 
 
