@@ -551,6 +551,33 @@ def test_hand_slots_follow_the_trick_leader(lock):
     env.close()
 
 
+def test_pipeline_is_cuda_graph_capturable():
+    """Every entry point only enqueues stream-ordered work (incl. the programmatic-dependent-launch chain of play_steps), so a
+    caller can capture deal -> 48 steps -> score into a CUDA graph and replay it."""
+    import torch
+    n = 30000
+    env = _env(n, seed=5)
+    env.rollout(16, first_game_id=0)
+    ref, sc_ref = env.stats().copy(), env.scores[:n].clone()
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        env.reset_stats(); env.rollout(16, first_game_id=0)          # warm-up on the capture stream
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            env.reset_stats()
+            env.setup_synth(16, 0)
+            env.step_random(48)
+            env.score()
+    for _ in range(2):
+        env.scores.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert (env.stats()[:21] == ref[:21]).all() and bool((env.scores[:n] == sc_ref).all())
+    del sc_ref, g
+    env.close()
+
+
 def test_error_paths_are_loud():
     """Bad arguments and bad inputs come back as error codes / error bits with a message, never silently."""
     import torch
