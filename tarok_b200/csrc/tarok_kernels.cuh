@@ -149,12 +149,13 @@ enum : u32 { ST_DEAL_RETRY = 7 };
 // The pile walk keeps CUMULATIVE state: T_j = free slots in piles 0..j.  A draw r picks pile s = min{j : r < T_j}, i.e.
 // q_j = (r < T_j) holds exactly for j >= s, and the update is T_j -= q_j.  The four T_j (<= 54) live in the four bytes of
 // ONE register with bit 7 of every byte set, so that a single subtraction compares all four at once (bit 7 of byte j of
-// T - (r + 1) * 0x01010101 survives iff r < T_j; no borrow can cross a byte); the four q_j of the eight cards of a Philox
+// T - (r + 1) * 0x01010101 survives iff r < T_j; no borrow can cross a byte: every byte stays >= 0x80 - 54); the four q_j of the eight cards of a Philox
 // block are shifted into one accumulator (byte j = the block's eight q_j bits) and transposed into the cumulative
 // bitboards H_j = cards in piles 0..j with byte permutes once per block group: 6 integer instructions per card after the
 // draw.  The hands are H_0, H_1^H_0, H_2^H_1, H_3^H_2 and the talon ALL54 ^ H_3.
 __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
-    u32 T = 0x80808080u | 12u | (24u << 8) | (36u << 16) | (48u << 24);
+    // T holds T_j - 1 (+ 0x80) per byte, so that the comparison is ONE multiply-add: T - r * 0x01010101 = T + r * 0xFEFEFEFF
+    u32 T = (0x80808080u | 12u | (24u << 8) | (36u << 16) | (48u << 24)) - 0x01010101u;
     u32 rev[7];
     u32 L = 0;
 #pragma unroll
@@ -171,7 +172,7 @@ __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
                 const u32 m = x * n;
                 u32 r = m >> 16;
                 if (__builtin_expect((m & 0xFFFFu) < (65536u % n), 0)) r = draw_loop(rng.seed, gid, ST_DEAL_RETRY, (u32)c, n, 0u);
-                const u32 q = ((T - (r * 0x01010101u + 0x01010101u)) >> 7) & 0x01010101u;   // byte j = (r < T_j)
+                const u32 q = ((r * 0xFEFEFEFFu + T) >> 7) & 0x01010101u;                  // byte j = (r < T_j)
                 T -= q;
                 acc = acc * 2u + q;
             } else {
