@@ -48,6 +48,30 @@ def klop(n, seed):
     return n, 48 * n, time.perf_counter() - t0
 
 
+def nevronski(n, seed):
+    """n deals through Tarok.paralel_start with four of the reference's own Nevronski_igralec (BASELINE config 4's path) on
+    the restated networks (tarok_b200/compat/torch_models.py fills the module missing upstream); CPU forward passes."""
+    import importlib.util
+    import tempfile
+    import numpy as np
+    import torch
+    from oracle import ref_harness as H
+    spec = importlib.util.spec_from_file_location("torch_models", os.path.join(ROOT, "tarok_b200", "compat", "torch_models.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules["torch_models"] = mod
+    ref = H.load_reference()
+    random.seed(seed); np.random.seed(seed & 0x7FFFFFFF); torch.manual_seed(seed)
+    os.chdir(tempfile.mkdtemp())                      # the player creates its save directory relative to the cwd
+    players = [ref.Igralec.Nevronski_igralec() for _ in range(4)]
+    t = ref.Tarok.Tarok(players, n)
+    t.izpis = False
+    t0 = time.perf_counter()
+    t.paralel_start()
+    dt = time.perf_counter() - t0
+    return n, 48 * n, dt                              # upper bound: Berac games stop early (a few per cent of the deals)
+
+
 def _run(args):
     fn, n, seed = args
     with open(os.devnull, "w") as devnull:            # the reference prints progress lines
@@ -63,10 +87,13 @@ def main():
     per = int(sys.argv[1]) if len(sys.argv) > 1 else 1250
     workers = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 1)
     out = {"host": "build container", "cpu_count": os.cpu_count(), "python": sys.version.split()[0], "results": []}
-    for fn in ("klop", "paralel_start"):
-        for p in (1, workers):
+    for fn in ("klop", "paralel_start", "nevronski"):
+        for p in ((1,) if fn == "nevronski" else (1, workers)):
             t0 = time.perf_counter()
-            if p == 1:
+            if fn == "nevronski":                      # own process: Igralec must be imported with the real network module
+                with mp.get_context("spawn").Pool(1) as pool:
+                    res = pool.map(_run, [(fn, max(8, per // 8), 1)])
+            elif p == 1:
                 res = [_run((fn, per, 1))]
             else:
                 with mp.Pool(p) as pool:
