@@ -432,11 +432,12 @@ class Tarok:
 
     def _na_napravi(self, st_iger, rotacija):
         """Fast path: four Bot_igralec -> deal, Bot bidding, exchange, 48 random plays and scoring entirely
-        in the kernels; only the 32-entry statistics vector comes back."""
+        on the device (the fused rollout kernel: bit-identical to the 50-launch stepwise pipeline, one launch); only the
+        32-entry statistics vector comes back."""
         seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
         env = E.TarokEnv(st_iger, seed=seed, device=self.device)
         env.set_materialise(False)                       # only the result sums are needed (Tarok.py:59-61)
-        env.rollout(E.MODE_AUCTION_BOT, first_game_id=0, fused=False)
+        env.rollout(E.MODE_AUCTION_BOT, first_game_id=0, fused=True)
         st = env.stats()
         self.statistika = st
         vsote = st[E.S_PLAYER:E.S_PLAYER + 4] if rotacija else st[E.S_SEAT:E.S_SEAT + 4]
