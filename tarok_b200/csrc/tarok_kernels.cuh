@@ -912,27 +912,28 @@ __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64
 // registers (one lane = one game).  Same device functions, same Philox draws, hence bit-identical to
 // the stepwise pipeline.  Not HBM-bound: 8 B/deal written.
 // ------------------------------------------------------------------------------------------------
-struct FusedGame { u64 h0, h1, h2, h3, p0, p1, p2, p3, talon, order, meta; };
+struct FusedGame { u64 h0, h1, h2, h3, p0, p1, p2, p3, talon, order, meta; };   // h0..h3: hand SLOTS (leader-relative)
 
-// One card play of the fused rollout at trick position J (compile-time: the loop over a trick is unrolled).
+// One card play of the fused rollout at trick position J (compile-time: the loop over a trick is unrolled).  The hands are
+// kept in leader-relative slots here too: the mover is register hJ, no select chain and no conditional write-back; the four
+// registers are re-seated from the winner when the trick closes.
 template <int J>
 __device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, const Rng& rng, u64 gid, u32 trick, bool klop,
                                            uint8_t* hist_row, u64 na, u32* log_row = nullptr) {
-    const u32 mover = (((u32)f.meta >> M_LEADER) + (u32)J) & 3u;
-    u64 hand = sel4(f.h0, f.h1, f.h2, f.h3, mover);
+    u64& hand = J == 0 ? f.h0 : J == 1 ? f.h1 : J == 2 ? f.h2 : f.h3;
     const u64 legal = legal_moves(hand, J != 0, (u32)(f.meta >> 32) & 63u, klop);
     const u32 n = (u32)__popcll(legal);
     const u32 card = nth_set_bit(legal, play_draw<J>(blk, rng, gid, trick * 4 + J, n));
+    if (hist_row) hist_row[(u64)J * na] = (uint8_t)((((((u32)f.meta >> M_LEADER) + (u32)J) & 3u) << 6) | card);
     PlayResult pr;
     f.meta = play_card<false, J>(f.meta, hand, card, f.talon, f.order, pr);
-    if (hist_row) hist_row[(u64)J * na] = (uint8_t)((mover << 6) | card);
-    f.h0 = mover == 0 ? hand : f.h0; f.h1 = mover == 1 ? hand : f.h1; f.h2 = mover == 2 ? hand : f.h2; f.h3 = mover == 3 ? hand : f.h3;
     if (J == 3) {
         if (log_row) *log_row = ((u32)(f.meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
         const u64 b = pr.pile_bits;
         f.p0 |= pr.winner == 0 ? b : 0ull; f.p1 |= pr.winner == 1 ? b : 0ull;
         f.p2 |= pr.winner == 2 ? b : 0ull; f.p3 |= pr.winner == 3 ? b : 0ull;
         f.talon &= ~pr.talon_clear;
+        rotate4(f.h0, f.h1, f.h2, f.h3, pr.winner_rel);
     }
 }
 
@@ -992,6 +993,7 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         }
         const u32 contract = mget(meta, M_CONTRACT, 4);
         const bool klop = klop_rules(contract);
+        seats_to_slots(h0, h1, h2, h3, leader_of(meta));
         FusedGame fg{h0, h1, h2, h3, p0, p1, p2, p3, talon, order, meta};
         for (u32 trick = 0; trick < 12 && mget(fg.meta, M_PHASE, 2) == PH_PLAY; trick++) {
             Words4 blk = play_block(e.rng, gid, trick);                // 4 plays = half of one Philox block
@@ -1007,8 +1009,7 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         if (!err && mget(meta, M_PHASE, 2) == PH_DONE) packed = score_game(meta, p0, p1, p2, p3, talon);
         if (out) out[g] = packed;
     }
-    if (write_state && g < na) {
-        seats_to_slots(h0, h1, h2, h3, leader_of(meta));
+    if (write_state && g < na) {                         // h0..h3 are slots already (identity for a game that never started)
         e.hands[g] = h0; e.hands[na + g] = h1; e.hands[2 * na + g] = h2; e.hands[3 * na + g] = h3;
         e.piles[g] = p0; e.piles[na + g] = p1; e.piles[2 * na + g] = p2; e.piles[3 * na + g] = p3;
         e.talon[g] = talon; e.torder[g] = order; e.meta[g] = meta; e.mask[g] = 0;
