@@ -9,7 +9,10 @@
  *
  *   word(gid, stream, idx)  = philox4x32_10(key = seed, ctr = {gid.lo, gid.hi, stream | attempt<<16, idx>>2})[idx&3]
  *   draw(gid, stream, idx, n) = Lemire multiply-shift with rejection on word(...) -> uniform in [0,n)
- *   streams: 0 deal, 1 bids, 2 king, 3 exchange, 4 play, 5 forced contract/declarer, 6 play retry
+ *   batched draws: k exact draws with bounds n_1..n_k from ONE word x: r_i = hi32(x * n_i), x = lo32(x * n_i); the tuple is
+ *     accepted iff the final x >= 2^32 mod (n_1 * ... * n_k) (Lemire's method for the product bound, read digit by digit),
+ *     else the word is redrawn with attempt = 1, 2, ...
+ *   streams: 0 deal, 1 bids, 4 play, 5 setup (forced contract / declarer / king, exchange), 6 play retry, 7 deal retry
  *   play draws (n <= 12) use 16-bit lanes: one Philox block per (game pair = gid>>1, trick) holds eight
  *   16-bit values, lane = (gid&1)*4 + play-in-trick; 16-bit Lemire, rejected sliver -> 32-bit draw on stream 6
  *
@@ -23,6 +26,9 @@
 #define PH_M1 0xCD9E8D57u
 #define PH_W0 0x9E3779B9u
 #define PH_W1 0xBB67AE85u
+
+enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5, ST_PLAY_RETRY = 6, ST_DEAL_RETRY = 7 };
+enum { MODE_NAVADNA_MIX = 16, MODE_AUCTION_UNIFORM = 17, MODE_AUCTION_BOT = 18 };
 
 void syn_philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
     for (int r = 0; r < 10; r++) {
@@ -49,31 +55,48 @@ uint32_t syn_draw(uint64_t seed, uint64_t gid, uint32_t stream, uint32_t idx, ui
     }
 }
 
-enum { ST_DEAL = 0, ST_BID = 1, ST_KING = 2, ST_EXCH = 3, ST_PLAY = 4, ST_FORCE = 5, ST_PLAY_RETRY = 6, ST_DEAL_RETRY = 7 };
-enum { MODE_NAVADNA_MIX = 16, MODE_AUCTION_UNIFORM = 17, MODE_AUCTION_BOT = 18 };
+
+static uint32_t bdraw(uint32_t* x, uint32_t n) {
+    uint64_t m = (uint64_t)(*x) * n;
+    *x = (uint32_t)m;
+    return (uint32_t)(m >> 32);
+}
+
+/* k batched draws from word `word` of (gid, stream): attempt 0 reads the stream's own block, a rejected word is redrawn
+   from (retry_stream | attempt << 16) with attempt = 1, 2, ... */
+static void syn_bdraws(uint64_t seed, uint64_t gid, uint32_t stream, uint32_t retry_stream, uint32_t word,
+                       const uint32_t* n, int k, uint32_t* r) {
+    for (uint32_t attempt = 0;; attempt++) {
+        uint32_t c[4] = { (uint32_t)gid, (uint32_t)(gid >> 32), attempt ? (retry_stream | (attempt << 16)) : stream, word >> 2 };
+        syn_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint32_t x = c[word & 3], prod = 1;
+        for (int i = 0; i < k; i++) { r[i] = bdraw(&x, n[i]); prod *= n[i]; }
+        if (x >= (uint32_t)((1ull << 32) % prod)) return;
+    }
+}
 
 /* Uniform deal: card c = 0..53 goes to a uniformly random free slot among the 54-c left; slots
    are exchangeable inside a pile, so this is a walk over the remaining capacities of the piles
-   (seat 0..3: 12 each, then the talon: 6); the 54 draws use 16-bit lanes of Philox blocks 0..6 (16-bit
-   Lemire, rejected sliver -> 32-bit draw on stream 7).  The ORDER of the six talon cards (it matters:
-   Navadna_igra.py:44, Klop.py:69) is a uniform permutation decoded from word 27 (32-bit Lemire,
-   n = 720, Lehmer code over the talon ids in ascending order).  Exported as the permutation
-   Igra.razdeli would have consumed: seat slices ascending by id, then the ordered talon. */
+   (seat 0..3: 12 each, then the talon: 6).  The 53 draws are batched: words 0..5 of the deal stream carry
+   three cards each (cards 0..17), words 6..13 four each (cards 18..49), word 14 cards 50..52; card 53 takes the
+   last slot.  The ORDER of the six talon cards (it matters: Navadna_igra.py:44, Klop.py:69) is a uniform
+   permutation decoded from word 15 (32-bit Lemire, n = 720, Lehmer code over the talon ids in ascending order).
+   Exported as the permutation Igra.razdeli would have consumed: seat slices ascending by id, then the ordered talon. */
 void syn_deal(uint64_t seed, uint64_t gid, uint8_t perm[54]) {
     int cap[4] = { 12, 12, 12, 12 }, fill[4] = { 0, 0, 0, 0 };
     uint8_t tal[6];
     int nt = 0;
-    uint32_t w[28];
-    for (uint32_t b = 0; b < 7; b++) {          /* 28 words = 56 sixteen-bit lanes */
-        uint32_t c[4] = { (uint32_t)gid, (uint32_t)(gid >> 32), ST_DEAL, b };
-        syn_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        memcpy(w + 4 * b, c, sizeof(c));
+    uint32_t draws[54];
+    for (int w = 0; w < 15; w++) {
+        int c0 = w < 6 ? 3 * w : w < 14 ? 18 + 4 * (w - 6) : 50;
+        int nc = (w < 6 || w == 14) ? 3 : 4;
+        uint32_t n[4];
+        for (int i = 0; i < nc; i++) n[i] = (uint32_t)(54 - (c0 + i));
+        syn_bdraws(seed, gid, ST_DEAL, ST_DEAL_RETRY, (uint32_t)w, n, nc, draws + c0);
     }
+    draws[53] = 0;
     for (int c = 0; c < 54; c++) {
-        uint32_t n = (uint32_t)(54 - c);
-        uint32_t x = (w[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-        uint32_t m = x * n, r = m >> 16;
-        if ((m & 0xFFFFu) < (65536u % n)) r = syn_draw(seed, gid, ST_DEAL_RETRY, (uint32_t)c, n);
+        uint32_t r = draws[c];
         int s;
         for (s = 0; s < 4; s++) {
             if (r < (uint32_t)cap[s]) break;
@@ -82,7 +105,9 @@ void syn_deal(uint64_t seed, uint64_t gid, uint8_t perm[54]) {
         if (s < 4) { perm[12 * s + fill[s]++] = (uint8_t)c; cap[s]--; }
         else tal[nt++] = (uint8_t)c;
     }
-    uint64_t mm = (uint64_t)w[27] * 720u;
+    uint32_t cw[4] = { (uint32_t)gid, (uint32_t)(gid >> 32), ST_DEAL, 3 };
+    syn_philox4x32_10(cw, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint64_t mm = (uint64_t)cw[3] * 720u;
     uint32_t L = (uint32_t)(mm >> 32);
     if ((uint32_t)mm < 256u) L = syn_draw(seed, gid, ST_DEAL_RETRY, 54, 720);     /* 2^32 % 720 = 256 */
     static const uint32_t fact[6] = { 120, 24, 6, 2, 1, 1 };
@@ -105,12 +130,13 @@ static void index2igra(int idx, int* tip, int* suit) {
            *tip = t[idx - 13]; *suit = ORC_NO_KING; }
 }
 
-typedef struct { uint64_t seed, gid; int tip[4]; } bid_ctx;
+typedef struct { uint64_t seed, gid; int tip[4]; uint32_t digit[16]; } bid_ctx;
 static int want_uniform(void* p, int seat, int call) { (void)call; return ((bid_ctx*)p)->tip[seat]; }
 static int want_bot(void* p, int seat, int call) {
     (void)seat;
     bid_ctx* b = (bid_ctx*)p;     /* np.random.choice([Naprej,Tri,Dve,Ena], p=[.5,1/6,1/6,1/6]), Igralec.py:151 */
-    uint32_t u = syn_draw(b->seed, b->gid, ST_BID, (uint32_t)call, 6);
+    /* call i takes the i-th base-6 digit of words 0 and 1 of the bid block (eight batched draws each) */
+    uint32_t u = call < 16 ? b->digit[call] : syn_draw(b->seed, b->gid, ST_BID, (uint32_t)(64 + call), 6);
     return u < 3 ? ORC_NAPREJ : (int)(ORC_TRI + (u - 3));
 }
 
@@ -139,23 +165,34 @@ int syn_rollout(uint64_t seed, uint64_t gid, int mode, orc_game* g, uint8_t perm
     if (mode == MODE_AUCTION_UNIFORM || mode == MODE_AUCTION_BOT) {
         bid_ctx b; b.seed = seed; b.gid = gid;
         int suit[4];
-        if (mode == MODE_AUCTION_UNIFORM)
-            for (int s = 0; s < 4; s++) index2igra((int)syn_draw(seed, gid, ST_BID, (uint32_t)s, 18), &b.tip[s], &suit[s]);
+        if (mode == MODE_AUCTION_UNIFORM) {
+            static const uint32_t n18[4] = { 18, 18, 18, 18 };
+            uint32_t idx[4];
+            syn_bdraws(seed, gid, ST_BID, ST_BID, 0, n18, 4, idx);
+            for (int s = 0; s < 4; s++) index2igra((int)idx[s], &b.tip[s], &suit[s]);
+        } else {
+            static const uint32_t n6[8] = { 6, 6, 6, 6, 6, 6, 6, 6 };
+            syn_bdraws(seed, gid, ST_BID, ST_BID, 0, n6, 8, b.digit);
+            syn_bdraws(seed, gid, ST_BID, ST_BID, 1, n6, 8, b.digit + 8);
+        }
         orc_licitacija(mode == MODE_AUCTION_UNIFORM ? want_uniform : want_bot, &b,
                        mode == MODE_AUCTION_UNIFORM, &declarer, &contract, 0);
         if (contract >= ORC_TRI && contract <= ORC_ENA)
-            king = mode == MODE_AUCTION_UNIFORM ? suit[declarer] : (int)syn_draw(seed, gid, ST_KING, 0, 4);
+            king = mode == MODE_AUCTION_UNIFORM ? suit[declarer] : (int)syn_draw(seed, gid, ST_FORCE, 2, 4);
     } else {
-        contract = mode == MODE_NAVADNA_MIX ? (int)(ORC_TRI + syn_draw(seed, gid, ST_FORCE, 0, 3)) : mode;
-        if (contract != ORC_KLOP) declarer = (int)syn_draw(seed, gid, ST_FORCE, 1, 4);
-        if (contract >= ORC_TRI && contract <= ORC_ENA) king = (int)syn_draw(seed, gid, ST_KING, 0, 4);
+        static const uint32_t n344[3] = { 3, 4, 4 };      /* word 0 of the setup block: contract of the mix, declarer, king */
+        uint32_t r[3];
+        syn_bdraws(seed, gid, ST_FORCE, ST_FORCE, 0, n344, 3, r);
+        contract = mode == MODE_NAVADNA_MIX ? (int)(ORC_TRI + r[0]) : mode;
+        if (contract != ORC_KLOP) declarer = (int)r[1];
+        if (contract >= ORC_TRI && contract <= ORC_ENA) king = (int)r[2];
     }
     orc_zacni_igro(g, contract, declarer, king);
     *group_out = ORC_NO_GROUP; *discard_out = 0;
     memset(cards, 0xFF, 48);
     if (g->phase == 1) {
         int k = orc_talon_k(contract);
-        int grp = mode == MODE_AUCTION_UNIFORM ? (int)syn_draw(seed, gid, ST_EXCH, 0, g->group_cnt) : 0;
+        int grp = mode == MODE_AUCTION_UNIFORM ? (int)syn_draw(seed, gid, ST_FORCE, 3, g->group_cnt) : 0;
         /* discardable set after the pick-up: Roka.mozno_zalozit on hand + group (Igralec.py:163-166) */
         uint64_t avail = 0;
         orc_game tmp = *g;
@@ -170,9 +207,11 @@ int syn_rollout(uint64_t seed, uint64_t gid, int mode, orc_game* g, uint8_t perm
         uint8_t d[3];
         uint64_t dm = 0;
         if (nm < k) { g->error = 1; return -1; }
+        uint32_t nb[3], rd[3];                           /* word 1 of the setup block: the k discards, batched */
+        for (int j = 0; j < k; j++) nb[j] = (uint32_t)(nm - j);
+        syn_bdraws(seed, gid, ST_FORCE, ST_FORCE, 1, nb, k, rd);
         for (int j = 0; j < k; j++) {
-            uint32_t r = syn_draw(seed, gid, ST_EXCH, (uint32_t)(1 + j), (uint32_t)__builtin_popcountll(avail));
-            int c = nth_lowest(avail, r);
+            int c = nth_lowest(avail, rd[j]);
             d[j] = (uint8_t)c; avail &= ~(1ull << c); dm |= 1ull << c;
         }
         *group_out = (uint8_t)grp; *discard_out = dm;

@@ -98,6 +98,40 @@ __device__ __forceinline__ u32 draw(const Rng& rng, u64 gid, u32 stream, u32 idx
     return draw_from_word(x, rng, gid, stream, idx, n);
 }
 
+// ---- batched bounded draws -------------------------------------------------------------------------
+// Several exact draws from ONE 32-bit word (Brackett-Rozinsky & Lemire, "Batched ranged random integer generation"):
+//   r_1 = hi32(x * n_1), x <- lo32(x * n_1);  r_2 = hi32(x * n_2), x <- lo32(x * n_2); ...
+// By induction floor(x0 * B / 2^32) = the mixed-radix number (r_1, ..., r_k) with B = n_1 * ... * n_k and the final x is
+// (x0 * B) mod 2^32, so this is Lemire's multiply-shift for the bound B read digit by digit: the tuple is exactly uniform
+// iff the final x >= 2^32 mod B.  A rejected word (probability < B / 2^32) is redrawn whole on the retry stream with
+// attempt = 1, 2, ...  Two multiplies per draw, both on the FMA pipe, and one compare per word.
+__device__ __forceinline__ u32 bdraw(u32& x, u32 n) { const u32 r = __umulhi(x, n); x *= n; return r; }
+
+// Cold path: redraw word `word` of (gid, stream) until accepted; bounds8 = the k <= 8 bounds, 8 bits each (each <= 63);
+// returns the k results, 6 bits each.
+__device__ __noinline__ u64 bdraw_retry(u64 seed, u64 gid, u32 stream, u32 word, u64 bounds8, u32 k) {
+    for (u32 attempt = 1;; attempt++) {
+        u32 c0 = (u32)gid, c1 = (u32)(gid >> 32), c2 = stream | (attempt << 16), c3 = word >> 2;
+        u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+        for (int r = 0; r < 10; r++) {
+            const u32 hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+            const u32 hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+            c0 = hi1 ^ c1 ^ k0; c2 = hi0 ^ c3 ^ k1; c1 = lo1; c3 = lo0;
+            k0 += PHILOX_W0; k1 += PHILOX_W1;
+        }
+        const u32 j = word & 3u;
+        u32 x = j == 0 ? c0 : j == 1 ? c1 : j == 2 ? c2 : c3;
+        u64 out = 0;
+        u32 prod = 1;
+        for (u32 i = 0; i < k; i++) {
+            const u32 n = (u32)(bounds8 >> (8u * i)) & 0xFFu;
+            out |= (u64)bdraw(x, n) << (6u * i);
+            prod *= n;
+        }
+        if (x >= (0u - prod) % prod) return out;
+    }
+}
+
 // ---- play draws -------------------------------------------------------------------------------------
 // A legal mask holds at most 12 cards, so a play needs far fewer than 32 random bits.  One Philox block is
 // shared by TWO consecutive games (pair = gid >> 1) and the FOUR plays of one trick: eight 16-bit lanes,

@@ -31,6 +31,7 @@ struct tarok_env {
     tk::Env e;
     // staging buffers of the host-buffer entry point
     uint8_t* st_perm; uint8_t* st_contract; uint8_t* st_declarer; uint8_t* st_king;
+    int staging_ready;                         // set only after every stream / event / buffer below exists
     cudaStream_t s_up, s_down;                 // internal copy streams of the chunked host pipeline
     cudaEvent_t ev_fork, ev_join, ev_up[TK_MAX_CHUNKS], ev_done[TK_MAX_CHUNKS];
     std::atomic<int> exports;
@@ -63,6 +64,23 @@ static int fail(tarok_env* h, int code, const char* fmt, ...) {
         if (_e != cudaSuccess) return fail(h, -3, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
         (h)->launches++;                                                                          \
     } while (0)
+
+// Staging resources of the host-buffer entries: every member is null until created, so a partial set can be torn down.
+static void free_staging(tarok_env* h) {
+    if (h->s_up) cudaStreamDestroy(h->s_up);
+    if (h->s_down) cudaStreamDestroy(h->s_down);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (int c = 0; c < TK_MAX_CHUNKS; c++) {
+        if (h->ev_up[c]) cudaEventDestroy(h->ev_up[c]);
+        if (h->ev_done[c]) cudaEventDestroy(h->ev_done[c]);
+    }
+    cudaFree(h->st_perm); cudaFree(h->st_contract); cudaFree(h->st_declarer); cudaFree(h->st_king);
+    h->s_up = h->s_down = nullptr; h->ev_fork = h->ev_join = nullptr;
+    memset(h->ev_up, 0, sizeof(h->ev_up)); memset(h->ev_done, 0, sizeof(h->ev_done));
+    h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
+    h->staging_ready = 0;
+}
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline unsigned grid1(u64 n_alloc) { return (unsigned)(n_alloc / tk::CTA); }        // one game per lane
@@ -141,6 +159,8 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     memset(&h->e, 0, sizeof(h->e));
     h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->materialise = 1; h->chunks = 8; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
+    h->s_up = h->s_down = nullptr; h->ev_fork = h->ev_join = nullptr; h->staging_ready = 0;
+    memset(h->ev_up, 0, sizeof(h->ev_up)); memset(h->ev_done, 0, sizeof(h->ev_done));
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;
     tk::philox_keys_init(h->e.rng, seed);
@@ -163,6 +183,8 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     TK_ALLOC(h->e.stats, TAROK_STATS_LEN * 8);
     TK_ALLOC(h->e.tricklog, 12 * na * 4);
     cudaMemset(h->e.tricklog, 0, 12 * na * 4);
+    TK_ALLOC(h->e.dpts, na);
+    cudaMemset(h->e.dpts, 0, na);
     if (flags & TAROK_FLAG_HISTORY) {
         TK_ALLOC(h->e.hist, 48 * na);
         TK_ALLOC(h->e.hands0, 4 * na * 8);
@@ -196,13 +218,8 @@ int tarok_destroy(tarok_t* h) {
     DeviceGuard dg(h->device);
     cudaFree(h->e.hands); cudaFree(h->e.piles); cudaFree(h->e.talon); cudaFree(h->e.torder);
     cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats); cudaFree(h->e.tricklog);
-    cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist);
-    if (h->st_perm) {
-        cudaStreamDestroy(h->s_up); cudaStreamDestroy(h->s_down);
-        cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
-        for (int c = 0; c < TK_MAX_CHUNKS; c++) { cudaEventDestroy(h->ev_up[c]); cudaEventDestroy(h->ev_done[c]); }
-    }
-    cudaFree(h->st_perm); cudaFree(h->st_contract); cudaFree(h->st_declarer); cudaFree(h->st_king);
+    cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist); cudaFree(h->e.dpts);
+    free_staging(h);
     delete h;
     return 0;
 }
@@ -468,9 +485,9 @@ int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id
     return 0;
 }
 
-// Lazily created: the copy streams, events and device staging buffers of the host-buffer entries.
-static int ensure_staging(tarok_t* h) {
-    if (h->st_perm) return 0;
+// Lazily created: the copy streams, events and device staging buffers of the host-buffer entries.  The handle is marked
+// ready only once everything exists; a failure half-way frees what was created, so the next call starts from scratch.
+static int create_staging(tarok_t* h) {
     TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
     TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
     TK_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -483,6 +500,13 @@ static int ensure_staging(tarok_t* h) {
     TK_CUDA(h, cudaMalloc((void**)&h->st_contract, h->e.n_alloc));
     TK_CUDA(h, cudaMalloc((void**)&h->st_declarer, h->e.n_alloc));
     TK_CUDA(h, cudaMalloc((void**)&h->st_king, h->e.n_alloc));
+    return 0;
+}
+static int ensure_staging(tarok_t* h) {
+    if (h->staging_ready) return 0;
+    const int rc = create_staging(h);
+    if (rc) { free_staging(h); return rc; }
+    h->staging_ready = 1;
     return 0;
 }
 

@@ -4,7 +4,7 @@
 // the 512-game CTA tile, every array 256-byte aligned):
 //   hands[4][n_alloc] (leader-relative slots, see "hand slots" below; everything else is indexed by seat)
 //   piles[4][n_alloc]  talon[n_alloc]  torder[n_alloc]  meta[n_alloc]
-//   mask[n_alloc]  scores[n_alloc] (int16 x4)  tricklog[12][n_alloc] (uint32)
+//   mask[n_alloc]  scores[n_alloc] (int16 x4)  tricklog[12][n_alloc] (uint32)  dpts[n_alloc] (uint8)
 //   optional (TAROK_FLAG_HISTORY): hist[48][n_alloc] (uint8)  hands0[4][n_alloc]  discard[n_alloc]  qmax_hist[48][n_alloc] (float)
 // The stepwise kernels give each lane TWO consecutive games so that every per-field access is one
 // 128-bit load/store (ld.global.v2.u64): a warp covers a 64-game tile = 512 contiguous bytes per
@@ -24,7 +24,8 @@ constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane 
 struct Env {
     u64* hands; u64* piles; u64* talon; u64* torder; u64* meta; u64* mask; u64* scores;
     uint8_t* hist; u64* hands0; u64* discard; float* qmax_hist; long long* stats;
-    u32* tricklog;                         // [12][n_alloc]: trick k of game g = 4 cards (24 bit, play order) | winner << 24
+    u32* tricklog;                         // [12][n_alloc]: trick k of game g = 4 cards (24 bit, play order) | winner << 24 | card points << 26
+    uint8_t* dpts;                         // [n_alloc]: card points of the declarer's discards (scoring reads this instead of the piles)
     u64 n, n_alloc, first_gid;
     Rng rng;                               // seed + precomputed Philox round keys
 };
@@ -139,53 +140,92 @@ __device__ __forceinline__ u64 order_from_lehmer(u64 talon, u32 L) {
     return order;
 }
 
-// 54 bounded draws with n <= 54 need few random bits: they use 16-bit lanes (half c of the 28 words of Philox
-// blocks 0..6; 16-bit Lemire, the rejected sliver -- probability < n/65536 -- redraws on stream ST_DEAL_RETRY);
-// the talon permutation uses the last full word (32-bit Lemire, n = 720).  7 Philox blocks per deal.
+// The 53 bounded draws of a deal (n = 54 - c for card c; card 53 has no choice left) are BATCHED: several exact draws
+// from one 32-bit Philox word (philox.cuh, bdraw): words 0..5 carry three cards each (cards 0..17), words 6..13 four each
+// (cards 18..49), word 14 cards 50..52, word 15 whole the talon order (32-bit Lemire, n = 720).  16 words = 4 Philox
+// blocks per deal (the 16-bit-lane version of round 1 needed 7), two multiplies per draw on the FMA pipe and one
+// rejection compare per WORD (probability of a redraw < 1e-3 per deal; redraws go to stream ST_DEAL_RETRY).
 // Card c lives in the low word of a bitboard for c < 32 and in the high word otherwise, which is known at
-// compile time in the unrolled loop: every update is one predicated 32-bit OR.
+// compile time in the unrolled loop.
 enum : u32 { ST_DEAL_RETRY = 7 };
+
+__host__ __device__ constexpr int deal_first_card(int w) { return w < 6 ? 3 * w : w < 14 ? 18 + 4 * (w - 6) : 50; }
+__host__ __device__ constexpr int deal_cards_in(int w) { return (w < 6 || w == 14) ? 3 : 4; }
+__host__ __device__ constexpr u32 deal_prod(int w) {
+    u32 p = 1;
+    for (int i = 0; i < deal_cards_in(w); i++) p *= (u32)(54 - (deal_first_card(w) + i));
+    return p;
+}
+__host__ __device__ constexpr u64 deal_bounds8(int w) {
+    u64 b = 0;
+    for (int i = 0; i < deal_cards_in(w); i++) b |= (u64)(54 - (deal_first_card(w) + i)) << (8 * i);
+    return b;
+}
 
 // The pile walk keeps CUMULATIVE state: T_j = free slots in piles 0..j.  A draw r picks pile s = min{j : r < T_j}, i.e.
 // q_j = (r < T_j) holds exactly for j >= s, and the update is T_j -= q_j.  The four T_j (<= 54) live in the four bytes of
 // ONE register with bit 7 of every byte set, so that a single subtraction compares all four at once (bit 7 of byte j of
-// T - (r + 1) * 0x01010101 survives iff r < T_j; no borrow can cross a byte: every byte stays >= 0x80 - 54); the four q_j of the eight cards of a Philox
-// block are shifted into one accumulator (byte j = the block's eight q_j bits) and transposed into the cumulative
-// bitboards H_j = cards in piles 0..j with byte permutes once per block group: 6 integer instructions per card after the
+// T - (r + 1) * 0x01010101 survives iff r < T_j; no borrow can cross a byte: every byte stays >= 0x80 - 54); the four q_j of
+// eight consecutive cards are shifted into one accumulator (byte j = their eight q_j bits) and transposed into the cumulative
+// bitboards H_j = cards in piles 0..j with byte permutes at the end: 5 integer instructions per card after the
 // draw.  The hands are H_0, H_1^H_0, H_2^H_1, H_3^H_2 and the talon ALL54 ^ H_3.
+struct DealWalk { u32 T, acc; u32 rev[7]; };
+
+__device__ __forceinline__ void deal_place(DealWalk& d, int c, u32 r) {             // c is a compile-time constant at every call
+    const u32 q = ((r * 0xFEFEFEFFu + d.T) >> 7) & 0x01010101u;                     // byte j = (r < T_j)
+    d.T -= q;
+    d.acc = d.acc * 2u + q;
+    if ((c & 7) == 7) { d.rev[c >> 3] = __brev(d.acc); d.acc = 0; }                 // byte 3 - j: bit jj = q_j of card 8 * (c >> 3) + jj
+}
+
+template <int W>
+__device__ __forceinline__ void deal_word(DealWalk& d, u32 x, const Rng& rng, u64 gid) {
+    constexpr int C0 = deal_first_card(W), NC = deal_cards_in(W);
+    constexpr u32 THRESH = (u32)((1ull << 32) % deal_prod(W));
+    u32 r[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) r[i] = bdraw(x, (u32)(54 - (C0 + i)));
+    if (__builtin_expect(x < THRESH, 0)) {
+        const u64 p = bdraw_retry(rng.seed, gid, ST_DEAL_RETRY, (u32)W, deal_bounds8(W), (u32)NC);
+#pragma unroll
+        for (int i = 0; i < NC; i++) r[i] = (u32)(p >> (6 * i)) & 63u;
+    }
+#pragma unroll
+    for (int i = 0; i < NC; i++) deal_place(d, C0 + i, r[i]);
+}
+
 __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
     // T holds T_j - 1 (+ 0x80) per byte, so that the comparison is ONE multiply-add: T - r * 0x01010101 = T + r * 0xFEFEFEFF
-    u32 T = (0x80808080u | 12u | (24u << 8) | (36u << 16) | (48u << 24)) - 0x01010101u;
-    u32 rev[7];
-    u32 L = 0;
-#pragma unroll
-    for (int blk = 0; blk < 7; blk++) {
-        Words4 b = philox_block(rng, gid, ST_DEAL, (u32)blk);
-        u32 acc = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int c = blk * 8 + j;
-            const u32 word = b.w[j >> 1];
-            if (c < 54) {
-                const u32 n = (u32)(54 - c);
-                const u32 x = (j & 1) ? (word >> 16) : (word & 0xFFFFu);
-                const u32 m = x * n;
-                u32 r = m >> 16;
-                if (__builtin_expect((m & 0xFFFFu) < (65536u % n), 0)) r = draw_loop(rng.seed, gid, ST_DEAL_RETRY, (u32)c, n, 0u);
-                const u32 q = ((r * 0xFEFEFEFFu + T) >> 7) & 0x01010101u;                  // byte j = (r < T_j)
-                T -= q;
-                acc = acc * 2u + q;
-            } else {
-                acc *= 2u;                                       // pad: keeps card j of the block at bit 7 - j
-                if (c == 55) {                                   // word 27 whole: the talon order
-                    const u64 m = (u64)word * 720u;
-                    L = (u32)(m >> 32);
-                    if (__builtin_expect((u32)m < 256u, 0)) L = draw_loop(rng.seed, gid, ST_DEAL_RETRY, 54u, 720u, 0u);   // 2^32 % 720 = 256
-                }
-            }
-        }
-        rev[blk] = __brev(acc);                                  // byte 3 - j: bit jj = q_j of card 8 * blk + jj
+    DealWalk d;
+    d.T = (0x80808080u | 12u | (24u << 8) | (36u << 16) | (48u << 24)) - 0x01010101u;
+    d.acc = 0;
+    u32 L;
+    {
+        const Words4 b = philox_block(rng, gid, ST_DEAL, 0u);
+        deal_word<0>(d, b.w[0], rng, gid); deal_word<1>(d, b.w[1], rng, gid);
+        deal_word<2>(d, b.w[2], rng, gid); deal_word<3>(d, b.w[3], rng, gid);
     }
+    {
+        const Words4 b = philox_block(rng, gid, ST_DEAL, 1u);
+        deal_word<4>(d, b.w[0], rng, gid); deal_word<5>(d, b.w[1], rng, gid);
+        deal_word<6>(d, b.w[2], rng, gid); deal_word<7>(d, b.w[3], rng, gid);
+    }
+    {
+        const Words4 b = philox_block(rng, gid, ST_DEAL, 2u);
+        deal_word<8>(d, b.w[0], rng, gid); deal_word<9>(d, b.w[1], rng, gid);
+        deal_word<10>(d, b.w[2], rng, gid); deal_word<11>(d, b.w[3], rng, gid);
+    }
+    {
+        const Words4 b = philox_block(rng, gid, ST_DEAL, 3u);
+        deal_word<12>(d, b.w[0], rng, gid); deal_word<13>(d, b.w[1], rng, gid);
+        deal_word<14>(d, b.w[2], rng, gid);
+        const u64 m = (u64)b.w[3] * 720u;                        // word 15 whole: the talon order
+        L = (u32)(m >> 32);
+        if (__builtin_expect((u32)m < 256u, 0)) L = draw_loop(rng.seed, gid, ST_DEAL_RETRY, 54u, 720u, 0u);   // 2^32 % 720 = 256
+    }
+    deal_place(d, 53, 0u);                                       // the last card takes the last free slot
+    d.rev[6] = __brev(d.acc << 2);                               // cards 48..53 sit at bits 7..2 of the last accumulator
+    const u32* rev = d.rev;
     // 4 x 4 byte transposes: H_j.lo = byte (3 - j) of rev[0..3], H_j.hi = byte (3 - j) of rev[4..6]
     u64 H[4];
 #pragma unroll
@@ -199,11 +239,11 @@ __device__ __forceinline__ Dealt deal_philox(const Rng& rng, u64 gid) {
         const u32 hi = (hi45 & 0xFFFFu) | (hi6 << 16);
         H[j] = ((u64)hi << 32) | lo;
     }
-    Dealt d;
-    d.h0 = H[0]; d.h1 = H[1] ^ H[0]; d.h2 = H[2] ^ H[1]; d.h3 = H[3] ^ H[2];
-    d.talon = ALL54 ^ H[3];
-    d.order = order_from_lehmer(d.talon, L);
-    return d;
+    Dealt dd;
+    dd.h0 = H[0]; dd.h1 = H[1] ^ H[0]; dd.h2 = H[2] ^ H[1]; dd.h3 = H[3] ^ H[2];
+    dd.talon = ALL54 ^ H[3];
+    dd.order = order_from_lehmer(dd.talon, L);
+    return dd;
 }
 
 __global__ void __launch_bounds__(CTA, 4) k_deal(Env e) {
@@ -218,6 +258,7 @@ __global__ void __launch_bounds__(CTA, 4) k_deal(Env e) {
     e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = 0;
     if (e.hands0) { e.hands0[g] = d.h0; e.hands0[na + g] = d.h1; e.hands0[2 * na + g] = d.h2; e.hands0[3 * na + g] = d.h3; }
     if (e.discard) e.discard[g] = 0;
+    e.dpts[g] = 0;
 }
 
 // Deal injection (Igra.shuffle patch, Igra.py:10,67): perm uint8 [n,54].  The CTA stages its
@@ -269,6 +310,7 @@ __global__ void __launch_bounds__(CTA) k_set_deals(Env e, const uint8_t* __restr
     e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = 0;
     if (e.hands0) { e.hands0[g] = d.h0; e.hands0[na + g] = d.h1; e.hands0[2 * na + g] = d.h2; e.hands0[3 * na + g] = d.h3; }
     if (e.discard) e.discard[g] = 0;
+    e.dpts[g] = 0;
 }
 
 // Compact deal record (24 B = three u64 words; include/tarok_b200.h "deal records"): three bit planes over the 54 card
@@ -331,15 +373,39 @@ enum : int { SRC_FORCED = 0, SRC_INTENTS = 1, SRC_SYNTH = 2 };
 
 struct WantFixed { int tip[4]; __device__ int operator()(int seat, int) const {
     return seat == 0 ? tip[0] : seat == 1 ? tip[1] : seat == 2 ? tip[2] : tip[3]; } };
-struct WantBot { const Rng& rng; u64 gid; __device__ int operator()(int, int call) const {
-    // np.random.choice([Naprej,Tri,Dve,Ena], p=[.5,1/6,1/6,1/6]) at EVERY call (Igralec.py:151)
-    u32 u = draw(rng, gid, ST_BID, (u32)call, 6u);
+// np.random.choice([Naprej,Tri,Dve,Ena], p=[.5,1/6,1/6,1/6]) at EVERY call (Igralec.py:151): call i takes the i-th of the
+// sixteen base-6 digits decoded from words 0 and 1 of the bid block (eight batched draws per word); an auction of
+// Bot players never needs more (the bids only rise Tri -> Dve -> Ena), calls past 16 would use one word each.
+struct WantBot { const Rng& rng; u64 gid; u64 digits; __device__ int operator()(int, int call) const {
+    const u32 u = call < 16 ? (u32)(digits >> (3 * call)) & 7u : draw(rng, gid, ST_BID, 64u + (u32)call, 6u);
     return u < 3u ? (int)C_NAPREJ : (int)(C_TRI + (u - 3u)); } };
 
-// Resolves (contract, declarer, king) for one game from the chosen source.
+constexpr u64 BOUNDS8_6x8 = 0x0606060606060606ull;
+__device__ __forceinline__ u32 bot_digits8(u32 x, const Rng& rng, u64 gid, u32 word) {    // eight draws of [0,6) -> 3 bits each
+    u32 out = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) out |= bdraw(x, 6u) << (3 * i);
+    if (__builtin_expect(x < (u32)((1ull << 32) % 1679616ull), 0)) {
+        const u64 p = bdraw_retry(rng.seed, gid, ST_BID, word, BOUNDS8_6x8, 8u);
+        out = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) out |= ((u32)(p >> (6 * i)) & 7u) << (3 * i);
+    }
+    return out;
+}
+
+// The synthetic pre-play decisions of one game other than the bids come from ONE Philox block, (gid, ST_FORCE, 0):
+//   word 0: forced contract of the mixed mode (n = 3), declarer (4), called king (4) -- three batched draws;
+//   word 1: talon exchange -- the k discards (n = a, a-1, a-2 with a = discardable cards after the pick-up), batched;
+//   word 2: the king a Bot_igralec declarer calls (n = 4, Igralec.py:155-156);
+//   word 3: the talon group when it is random (n = number of groups, Igralec.py:369-370).
+__device__ __forceinline__ Words4 setup_block(const Rng& rng, u64 gid) { return philox_block(rng, gid, ST_FORCE, 0u); }
+
+// Resolves (contract, declarer, king) for one game from the chosen source.  `sb` = setup_block (SRC_SYNTH only).
 template <int SRC>
 __device__ __forceinline__ void resolve_contract(const Rng& rng, u64 gid, u32 mode, const uint8_t* a, const uint8_t* b,
-                                                 const uint8_t* c, u64 g, u32& contract, u32& declarer, u32& king) {
+                                                 const uint8_t* c, u64 g, const Words4& sb, u32& contract, u32& declarer,
+                                                 u32& king) {
     if (SRC == SRC_FORCED) {
         contract = a[g]; declarer = b[g]; king = c ? c[g] : NO_KING;
     } else if (SRC == SRC_INTENTS) {
@@ -353,26 +419,40 @@ __device__ __forceinline__ void resolve_contract(const Rng& rng, u64 gid, u32 mo
         // king = the suit attached to the declarer's ORIGINAL intent (Igralec.py:298,308-310)
         king = d == 0 ? su[0] : d == 1 ? su[1] : d == 2 ? su[2] : su[3];
     } else {
-        if (mode == 17u) {          // TAROK_MODE_AUCTION_UNIFORM
-            Words4 blk = philox_block(rng, gid, ST_BID, 0u);
+        if (mode == 17u) {          // TAROK_MODE_AUCTION_UNIFORM: four batched draws of [0,18) from word 0 of the bid block
+            u32 x = philox_block(rng, gid, ST_BID, 0u).w[0];
+            u32 idx[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) idx[s] = bdraw(x, 18u);
+            if (__builtin_expect(x < (u32)((1ull << 32) % 104976ull), 0)) {
+                const u64 p = bdraw_retry(rng.seed, gid, ST_BID, 0u, 0x12121212ull, 4u);
+#pragma unroll
+                for (int s = 0; s < 4; s++) idx[s] = (u32)(p >> (6 * s)) & 63u;
+            }
             WantFixed w; u32 su[4];
 #pragma unroll
-            for (int s = 0; s < 4; s++) index2igra(draw_from_word(blk.w[s], rng, gid, ST_BID, (u32)s, 18u), w.tip[s], su[s]);
+            for (int s = 0; s < 4; s++) index2igra(idx[s], w.tip[s], su[s]);
             int d, k;
             licitacija<true>(w, d, k);
             contract = (u32)k; declarer = (u32)d;
             king = d == 0 ? su[0] : d == 1 ? su[1] : d == 2 ? su[2] : su[3];
         } else if (mode == 18u) {   // TAROK_MODE_AUCTION_BOT
-            WantBot w{rng, gid};
+            const Words4 bb = philox_block(rng, gid, ST_BID, 0u);
+            WantBot w{rng, gid, (u64)bot_digits8(bb.w[0], rng, gid, 0u) | ((u64)bot_digits8(bb.w[1], rng, gid, 1u) << 24)};
             int d, k;
             licitacija<false>(w, d, k);
             contract = (u32)k; declarer = (u32)d;
-            king = is_king_game(contract) ? draw(rng, gid, ST_KING, 0u, 4u) : NO_KING;   // Igralec.py:155-156
+            king = is_king_game(contract) ? draw_from_word(sb.w[2], rng, gid, ST_FORCE, 2u, 4u) : NO_KING;   // Igralec.py:155-156
         } else {
-            Words4 blk = philox_block(rng, gid, ST_FORCE, 0u);
-            contract = mode == 16u ? C_TRI + draw_from_word(blk.w[0], rng, gid, ST_FORCE, 0u, 3u) : mode;
-            declarer = contract == C_KLOP ? 0u : draw_from_word(blk.w[1], rng, gid, ST_FORCE, 1u, 4u);
-            king = is_king_game(contract) ? draw(rng, gid, ST_KING, 0u, 4u) : NO_KING;
+            u32 x = sb.w[0];
+            u32 c3 = bdraw(x, 3u), d4 = bdraw(x, 4u), k4 = bdraw(x, 4u);
+            if (__builtin_expect(x < 16u, 0)) {                                  // 2^32 mod 48
+                const u64 p = bdraw_retry(rng.seed, gid, ST_FORCE, 0u, 0x040403ull, 3u);
+                c3 = (u32)p & 63u; d4 = (u32)(p >> 6) & 63u; k4 = (u32)(p >> 12) & 63u;
+            }
+            contract = mode == 16u ? C_TRI + c3 : mode;
+            declarer = contract == C_KLOP ? 0u : d4;
+            king = is_king_game(contract) ? k4 : NO_KING;
         }
     }
 }
@@ -387,7 +467,9 @@ __global__ void __launch_bounds__(CTA) k_begin(Env e, u32 mode, const uint8_t* _
     const u64 na = e.n_alloc;
     u64 h0 = e.hands[g], h1 = e.hands[na + g], h2 = e.hands[2 * na + g], h3 = e.hands[3 * na + g];
     u32 contract, declarer, king;
-    resolve_contract<SRC>(e.rng, e.first_gid + g, mode, a, b, c, g, contract, declarer, king);
+    Words4 sb = {{0, 0, 0, 0}};
+    if (SRC == SRC_SYNTH) sb = setup_block(e.rng, e.first_gid + g);
+    resolve_contract<SRC>(e.rng, e.first_gid + g, mode, a, b, c, g, sb, contract, declarer, king);
     slots_to_seats(h0, h1, h2, h3, leader_of(meta));             // identity in practice: a dealt game has leader 0
     meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
     if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
@@ -404,24 +486,40 @@ __global__ void __launch_bounds__(CTA) k_begin(Env e, u32 mode, const uint8_t* _
 // and lays k discardable cards (Roka.mozno_zalozit, Roka.py:23-27) into the own pile (Igralec.py:161-171).
 // ------------------------------------------------------------------------------------------------
 // Returns false (error) if the action is invalid or fewer than k cards can be laid down (Q19).
+// SYNTH: the decision is drawn from words 1 and 3 of the setup block `sb`.
+// Card points of a bitboard (Roka.vrednost_stiha's per-card values, Roka.py:76-91): 1 + J 1, C 2, Q 3, K / trula 4 extra.
+__device__ __forceinline__ u32 card_points(u64 s) {
+    return (u32)(__popcll(s) + __popcll(s & JACKS) + 2 * __popcll(s & CAVALS) + 3 * __popcll(s & QUEENS)
+                 + 4 * __popcll(s & (KINGS | TRULA)));
+}
+
 template <bool SYNTH>
-__device__ __forceinline__ bool exchange_game(const Rng& rng, u64 gid, u32 random_group, u64& meta, u64& hand, u64& pile,
-                                              u64& talon, u64 order, u32 group, u64 discard, u64& discard_out) {
+__device__ __forceinline__ bool exchange_game(const Rng& rng, u64 gid, u32 random_group, const Words4& sb, u64& meta, u64& hand,
+                                              u64& pile, u64& talon, u64 order, u32 group, u64 discard, u64& discard_out) {
     u32 contract = mget(meta, M_CONTRACT, 4);
     u32 k = talon_k(contract);
     u32 ngroups = 6u / k;
     u64 gb_synth = 0;
     if (SYNTH) {
-        Words4 blk = philox_block(rng, gid, ST_EXCH, 0u);
-        group = random_group ? draw_from_word(blk.w[0], rng, gid, ST_EXCH, 0u, ngroups) : 0u;   // Bot: group 0 (Igralec.py:162)
+        // Bot: group 0 (Igralec.py:162); neural random branch: a uniform group (Igralec.py:369-370), its own word
+        group = random_group ? draw_from_word(sb.w[3], rng, gid, ST_FORCE, 3u, ngroups) : 0u;
         gb_synth = talon_group_bits(order, k, group);
         u64 avail = (hand | gb_synth) & DISCARDABLE;
-        if ((u32)__popcll(avail) < k) return false;
+        const u32 a = (u32)__popcll(avail);
+        if (a < k) return false;
+        u32 x = sb.w[1], prod = 1, rd[3] = {0, 0, 0};
+#pragma unroll
+        for (u32 j = 0; j < 3; j++) if (j < k) { rd[j] = bdraw(x, a - j); prod *= a - j; }
+        if (__builtin_expect(x < prod, 0) && x < (0u - prod) % prod) {           // rejected sliver: redraw the word
+            u64 bb = 0;
+            for (u32 j = 0; j < k; j++) bb |= (u64)(a - j) << (8 * j);
+            const u64 p1 = bdraw_retry(rng.seed, gid, ST_FORCE, 1u, bb, k);
+            for (u32 j = 0; j < 3; j++) rd[j] = (u32)(p1 >> (6 * j)) & 63u;
+        }
         discard = 0;
-        for (u32 j = 0; j < k; j++) {               // uniform k-subset = random.sample (Igralec.py:166)
-            u32 wj = j == 0 ? blk.w[1] : j == 1 ? blk.w[2] : blk.w[3];
-            u32 r = draw_from_word(wj, rng, gid, ST_EXCH, 1u + j, (u32)__popcll(avail));
-            u64 bit = 1ull << nth_set_bit(avail, r);
+#pragma unroll
+        for (u32 j = 0; j < 3; j++) if (j < k) {    // uniform k-subset = random.sample (Igralec.py:166)
+            u64 bit = 1ull << nth_set_bit(avail, rd[j]);
             avail ^= bit; discard |= bit;
         }
     }
@@ -453,7 +551,9 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
     u64 hand = sel4(h0, h1, h2, h3, decl);
     u64 pile = e.piles[decl * na + g];
     u64 talon = e.talon[g], order = e.torder[g], dout = 0;
-    bool ok = exchange_game<SYNTH>(e.rng, e.first_gid + g, random_group, meta, hand, pile, talon, order,
+    Words4 sb = {{0, 0, 0, 0}};
+    if (SYNTH) sb = setup_block(e.rng, e.first_gid + g);
+    bool ok = exchange_game<SYNTH>(e.rng, e.first_gid + g, random_group, sb, meta, hand, pile, talon, order,
                                    SYNTH ? 0u : (u32)group[g], SYNTH ? 0ull : discard[g], dout);
     if (!ok) {
         meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
@@ -467,6 +567,7 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
     e.talon[g] = talon;
     e.meta[g] = meta;
     if (e.discard) e.discard[g] = dout;
+    e.dpts[g] = (uint8_t)card_points(dout);
     u32 mv = mover_of(meta);
     e.mask[g] = mask_for_mover(meta, mv == decl ? hand : sel4(h0, h1, h2, h3, mv));
 }
@@ -496,12 +597,13 @@ __global__ void __launch_bounds__(CTA) k_setup_synth(Env e, u32 mode) {
         d = deal_philox(e.rng, gid);
         s0 = d.h0; s1 = d.h1; s2 = d.h2; s3 = d.h3;
         u32 contract, declarer, king;
-        resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, contract, declarer, king);
+        const Words4 sb = setup_block(e.rng, gid);
+        resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, sb, contract, declarer, king);
         meta = begin_contract(meta_fresh(), contract, declarer, king, d.h0, d.h1, d.h2, d.h3);
         if (mget(meta, M_PHASE, 2) == PH_EXCHANGE) {
             const u32 decl = mget(meta, M_DECL, 2);
             u64 hand = sel4(d.h0, d.h1, d.h2, d.h3, decl), pile = 0;
-            if (exchange_game<true>(e.rng, gid, mode == 17u, meta, hand, pile, d.talon, d.order, 0u, 0ull, dout)) {
+            if (exchange_game<true>(e.rng, gid, mode == 17u, sb, meta, hand, pile, d.talon, d.order, 0u, 0ull, dout)) {
                 d.h0 = decl == 0 ? hand : d.h0; d.h1 = decl == 1 ? hand : d.h1;
                 d.h2 = decl == 2 ? hand : d.h2; d.h3 = decl == 3 ? hand : d.h3;
                 p0 = decl == 0 ? pile : 0ull; p1 = decl == 1 ? pile : 0ull;
@@ -519,6 +621,7 @@ __global__ void __launch_bounds__(CTA) k_setup_synth(Env e, u32 mode) {
     e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = mask;
     if (e.hands0) { e.hands0[g] = s0; e.hands0[na + g] = s1; e.hands0[2 * na + g] = s2; e.hands0[3 * na + g] = s3; }
     if (e.discard) e.discard[g] = dout;
+    e.dpts[g] = (uint8_t)card_points(dout);
 }
 
 // The two card ids of a lane's game pair.  The caller's array holds exactly n_games bytes: never read past it.
@@ -564,7 +667,7 @@ __device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u6
     } else {
         // append-only trick log (4 B, coalesced) instead of a scattered read-modify-write of the winner's pile;
         // k_score materialises the piles (and the Klop talon) from it
-        e.tricklog[(u64)(plays >> 2) * na + g] = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);   // 12 rows: 64-bit index
+        e.tricklog[(u64)(plays >> 2) * na + g] = log_entry((u32)(meta >> 32) & 0xFFFFFFu, pr.winner);   // 12 rows: 64-bit index
         s3 = hand;                                                 // the trick closes from slot 3
         const u32 w = pr.winner_rel;                               // the winner's slot = its index in the trick
         if (w == 0u) {
@@ -618,7 +721,7 @@ __device__ __forceinline__ void step_pair_general(const Env& e, u32 g, ulonglong
 // hm = slot POS (the mover's hand); POS < 3: n0 = slot POS + 1 (the next seat); POS == 3: n0, n1, n2 = slots 0, 1, 2.
 template <bool RANDOM, int POS>
 __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u64& hm, u64& n0, u64& n1, u64& n2, u32 card,
-                                               const Words4& rnd, u64& next_mask, u32& log_entry) {
+                                               const Words4& rnd, u64& next_mask, u32& log_out) {
     const u32 na = (u32)e.n_alloc;
     const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 leader = (lo >> M_LEADER) & 3u, kf = (lo >> M_KLOPFAM) & 1u;
@@ -639,7 +742,7 @@ __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u
     if (POS < 3) {
         next_mask = legal_moves(n0, true, (u32)(meta >> 32) & 63u, kf);
     } else {
-        log_entry = ((u32)(meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
+        log_out = log_entry((u32)(meta >> 32) & 0xFFFFFFu, pr.winner);
         rotate4(n0, n1, n2, hm, pr.winner_rel);                    // slots 0..3 re-seated from the winner
         // the winner opens the next trick: everything it holds (minus the Klop-family pagat rule), nothing once finished
         next_mask = (((u32)meta >> M_PHASE) & 3u) == PH_PLAY ? legal_moves(n0, false, 0u, kf) : 0ull;
@@ -812,7 +915,7 @@ __global__ void __launch_bounds__(CTA) k_legal_mask(Env e, u64* __restrict__ out
 // score: Roka.prestej + the three start() epilogues; accumulates the statistics vector.
 // 56 B/deal algorithmic: R 4 piles 32 + talon 8 + meta 8, W int16[4] 8.
 // ------------------------------------------------------------------------------------------------
-// Piles are materialised here: pile[s] = what the exchange laid down (stored) | the tricks seat s won (trick log);
+// Piles are materialised here (MAT): pile[s] = what the exchange laid down (stored) | the tricks seat s won (trick log);
 // in Klop the talon loses the cards that went into tricks 1..6.  Idempotent.
 __device__ __forceinline__ void materialise(u64 meta, const uint2* log12, int which, u64 order,
                                             u64& p0, u64& p1, u64& p2, u64& p3, u64& talon) {
@@ -824,46 +927,65 @@ __device__ __forceinline__ void materialise(u64 meta, const uint2* log12, int wh
             const u32 entry = which ? log12[k].y : log12[k].x;
             u64 tc;
             const u64 b = trick_bits(entry, k, klop, order, tc);
-            const u32 w = entry >> 24;
+            const u32 w = (entry >> 24) & 3u;
             p0 |= w == 0 ? b : 0ull; p1 |= w == 1 ? b : 0ull; p2 |= w == 2 ? b : 0ull; p3 |= w == 3 ? b : 0ull;
             talon &= ~tc;
         }
     }
 }
 
-// MAT = write the materialised piles / talon back (the exported fields then hold the full piles); without it only the
-// scores and statistics are produced (pipelines that, like Tarok.paralel_start, only need the results).
-// Scores only (no per-seat piles): what each contract family's epilogue actually needs from the trick log.
-__device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int which, u64 order, u64 p0, u64 p1, u64 p2,
-                                              u64 p3, u64 talon) {
-    const u32 contract = mget(meta, M_CONTRACT, 4), decl = mget(meta, M_DECL, 2), tricks = mget(meta, M_TRICKS, 4);
+// Scores straight from the trick log: every entry carries its winner and the card points of its four cards, and
+// Roka.prestej is order independent -- sum(points) - 2 * floor(n / 3) - [n % 3 != 0] over the n cards of a pile
+// (Roka.py:55-98) -- so no bitboard is rebuilt: per trick one compare-and-add.
+//   Navadna / Solo (Navadna_igra.py:80-113): the team's points = the declarer's discards (`dpts`, k cards) + the tricks won by
+//     a seat of `ekipa`; the leftover talon joins them iff a lone declarer in a king game took the called king (Q7).
+//   Klop (Klop.py:36-45): per seat; the talon card of tricks 1..6 (popped from the END, Klop.py:67-71) goes to the winner.
+//   Berac (Berac.py:33-44): the game stops on the declarer's first trick, so "the declarer took a trick" = "the last
+//     trick's winner is the declarer".
+__device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int which, u32 dpts, u64 talon, u64 order) {
+    const u32 lo = (u32)meta;
+    const u32 contract = lo & 15u, decl = (lo >> M_DECL) & 3u, tricks = (lo >> M_TRICKS) & 15u;
     if (is_navadna(contract)) {
-        const u32 team = mget(meta, M_TEAM, 4);
-        u64 pd = sel4(p0, p1, p2, p3, decl);              // stored piles hold only the declarer's discards so far
-        u64 tp = pd;
+        const u32 team = (lo >> M_TEAM) & 15u, king = (lo >> M_KING) & 7u;
+        u32 pts = dpts, won = 0;
+        const bool lone = contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING;
+        const u32 kid = (king & 3u) * 8u + 7u;
+        bool took_king = false;
 #pragma unroll
         for (u32 k = 0; k < 12; k++) {
-            if (k < tricks) {
-                const u32 entry = which ? log12[k].y : log12[k].x;
-                u64 tc;
-                const u64 b = trick_bits(entry, k, false, 0ull, tc);
-                const u32 w = entry >> 24;
-                tp |= ((team >> w) & 1u) ? b : 0ull;
-                pd |= w == decl ? b : 0ull;
-            }
+            const u32 entry = which ? log12[k].y : log12[k].x;
+            const bool mine = k < tricks && ((team >> ((entry >> 24) & 3u)) & 1u);
+            pts += mine ? (entry >> 26) & 31u : 0u;
+            won += mine ? 1u : 0u;
+            if (lone) took_king |= mine && trick_has(entry, kid);       // a lone declarer is the whole team
         }
-        return score_navadna(meta, tp, pd, talon);
+        u32 n = 4u * won + (((lo >> M_GROUP) & 7u) != NO_GROUP ? talon_k(contract) : 0u);
+        if (lone && took_king) { pts += card_points(talon); n += (u32)__popcll(talon); }   // leftover talon (Q7)
+        return score_navadna_v(meta, prestej_pn((int)pts, (int)n));
     }
-    if (is_berac(contract)) {
-        bool took = false;
+    if (is_berac(contract)) return score_berac(meta, ((lo >> M_WINNER) & 3u) == decl);
+    if (contract != C_KLOP) return 0ull;
+    u32 acc = 0;                                          // per seat one byte: card points (<= 106) of the pile
+    u32 cnt = 0;                                          // per seat one byte: cards
 #pragma unroll
-        for (u32 k = 0; k < 12; k++) took |= k < tricks && ((which ? log12[k].y : log12[k].x) >> 24) == decl;
-        return score_berac(meta, took);
+    for (u32 k = 0; k < 12; k++) {
+        if (k < tricks) {
+            const u32 entry = which ? log12[k].y : log12[k].x;
+            u32 p = (entry >> 26) & 31u, c = 4u;
+            if (k < 6) { p += card_points1((u32)(order >> (6 * (5 - k))) & 63u); c = 5u; }
+            const u32 sh = 8u * ((entry >> 24) & 3u);
+            acc += p << sh; cnt += c << sh;
+        }
     }
-    materialise(meta, log12, which, order, p0, p1, p2, p3, talon);
-    return contract == C_KLOP ? score_klop(p0, p1, p2, p3) : 0ull;
+    const int a = prestej_pn((int)(acc & 255u), (int)(cnt & 255u)), b = prestej_pn((int)((acc >> 8) & 255u), (int)((cnt >> 8) & 255u)),
+              c = prestej_pn((int)((acc >> 16) & 255u), (int)((cnt >> 16) & 255u)), d = prestej_pn((int)(acc >> 24), (int)(cnt >> 24));
+    const bool any = a > 35 || b > 35 || c > 35 || d > 35;
+    return pack_scores(any ? 0 : -a, any ? 0 : -b, any ? 0 : -c, any ? 0 : -d);
 }
 
+// MAT = also write the materialised piles / talon back (the exported fields then hold the full piles); without it only the
+// scores and statistics are produced (pipelines that, like Tarok.paralel_start, only need the results): what is read is
+// meta 8 + trick log 48 + talon 8 + discard points 1 (+ the talon order for Klop), 8 B of scores written.
 template <bool MAT>
 __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64 out_n) {
     u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
@@ -873,32 +995,32 @@ __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64
     u32 c0 = 0, c1 = 0, pl0 = 0, pl1 = 0;
     if (g < na) {
         ulonglong2 m = ld2(e.meta + g);
-        ulonglong2 p0 = ld2(e.piles + g), p1 = ld2(e.piles + na + g), p2 = ld2(e.piles + 2 * na + g),
-                   p3 = ld2(e.piles + 3 * na + g);
-        ulonglong2 t = ld2(e.talon + g), o = ld2(e.torder + g);
+        ulonglong2 t = ld2(e.talon + g);
+        const u32 dp = *reinterpret_cast<const unsigned short*>(e.dpts + g);
         uint2 log12[12];                                  // all twelve entries are fetched up front (one memory phase);
 #pragma unroll                                            // entries past the tricks played are stale and never looked at
         for (u32 k = 0; k < 12; k++) log12[k] = *reinterpret_cast<const uint2*>(e.tricklog + k * na + g);
+        c0 = mget(m.x, M_CONTRACT, 4); c1 = mget(m.y, M_CONTRACT, 4);
+        ulonglong2 o = {0, 0};
+        if (MAT || c0 == C_KLOP || c1 == C_KLOP) o = ld2(e.torder + g);
         if (MAT) {
-            materialise(m.x, log12, 0, o.x, p0.x, p1.x, p2.x, p3.x, t.x);
-            materialise(m.y, log12, 1, o.y, p0.y, p1.y, p2.y, p3.y, t.y);
+            ulonglong2 p0 = ld2(e.piles + g), p1 = ld2(e.piles + na + g), p2 = ld2(e.piles + 2 * na + g),
+                       p3 = ld2(e.piles + 3 * na + g);
+            ulonglong2 tt = t;
+            materialise(m.x, log12, 0, o.x, p0.x, p1.x, p2.x, p3.x, tt.x);
+            materialise(m.y, log12, 1, o.y, p0.y, p1.y, p2.y, p3.y, tt.y);
             *reinterpret_cast<ulonglong2*>(e.piles + g) = p0; *reinterpret_cast<ulonglong2*>(e.piles + na + g) = p1;
             *reinterpret_cast<ulonglong2*>(e.piles + 2 * na + g) = p2; *reinterpret_cast<ulonglong2*>(e.piles + 3 * na + g) = p3;
-            *reinterpret_cast<ulonglong2*>(e.talon + g) = t;
+            *reinterpret_cast<ulonglong2*>(e.talon + g) = tt;
         }
         e0 = ((m.x >> M_ERR) & 1ull) && g < e.n;
         e1 = ((m.y >> M_ERR) & 1ull) && g + 1 < e.n;
         f0 = mget(m.x, M_PHASE, 2) == PH_DONE && !((m.x >> M_ERR) & 1ull) && g < e.n;
         f1 = mget(m.y, M_PHASE, 2) == PH_DONE && !((m.y >> M_ERR) & 1ull) && g + 1 < e.n;
-        c0 = mget(m.x, M_CONTRACT, 4); c1 = mget(m.y, M_CONTRACT, 4);
         pl0 = g < e.n ? mget(m.x, M_PLAYS, 6) : 0u; pl1 = g + 1 < e.n ? mget(m.y, M_PLAYS, 6) : 0u;
-        if (MAT) {
-            if (f0) s0 = score_game(m.x, p0.x, p1.x, p2.x, p3.x, t.x);
-            if (f1) s1 = score_game(m.y, p0.y, p1.y, p2.y, p3.y, t.y);
-        } else {
-            if (f0) s0 = score_from_log(m.x, log12, 0, o.x, p0.x, p1.x, p2.x, p3.x, t.x);
-            if (f1) s1 = score_from_log(m.y, log12, 1, o.y, p0.y, p1.y, p2.y, p3.y, t.y);
-        }
+        // the (pre-materialisation) talon is what the Navadna epilogue needs: no exchange ever follows the first card
+        if (f0) s0 = score_from_log(m.x, log12, 0, dp & 0xFFu, t.x, o.x);
+        if (f1) s1 = score_from_log(m.y, log12, 1, dp >> 8, t.y, o.y);
         if (g + 1 < out_n) st2(out + g, s0, s1);
         else if (g < out_n) out[g] = s0;
     }
@@ -928,7 +1050,7 @@ __device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, cons
     PlayResult pr;
     f.meta = play_card<false, J>(f.meta, hand, card, f.talon, f.order, pr);
     if (J == 3) {
-        if (log_row) *log_row = ((u32)(f.meta >> 32) & 0xFFFFFFu) | (pr.winner << 24);
+        if (log_row) *log_row = log_entry((u32)(f.meta >> 32) & 0xFFFFFFu, pr.winner);
         const u64 b = pr.pile_bits;
         f.p0 |= pr.winner == 0 ? b : 0ull; f.p1 |= pr.winner == 1 ? b : 0ull;
         f.p2 |= pr.winner == 2 ? b : 0ull; f.p3 |= pr.winner == 3 ? b : 0ull;
@@ -973,23 +1095,32 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         } else d = deal_philox(e.rng, gid);
         h0 = d.h0; h1 = d.h1; h2 = d.h2; h3 = d.h3; talon = d.talon; order = d.order;
         meta = meta_fresh();
+        const Words4 sb = setup_block(e.rng, gid);       // the device-side pre-play decisions (contract unless forced, exchange)
         if (!ok) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
         else {
             u32 contract, declarer, king;
             if (DEALS == DEALS_RECORD) { contract = rec.contract; declarer = rec.declarer; king = rec.king; }
-            else if (fc) resolve_contract<SRC_FORCED>(e.rng, gid, mode, fc, fd, fk, g, contract, declarer, king);
-            else resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, contract, declarer, king);
+            else if (fc) resolve_contract<SRC_FORCED>(e.rng, gid, mode, fc, fd, fk, g, sb, contract, declarer, king);
+            else resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, sb, contract, declarer, king);
             meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
         }
+        if (write_state && e.hands0) {                   // hands as dealt (zacetna_roka), by seat: the replay kernels start from them
+            e.hands0[g] = h0; e.hands0[na + g] = h1; e.hands0[2 * na + g] = h2; e.hands0[3 * na + g] = h3;
+        }
+        u64 dout = 0;
         if (mget(meta, M_PHASE, 2) == PH_EXCHANGE) {
             u32 decl = mget(meta, M_DECL, 2);
-            u64 hand = sel4(h0, h1, h2, h3, decl), pile = 0, dout;
-            bool ok2 = exchange_game<true>(e.rng, gid, mode == 17u, meta, hand, pile, talon, order, 0u, 0ull, dout);
+            u64 hand = sel4(h0, h1, h2, h3, decl), pile = 0;
+            bool ok2 = exchange_game<true>(e.rng, gid, mode == 17u, sb, meta, hand, pile, talon, order, 0u, 0ull, dout);
             if (!ok2) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
             else {
                 h0 = decl == 0 ? hand : h0; h1 = decl == 1 ? hand : h1; h2 = decl == 2 ? hand : h2; h3 = decl == 3 ? hand : h3;
                 p0 = decl == 0 ? pile : p0; p1 = decl == 1 ? pile : p1; p2 = decl == 2 ? pile : p2; p3 = decl == 3 ? pile : p3;
             }
+        }
+        if (write_state) {
+            if (e.discard) e.discard[g] = dout;
+            e.dpts[g] = (uint8_t)card_points(dout);
         }
         const u32 contract = mget(meta, M_CONTRACT, 4);
         const bool klop = klop_rules(contract);

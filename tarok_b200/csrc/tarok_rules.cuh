@@ -133,6 +133,7 @@ __device__ __forceinline__ int prestej(u64 s) {
             + 4 * __popcll(s & (KINGS | TRULA));
     return pts - 2 * (n / 3) - ((n % 3) != 0);
 }
+__device__ __forceinline__ int prestej_pn(int pts, int n) { return pts - 2 * (n / 3) - ((n % 3) != 0); }
 // value of one trick for per-trick rewards: Roka.vrednost_stiha on 4 or 5 cards = sum - 2 (Roka.py:92-95)
 __device__ __forceinline__ int vrednost_stiha_bits(u64 s) {
     int n = __popcll(s);
@@ -325,7 +326,31 @@ __device__ __forceinline__ u64 play_card(u64 meta, u64& hand, u32 card, u64 talo
     return ((u64)hi << 32) | lo;
 }
 
-// Trick-log entry: the four cards in play order (24 bits) | winner seat << 24.  The bitboard the winner collected in
+// Card points of the four cards of a trick (Roka.vrednost_stiha's per-card values, Roka.py:76-91: suit ranks 1-4 -> 1,
+// J 2, C 3, Q 4, K 5; taroks 1, trula 5), computed on the packed 4 x 6-bit card ids at once (no per-card loop):
+// bit 5 of a field = tarok, bit 2 of a suit card = J or higher, and its low two bits + 1 = the extra points.
+// Checked against the per-card table on all 54^4 tuples (tests/test_closed_forms.py).
+__device__ __forceinline__ u32 trick_points(u32 f) {
+    const u32 B5 = 0x820820u;                                        // bit 5 of every field
+    const u32 hr = ~f & (f << 3) & B5;                               // suit card with rank >= J
+    const u32 v = ((f & 0x0C30C3u) + 0x041041u) & ((hr >> 5) * 7u);  // 1..4 extra for J, C, Q, K
+    const u32 a = f & (f << 1) & (f << 3);                           // bit 5: ids 52, 53 (mond, skis)
+    const u32 nz = (f & 0x7DF7DFu) + 0x7DF7DFu;                      // bit 5 set iff the low five bits are not all zero
+    const u32 tr = f & (a | ~nz) & B5;                               // trula: id 32 (pagat) | 52 | 53
+    return 4u + (((v * 0x041041u) >> 18) & 0x3Fu) + 4u * (u32)__popc(tr);
+}
+__device__ __forceinline__ u32 card_points1(u32 c) {                 // one card
+    return c >= 32u ? ((c == 32u || c >= 52u) ? 5u : 1u) : ((c & 4u) ? (c & 7u) - 2u : 1u);
+}
+// Does the trick (4 x 6-bit ids) contain card `id`?
+__device__ __forceinline__ bool trick_has(u32 f, u32 id) {
+    const u32 x = (f & 0xFFFFFFu) ^ (id * 0x041041u);
+    const u32 z = ((x & 0x7DF7DFu) + 0x7DF7DFu) | x;                 // bit 5 of a field set iff the field is non-zero
+    return (~z & 0x820820u) != 0u;
+}
+// Trick-log entry: the four cards in play order (24 bits) | winner seat << 24 | trick_points << 26 (5 bits).
+__device__ __forceinline__ u32 log_entry(u32 t24, u32 winner) { return t24 | (winner << 24) | (trick_points(t24) << 26); }
+// Trick-log entry, continued.  The bitboard the winner collected in
 // trick k: its four cards, plus in Klop the talon card popped from the END of the ordered talon in tricks 1..6
 // (Klop.py:67-71, Q4), which is also returned in `talon_card`.
 __device__ __forceinline__ u64 trick_bits(u32 entry, u32 k, bool is_klop, u64 talon_order, u64& talon_card) {
@@ -360,6 +385,15 @@ __device__ __forceinline__ u64 score_navadna(u64 meta, u64 tp, u64 pd, u64 talon
     const int v = prestej(tp);
     const int r = v - 35 + 2;                             // 5*round((v-35)/5): no ties for integers
     const int q = (r >= 0 ? r / 5 : -((-r + 4) / 5)) * 5; // floor division
+    const int val = (v > 35 ? 10 * (int)contract : -10 * (int)contract) + q;
+    return pack_scores((team & 1u) ? val : 0, (team & 2u) ? val : 0, (team & 4u) ? val : 0, (team & 8u) ? val : 0);
+}
+
+// The same epilogue from the team's card points and card count (prestej is order independent).
+__device__ __forceinline__ u64 score_navadna_v(u64 meta, int v) {
+    const u32 contract = mget(meta, M_CONTRACT, 4), team = mget(meta, M_TEAM, 4);
+    const int r = v - 35 + 2;
+    const int q = (r >= 0 ? r / 5 : -((-r + 4) / 5)) * 5;
     const int val = (v > 35 ? 10 * (int)contract : -10 * (int)contract) + q;
     return pack_scores((team & 1u) ? val : 0, (team & 2u) ? val : 0, (team & 4u) ? val : 0, (team & 8u) ? val : 0);
 }

@@ -401,15 +401,26 @@ class Tarok:
             yield from range(self.st_iger)
 
     def _vsi_na_napravi(self):
-        return all(getattr(i, "device_policy", None) == "bot" for i in self.igralci)
+        """The device fast path replaces the players' decisions by the in-kernel uniform bot, so it is only taken when
+        every player IS that bot: ``Bot_igralec`` itself, or a subclass that overrides none of its decision methods
+        or callbacks (an override would silently never run)."""
+        from .igralec import Bot_igralec, ODLOCITVE
+        for i in self.igralci:
+            if getattr(i, "device_policy", None) != "bot" or not isinstance(i, Bot_igralec):
+                return False
+            if any(getattr(type(i), m) is not getattr(Bot_igralec, m) for m in ODLOCITVE):
+                return False
+        return True
 
     def start(self):
         """Sequential single games, all with id 0 and no seat rotation (Tarok.py:23-28, Q14)."""
         if self._vsi_na_napravi():
             self._na_napravi(self.st_iger, rotacija=False)
         else:
-            for _ in range(self.st_iger):
-                r = _pozeni(Partije([list(self.igralci)], [0], device=self.device, seed=self.seed), self.igralci)
+            for i in range(self.st_iger):
+                # every sequential game is its own deal: game i draws from Philox counter (seed, i), like game i of the
+                # device path (the reference shuffles afresh for every Igra, Igra.py:66-67)
+                r = _pozeni(Partije([list(self.igralci)], [0], device=self.device, seed=self.seed, prvi_id=i), self.igralci)
                 for k, v in r[0].items():
                     self.rezultati[k] += v
         if self.izpis:
@@ -440,10 +451,14 @@ class Tarok:
         env.rollout(E.MODE_AUCTION_BOT, first_game_id=0, fused=True)
         st = env.stats()
         self.statistika = st
+        env.close()
+        if int(st[E.S_ERRORS]):
+            # the reference raises out of random.sample when fewer than k cards can be laid down (Igralec.py:166, Q19)
+            raise ValueError("Sample larger than population or is negative (%d of %d deals: a Bot_igralec declarer "
+                             "could not lay down enough cards)" % (int(st[E.S_ERRORS]), st_iger))
         vsote = st[E.S_PLAYER:E.S_PLAYER + 4] if rotacija else st[E.S_SEAT:E.S_SEAT + 4]
         for p, igralec in enumerate(self.igralci):
             self.rezultati[igralec] += int(vsote[p])
-        env.close()
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -108,6 +108,13 @@ class Igralec:
     __repr__ = __str__
 
 
+#: the methods whose override means "this is no longer the plain bot" (decisions and result callbacks)
+ODLOCITVE = ("licitiram", "izberi_barvo_kralja", "igraj_karto", "menjaj_iz_talona", "nova_igra", "pripavi_licitiram",
+             "konec_licitiranja", "pripravi_izbral_iz_talona", "izbral_iz_talona", "pripravi_igraj_karto", "rezultat_stiha",
+             "rezultat_igre", "poglej_karte_odprtega_beraca", "predict_licitiram", "predict_izberi_iz_talona",
+             "predict_igraj_karto")
+
+
 class Bot_igralec(Igralec):
     """Uniform-random legal-move player (Igralec.py:142-171).
 

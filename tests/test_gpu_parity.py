@@ -194,6 +194,29 @@ def test_rollout_matches_oracle(oracle, mode, gid0):
     env.close()
 
 
+@pytest.mark.parametrize("mode", [16, 17, 0])
+def test_fused_rollout_writes_the_replay_inputs(mode):
+    """On a FRESH history-keeping environment the fused rollout must leave everything the replay kernels read -- hands as
+    dealt, the declarer's discards, the discard points -- exactly as the stepwise pipeline does (round-1 advisor finding:
+    the fused kernel used to leave hands0 / discard stale)."""
+    n, seed, gid0 = 30011, 31337, 9
+    a, b = _env(n, seed=seed, history=True), _env(n, seed=seed, history=True)
+    a.rollout(mode, first_game_id=gid0, fused=False)
+    b.rollout(mode, first_game_id=gid0, fused=True)
+    for f in ("hands0", "discard", "hands", "piles", "talon", "meta"):
+        assert (u64(getattr(a, f)) == u64(getattr(b, f))).all(), f
+    assert (a.hist[:, :n].cpu().numpy() == b.hist[:, :n].cpu().numpy()).all()
+    da, sa, ra = a.targets()
+    db, sb, rb = b.targets()
+    assert (sa.cpu().numpy() == sb.cpu().numpy()).all() and (ra.cpu().numpy() == rb.cpu().numpy()).all()
+    assert (da.cpu().numpy() == db.cpu().numpy()).all()
+    # scoring again (idempotent) from the state the fused kernel wrote
+    sc = b.scores[:n].cpu().numpy().copy()
+    b.reset_stats()
+    assert (b.score().cpu().numpy() == sc).all()
+    a.close(); b.close()
+
+
 def test_desynchronised_batch_takes_the_general_path(oracle):
     """Games that start playing at different times (here: the contracts without a talon exchange play three cards before
     the others have exchanged) break the lock-step hint inside most warps; the per-warp vote must then send them through
