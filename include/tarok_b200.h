@@ -132,6 +132,9 @@ int tarok_exchange_synth(tarok_t* h, uint32_t random_group, void* stream);
 int tarok_legal_mask(tarok_t* h, uint64_t* out_dev, void* stream);   /* recomputed from the state */
 /* The four hands of every game indexed by SEAT (uint64 [4, n_alloc] on the device): TAROK_F_HANDS un-rotated. */
 int tarok_hands_by_seat(tarok_t* h, uint64_t* out_dev, void* stream);
+/* card_dev: uint8 [n_games], one card id per live game (entries of games not waiting for a card are ignored);
+   TAROK_CARD_SKIP leaves a live game untouched for this launch (advance a subset, e.g. SURVEY Q17). */
+#define TAROK_CARD_SKIP 0xFE
 int tarok_step(tarok_t* h, const uint8_t* card_dev, void* stream);   /* one card per live game */
 int tarok_step_random(tarok_t* h, void* stream);                     /* uniform-random legal card */
 int tarok_steps_random(tarok_t* h, uint32_t count, void* stream);    /* `count` back-to-back random steps */
@@ -178,6 +181,18 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
 #define TAROK_RECORD_BYTES 24
 int64_t tarok_pack_records(const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
                            const uint8_t* king_host /* or NULL */, uint64_t n, uint64_t* records_host /* [n,3] */);
+/* The same serialiser spread over `threads` host threads (std::thread; callers launched by torchrun run with
+   OMP_NUM_THREADS=1, so the count is explicit). */
+int64_t tarok_pack_records_mt(const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
+                              const uint8_t* king_host /* or NULL */, uint64_t n, uint64_t* records_host, int threads);
+/* tarok_rollout_host(fused = 1) that serialises the rows itself: each chunk of the upload/compute/download pipeline is
+   packed into records by `threads` host threads (a pool kept in the handle, pinned scratch owned by the handle) right
+   before its upload, so the caller keeps handing over what Igra.shuffle produces (Igra.py:65-73) and PCIe carries
+   24 B/deal.  Same outputs as tarok_rollout_host, bit-identical scores.  The pack runs on the calling thread + the pool:
+   the call returns when the last chunk is enqueued (device work still asynchronous on `stream`). */
+int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host,
+                              const uint8_t* declarer_host, const uint8_t* king_host, uint64_t first_global_game_id,
+                              int threads, int16_t* scores_host, int64_t* stats_host, void* stream);
 /* tarok_rollout_host(fused = 1) fed with deal records; same outputs, bit-identical scores. */
 int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t first_global_game_id,
                           int16_t* scores_host, int64_t* stats_host, void* stream);
@@ -192,6 +207,29 @@ int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t fir
    king [n_sel,4] (type 1), decl [n_sel,4], discard [n_sel,54], mozne [n_sel,54]; optional outputs may be NULL.
    Games that do not belong to the (net_type, rows) bucket get zeros and ok = 0. */
 int tarok_obs_shape(tarok_t* h, uint8_t* type_dev, uint8_t* rows_dev, void* stream);
+/* The same bucketing done on the device, for the `players` (1 or 4) players of Tarok.paralel_start -- the player of
+   seat s in game i is (s + i) % 4 (Tarok.py:34), every Nevronski_igralec keeps its own queues per net type
+   (Igralec.py:235-236,316-342): a stable counting sort of the games waiting for a card by
+   key = player * 28 + net_type * 7 + (T / 8 - 1).  sel_dev: int32 [n_games] receives the game indices grouped by key
+   (ascending key, ascending game index inside a key; only the first sum(counts) entries are written); selkey_dev
+   (uint8 [n_games], optional) the key of every listed position; counts_dev: uint32 [384] = 128 bucket sizes, 128 bucket
+   offsets into sel_dev (entry 255 = number of listed games), 128 bucket offsets in observation ROWS (sum of size * T over
+   the earlier buckets).  The caller reads counts once per step. */
+int tarok_obs_buckets(tarok_t* h, int players, int32_t* sel_dev, uint32_t* counts_dev, uint8_t* selkey_dev, void* stream);
+/* All buckets of a step in ONE launch each: tarok_obs_expand_buckets writes the inputs of every listed game into arenas
+   laid out so that each bucket's arrays are contiguous -- opp [rows,3,54] / hand [rows,54] at row counts[256 + key] +
+   (i - counts[128 + key]) * T for position i of sel_dev, the per-game vectors (talon [.,6,55], talon_klop [.,54], king [.,4],
+   decl [.,4], discard [.,54]) at index i -- i.e. bucket `key` reads opp_dev + counts[256+key]*162 as [size,T,3,54],
+   talon_dev + counts[128+key]*330 as [size,6,55] and so on.  Arena capacities: n_games * 56 rows / n_games entries.
+   tarok_select_action_buckets then applies tarok_select_action to every listed game with q_ptrs_dev[key] (a device table
+   of 128 device pointers, NULL = bucket not evaluated) = that bucket's [size,54] network output and
+   random_card4[player] = that player's epsilon (host array of 4). */
+int tarok_obs_expand_buckets(tarok_t* h, const int32_t* sel_dev, const uint8_t* selkey_dev, const uint32_t* counts_dev,
+                             uint64_t n_total, float* opp_dev, float* hand_dev, float* talon_dev, float* talon_klop_dev,
+                             float* king_dev, float* decl_dev, float* discard_dev, void* stream);
+int tarok_select_action_buckets(tarok_t* h, const float* const* q_ptrs_dev, const int32_t* sel_dev, const uint8_t* selkey_dev,
+                                const uint32_t* counts_dev, uint64_t n_total, const float* random_card4, uint8_t* card_dev,
+                                float* qmax_dev, void* stream);
 int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel_dev, uint64_t n_sel, float* opp_dev,
                      float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev, float* discard_dev,
                      float* mozne_dev, uint8_t* ok_dev, void* stream);

@@ -112,8 +112,12 @@ def build_full(n, seed):
     while len(recs) < n:
         perm = list(range(54))
         rng.shuffle(perm)
-        # bias towards low bids so that every contract incl. Klop shows up
-        idx = [rng.choice([0, 0, 0] + list(range(18))) for _ in range(4)]
+        # two thirds of the deals bid like Bot_igralec (Naprej 1/2, Tri / Dve / Ena 1/6 each, Igralec.py:151) -- the auctions
+        # in which Klop / Tri / Dve / Ena are decided --, one third uniformly over index2igra with extra weight on Naprej
+        if len(recs) % 3:
+            idx = [rng.choice([0, 0, 0, rng.randrange(1, 5), rng.randrange(5, 9), rng.randrange(9, 13)]) for _ in range(4)]
+        else:
+            idx = [rng.choice([0, 0, 0] + list(range(18))) for _ in range(4)]
         tips = [index2igra(i)[0] for i in idx]
         kings = [index2igra(i)[1] for i in idx]
         pol = H.Policy(intents=tips, king=kings, card="rand", discard="rand", group="rand", rng=rng)
@@ -125,7 +129,7 @@ def build_full(n, seed):
     return _pack(recs, dict(intent=np.array(intents, np.uint8)))
 
 
-def gen_full(n=400, seed=7):
+def gen_full(n=1500, seed=7):
     a = build_full(n, seed)
     np.savez_compressed(os.path.join(OUT, "traces_full.npz"), **a)
     print("traces_full.npz", len(a["contract"]), np.bincount(a["contract"], minlength=10))

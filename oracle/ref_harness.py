@@ -27,7 +27,20 @@ import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get("TAROK_REFERENCE_DIR", "/root/reference")
+def _find_reference():
+    """TAROK_REFERENCE_DIR, else ``baseline/_ref`` (the documented install target -- ``pip install --target baseline/_ref
+    /root/reference`` fails: the upstream tree has neither setup.py nor pyproject.toml), else ``/root/reference``."""
+    env = os.environ.get("TAROK_REFERENCE_DIR")
+    if env:
+        return env
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.path.join(root, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(cand, "Igra.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_DIR = _find_reference()
 
 _ref = None
 

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtarok_b200.so")
+# TAROK_B200_LIB selects a variant build of the same library (occupancy A/B experiments, tarok_b200/build.py --variant)
+LIB_PATH = os.environ.get("TAROK_B200_LIB") or os.path.join(_PKG, "libtarok_b200.so")
 
 # name -> (restype, argtypes); must list every function declared in include/tarok_b200.h
 _VP, _U64, _U32, _I = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
@@ -45,7 +46,12 @@ SIGNATURES = {
     "tarok_rollout_host": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _I, _VP, _VP, _VP]),
     "tarok_pack_records": (C.c_int64, [_VP, _VP, _VP, _VP, _U64, _VP]),
     "tarok_rollout_records": (_I, [_VP, _VP, _U64, _VP, _VP, _VP]),
+    "tarok_pack_records_mt": (C.c_int64, [_VP, _VP, _VP, _VP, _U64, _VP, _I]),
+    "tarok_rollout_host_packed": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _I, _VP, _VP, _VP]),
     "tarok_obs_shape": (_I, [_VP, _VP, _VP, _VP]),
+    "tarok_obs_buckets": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "tarok_obs_expand_buckets": (_I, [_VP, _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tarok_select_action_buckets": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP]),
     "tarok_obs_expand": (_I, [_VP, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tarok_obs_expand_at": (_I, [_VP, _I, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tarok_targets": (_I, [_VP, _VP, _U64, C.c_float, _VP, _VP, _VP, _VP]),

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 
+#include "tarok_host.h"
 #include "tarok_kernels.cuh"
 #include "tarok_obs.cuh"
 
@@ -32,6 +33,10 @@ struct tarok_env {
     // staging buffers of the host-buffer entry point
     uint8_t* st_perm; uint8_t* st_contract; uint8_t* st_declarer; uint8_t* st_king;
     int staging_ready;                         // set only after every stream / event / buffer below exists
+    tk::u32* cta_hist;                         // scratch of tarok_obs_buckets: [n_alloc / 256][128]
+    tarok_pack_pool* pool;                     // host threads of tarok_rollout_host_packed (lazily created)
+    uint64_t* pin_rec;                         // pinned scratch: the records of the chunk being uploaded [n_alloc, 3]
+    int pack_used[TK_MAX_CHUNKS];              // chunk c of the pinned scratch has an upload recorded on ev_up[c]
     cudaStream_t s_up, s_down;                 // internal copy streams of the chunked host pipeline
     cudaEvent_t ev_fork, ev_join, ev_up[TK_MAX_CHUNKS], ev_done[TK_MAX_CHUNKS];
     std::atomic<int> exports;
@@ -161,6 +166,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     h->s_up = h->s_down = nullptr; h->ev_fork = h->ev_join = nullptr; h->staging_ready = 0;
     memset(h->ev_up, 0, sizeof(h->ev_up)); memset(h->ev_done, 0, sizeof(h->ev_done));
+    h->cta_hist = nullptr; h->pool = nullptr; h->pin_rec = nullptr; memset(h->pack_used, 0, sizeof(h->pack_used));
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;
     tk::philox_keys_init(h->e.rng, seed);
@@ -220,6 +226,9 @@ int tarok_destroy(tarok_t* h) {
     cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats); cudaFree(h->e.tricklog);
     cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist); cudaFree(h->e.dpts);
     free_staging(h);
+    cudaFree(h->cta_hist);
+    tarok_pack_pool_destroy(h->pool);
+    if (h->pin_rec) cudaFreeHost(h->pin_rec);
     delete h;
     return 0;
 }
@@ -598,40 +607,56 @@ int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t fir
                               stats_host, s);
 }
 
-// Host-side serialiser (plain CPU code, no device work): permutation rows + forced contracts -> deal records.
-int64_t tarok_pack_records(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king,
-                           uint64_t n, uint64_t* records) {
-    if (!perm || !contract || !declarer || !records) return -1;
-    int64_t bad = 0;
-    for (uint64_t g = 0; g < n; g++) {
-        const uint8_t* row = perm + g * 54;
-        uint64_t w[3] = {0, 0, 0}, seen = 0, talon = 0;
-        for (int i = 0; i < 54; i++) {
-            const unsigned c = row[i], code = i < 48 ? (unsigned)i / 12u : 4u;
-            if (c >= 54) continue;
-            seen |= 1ull << c;
-            if (i >= 48) talon |= 1ull << c;
-            for (int p = 0; p < 3; p++) w[p] |= (uint64_t)((code >> p) & 1u) << c;
+// Third form of the host-buffer entry: the caller hands over permutation ROWS (what Igra.shuffle produces), the library
+// serialises each chunk into 24-byte deal records with `threads` host threads right before that chunk's upload, so PCIe
+// carries 24 instead of 57 bytes per deal and the packing of chunk c+1 overlaps the upload / play / download of chunk c.
+int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
+                              const uint8_t* king_host, uint64_t first_global_game_id, int threads, int16_t* scores_host,
+                              int64_t* stats_host, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!perm_host || !contract_host || !declarer_host) return fail(h, -1, "perm/contract/declarer host pointers are required");
+    if (threads < 1 || threads > 256) return fail(h, -1, "threads must be in 1..256");
+    DeviceGuard dg(h->device);
+    if (int rc = ensure_staging(h)) return rc;
+    if (!h->pin_rec) TK_CUDA(h, cudaHostAlloc((void**)&h->pin_rec, h->e.n_alloc * TAROK_RECORD_BYTES, cudaHostAllocDefault));
+    if (h->pool && tarok_pack_pool_threads(h->pool) != threads) { tarok_pack_pool_destroy(h->pool); h->pool = nullptr; }
+    if (!h->pool) h->pool = tarok_pack_pool_create(threads);
+    if (!h->pool) return fail(h, -4, "could not create the pack pool");
+    cudaStream_t s = S(stream);
+    TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
+    h->lock_plays = 0;
+    h->e.first_gid = first_global_game_id;
+    const u64 n = h->e.n, want = (u64)h->chunks;
+    const u64 chunk = (n >= (1ull << 18)) ? (((n + want - 1) / want + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
+    TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));
+    TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_fork, 0));
+    for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
+        const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
+        // the previous call's upload of this part of the pinned scratch must have left the host before it is overwritten
+        if (h->pack_used[c]) TK_CUDA(h, cudaEventSynchronize(h->ev_up[c]));
+        tarok_pack_pool_run(h->pool, perm_host, contract_host, declarer_host, king_host, b, e_, h->pin_rec);
+        TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * TAROK_RECORD_BYTES, (const uint8_t*)h->pin_rec + b * TAROK_RECORD_BYTES,
+                                   len * TAROK_RECORD_BYTES, cudaMemcpyHostToDevice, h->s_up));
+        TK_CUDA(h, cudaEventRecord(h->ev_up[c], h->s_up));
+        h->pack_used[c] = 1;
+        TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_up[c], 0));
+        tk::Env ev = h->e;
+        ev.n = e_;
+        tk::k_rollout_fused<tk::DEALS_RECORD><<<(unsigned)((len + tk::CTA - 1) / tk::CTA), tk::CTA, 0, s>>>(
+            ev, 0u, h->st_perm, nullptr, nullptr, nullptr, h->e.scores, 0, b);
+        TK_LAUNCH_OK(h);
+        if (scores_host) {
+            TK_CUDA(h, cudaEventRecord(h->ev_done[c], s));
+            TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_done[c], 0));
+            TK_CUDA(h, cudaMemcpyAsync((uint64_t*)scores_host + b, h->e.scores + b, len * 8, cudaMemcpyDeviceToHost, h->s_down));
         }
-        uint64_t ranks = 0;                                // position in the talon of its cards taken in ascending id
-        for (int i = 48; i < 54; i++) {
-            const unsigned c = row[i];
-            if (c >= 54) continue;
-            const int below = __builtin_popcountll(talon & ((1ull << c) - 1));
-            ranks |= (uint64_t)(i - 48) << (3 * below);
-        }
-        const unsigned k = (king && king[g] < 7u) ? king[g] : 7u;
-        if (seen != ((1ull << 54) - 1) || contract[g] > 15u || declarer[g] > 3u) {
-            // not a permutation / out-of-range contract: emit a record that decodes to an error game, like the row would
-            bad++;
-            w[0] = w[1] = w[2] = (1ull << 54) - 1;
-        }
-        w[0] |= (ranks & 0x1FF) << 54;
-        w[1] |= ((ranks >> 9) & 0x1FF) << 54;
-        w[2] |= (uint64_t)(contract[g] & 15u) << 54 | (uint64_t)(declarer[g] & 3u) << 58 | (uint64_t)(k & 7u) << 60;
-        records[g * 3] = w[0]; records[g * 3 + 1] = w[1]; records[g * 3 + 2] = w[2];
     }
-    return bad;
+    TK_CUDA(h, cudaEventRecord(h->ev_join, h->s_down));
+    TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
+    return 0;
 }
 
 // ---- observations ------------------------------------------------------------------------
@@ -641,6 +666,70 @@ int tarok_obs_shape(tarok_t* h, uint8_t* type_dev, uint8_t* rows_dev, void* stre
     if (!type_dev || !rows_dev) return fail(h, -1, "type_dev/rows_dev is null");
     DeviceGuard dg(h->device);
     tk::k_obs_shape<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, type_dev, rows_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_obs_buckets(tarok_t* h, int players, int32_t* sel_dev, uint32_t* counts_dev, uint8_t* selkey_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!sel_dev || !counts_dev) return fail(h, -1, "sel_dev/counts_dev is null");
+    if (players != 1 && players != 4) return fail(h, -1, "players must be 1 or 4");
+    DeviceGuard dg(h->device);
+    const unsigned n_cta = grid1(h->e.n_alloc);
+    if (!h->cta_hist) TK_CUDA(h, cudaMalloc((void**)&h->cta_hist, (size_t)n_cta * tk::BUCKETS * sizeof(u32)));
+    tk::k_bucket_hist<<<n_cta, tk::CTA, 0, S(stream)>>>(h->e, (u32)players, h->cta_hist);
+    TK_LAUNCH_OK(h);
+    tk::k_bucket_scan<<<1, tk::BUCKETS, 0, S(stream)>>>(h->cta_hist, n_cta, counts_dev);
+    TK_LAUNCH_OK(h);
+    tk::k_bucket_scatter<<<n_cta, tk::CTA, 0, S(stream)>>>(h->e, (u32)players, h->cta_hist, counts_dev, (int*)sel_dev, selkey_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_obs_expand_buckets(tarok_t* h, const int32_t* sel_dev, const uint8_t* selkey_dev, const uint32_t* counts_dev,
+                             uint64_t n_total, float* opp_dev, float* hand_dev, float* talon_dev, float* talon_klop_dev,
+                             float* king_dev, float* decl_dev, float* discard_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!h->e.hist) return fail(h, -1, "observations need TAROK_FLAG_HISTORY at tarok_create");
+    if (!sel_dev || !selkey_dev || !counts_dev) return fail(h, -1, "sel_dev/selkey_dev/counts_dev is null");
+    if (!opp_dev || !hand_dev || !talon_dev || !talon_klop_dev || !king_dev || !decl_dev || !discard_dev)
+        return fail(h, -1, "every arena pointer is required");
+    if ((((uintptr_t)opp_dev) | ((uintptr_t)hand_dev)) & 15u) return fail(h, -1, "opp_dev/hand_dev must be 16-byte aligned");
+    if ((((uintptr_t)talon_dev) | ((uintptr_t)talon_klop_dev) | ((uintptr_t)discard_dev)) & 7u)
+        return fail(h, -1, "talon/discard arenas must be 8-byte aligned");
+    if (n_total == 0) return 0;
+    if (n_total > h->e.n) return fail(h, -1, "n_total exceeds the number of games");
+    DeviceGuard dg(h->device);
+    tk::ObsArena a = {opp_dev, hand_dev, talon_dev, talon_klop_dev, king_dev, decl_dev, discard_dev};
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_obs_expand_all<<<(unsigned)((n_total + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, (const int*)sel_dev, selkey_dev, counts_dev, n_total, a);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+static inline u32 explore_threshold(float random_card) {
+    const double thr = (double)random_card * 4294967296.0;
+    return thr >= 4294967295.0 ? 0xFFFFFFFFu : (u32)thr;
+}
+
+int tarok_select_action_buckets(tarok_t* h, const float* const* q_ptrs_dev, const int32_t* sel_dev, const uint8_t* selkey_dev,
+                                const uint32_t* counts_dev, uint64_t n_total, const float* random_card4, uint8_t* card_dev,
+                                float* qmax_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!q_ptrs_dev || !sel_dev || !selkey_dev || !counts_dev || !card_dev || !random_card4)
+        return fail(h, -1, "q_ptrs_dev/sel_dev/selkey_dev/counts_dev/card_dev/random_card4 is null");
+    tk::Thresholds4 t4;
+    for (int p = 0; p < 4; p++) {
+        if (!(random_card4[p] >= 0.f && random_card4[p] <= 1.f)) return fail(h, -1, "random_card must be in [0,1]");
+        t4.t[p] = explore_threshold(random_card4[p]);
+    }
+    if (n_total == 0) return 0;
+    if (n_total > h->e.n) return fail(h, -1, "n_total exceeds the number of games");
+    DeviceGuard dg(h->device);
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_select_action_all<<<(unsigned)((n_total + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, q_ptrs_dev, (const int*)sel_dev, selkey_dev, counts_dev, n_total, t4, card_dev, qmax_dev);
     TK_LAUNCH_OK(h);
     return 0;
 }

@@ -21,6 +21,18 @@ namespace tk {
 constexpr int CTA = 256;
 constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane kernels
 
+// Resident CTAs per SM the register allocation is bounded for (A/B-measured on B200, profiles/r02/occupancy_ab.md; the
+// macros exist so that a variant library can be built with other bounds: python -m tarok_b200.build --variant ...).
+#ifndef TK_STEP_BLOCKS_RANDOM
+#define TK_STEP_BLOCKS_RANDOM 4
+#endif
+#ifndef TK_STEP_BLOCKS_FORCED
+#define TK_STEP_BLOCKS_FORCED 4
+#endif
+#ifndef TK_SETUP_BLOCKS
+#define TK_SETUP_BLOCKS 3
+#endif
+
 struct Env {
     u64* hands; u64* piles; u64* talon; u64* torder; u64* meta; u64* mask; u64* scores;
     uint8_t* hist; u64* hands0; u64* discard; float* qmax_hist; long long* stats;
@@ -42,6 +54,8 @@ __device__ __forceinline__ void st2(u64* p, u64 a, u64 b) { *reinterpret_cast<ul
 // ------------------------------------------------------------------------------------------------
 struct GameStat { bool fin, err; u64 packed; u32 contract, plays; u64 gid; };
 
+__device__ __forceinline__ u64 rotl64(u64 x, u32 r) { return r ? (x << r) | (x >> (64u - r)) : x; }
+
 template <int NG>
 __device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, const GameStat (&gs)[NG]) {
     __shared__ long long sh[S_USED];
@@ -49,18 +63,25 @@ __device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, 
     __syncthreads();
     const unsigned full = 0xFFFFFFFFu;
     int sc[4] = {0, 0, 0, 0}, pl[4] = {0, 0, 0, 0}, steps = 0;
+    // contract histogram: a warp holds at most 32 * NG <= 64 games, so one byte per contract cannot overflow when the
+    // three words (contracts 0-3, 4-7, 8-9) are summed over the warp with REDUX
+    u32 hist[3] = {0, 0, 0}, nfin = 0, nerr = 0;
 #pragma unroll
     for (int k = 0; k < NG; k++) {
-        int v[4];
+        const u64 by_seat = gs[k].fin ? gs[k].packed : 0ull;
+        // seat s of game i is player (s + i) % 4: the scores by player are the seat scores rotated by 16 * (i % 4) bits
+        const u64 by_player = rotl64(by_seat, 16u * ((u32)gs[k].gid & 3u));
 #pragma unroll
-        for (int s = 0; s < 4; s++) { v[s] = gs[k].fin ? (int)(int16_t)(gs[k].packed >> (16 * s)) : 0; sc[s] += v[s]; }
-        u32 rot = (u32)gs[k].gid & 3u;
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            u32 s = ((u32)p - rot) & 3u;
-            pl[p] += s == 0 ? v[0] : s == 1 ? v[1] : s == 2 ? v[2] : v[3];
+        for (int s = 0; s < 4; s++) {
+            sc[s] += (int)(int16_t)(by_seat >> (16 * s));
+            pl[s] += (int)(int16_t)(by_player >> (16 * s));
         }
         steps += (int)gs[k].plays;
+        const u32 c = gs[k].contract;
+        const u32 inc = (gs[k].fin && c < 10u) ? 1u << (8u * (c & 3u)) : 0u;
+        hist[0] += (c >> 2) == 0u ? inc : 0u; hist[1] += (c >> 2) == 1u ? inc : 0u; hist[2] += (c >> 2) == 2u ? inc : 0u;
+        nfin += gs[k].fin ? 1u : 0u;
+        nerr += gs[k].err ? 1u : 0u;
     }
     int mine = 0;
     const u32 lane = threadIdx.x & 31u;
@@ -71,21 +92,18 @@ __device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, 
         if (lane == (u32)(S_SEAT + s)) mine = a;
         if (lane == (u32)(S_PLAYER + s)) mine = b;
     }
-#pragma unroll
-    for (int c = 0; c < 10; c++) {
-        int a = 0;
-#pragma unroll
-        for (int k = 0; k < NG; k++) a += __popc(__ballot_sync(full, gs[k].fin && gs[k].contract == (u32)c));
-        if (lane == (u32)(S_CONTRACT + c)) mine = a;
-    }
     {
-        int a = 0, e = 0;
-#pragma unroll
-        for (int k = 0; k < NG; k++) { a += __popc(__ballot_sync(full, gs[k].fin)); e += __popc(__ballot_sync(full, gs[k].err)); }
-        int b = __reduce_add_sync(full, steps);
-        if (lane == S_FINISHED) mine = a;
+        const u32 h0 = __reduce_add_sync(full, hist[0]), h1 = __reduce_add_sync(full, hist[1]), h2 = __reduce_add_sync(full, hist[2]);
+        if (lane >= (u32)S_CONTRACT && lane < (u32)S_CONTRACT + 10u) {
+            const u32 c = lane - (u32)S_CONTRACT;
+            const u32 w = c < 4u ? h0 : c < 8u ? h1 : h2;
+            mine = (int)((w >> (8u * (c & 3u))) & 255u);
+        }
+        const u32 a = __reduce_add_sync(full, nfin | (nerr << 16));
+        const int b = __reduce_add_sync(full, steps);
+        if (lane == S_FINISHED) mine = (int)(a & 0xFFFFu);
         if (lane == S_STEPS) mine = b;
-        if (lane == S_ERRORS) mine = e;
+        if (lane == S_ERRORS) mine = (int)(a >> 16);
     }
     if (lane < S_USED && mine != 0) atomicAdd((unsigned long long*)&sh[lane], (unsigned long long)(long long)mine);
     __syncthreads();
@@ -585,7 +603,7 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
 // Philox draws as k_deal + k_begin<SYNTH> + k_exchange<SYNTH>, so the resulting state is bit-identical; the
 // state is written once instead of written, re-read and patched twice.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA) k_setup_synth(Env e, u32 mode) {
+__global__ void __launch_bounds__(CTA, TK_SETUP_BLOCKS) k_setup_synth(Env e, u32 mode) {
     const u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
     const u64 na = e.n_alloc;
     if (g >= na) return;
@@ -624,6 +642,9 @@ __global__ void __launch_bounds__(CTA) k_setup_synth(Env e, u32 mode) {
     e.dpts[g] = (uint8_t)card_points(dout);
 }
 
+// TAROK_CARD_SKIP (0xFE) as the supplied card leaves a live game untouched for this launch (a caller that advances only a
+// subset of the live games, e.g. the Solo_brez one-step lead of the reference's lock-step scheduler).
+constexpr u32 CARD_SKIP = 0xFEu;
 // The two card ids of a lane's game pair.  The caller's array holds exactly n_games bytes: never read past it.
 __device__ __forceinline__ u32 load_actions(const uint8_t* __restrict__ action, u32 g, u64 n) {
     if ((u64)g + 1 < n) return *reinterpret_cast<const unsigned short*>(action + g);
@@ -638,6 +659,17 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // Game indices are 32-bit inside the step kernels (n_alloc <= 2^29, enforced by tarok_create): one IMAD.WIDE
 // per address instead of 64-bit multiply chains.
+
+// The masks of a game pair after a step.  A live game that was told to skip (CARD_SKIP) keeps the mask it has; that
+// can only happen with externally supplied cards, and then the pair is written with scalar stores.
+template <bool RANDOM>
+__device__ __forceinline__ void store_masks(const Env& e, u32 g, const ulonglong2& m, bool a0, bool a1, u64 k0, u64 k1) {
+    const bool sk0 = !RANDOM && !a0 && (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && !((m.x >> M_ERR) & 1ull),
+               sk1 = !RANDOM && !a1 && (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && !((m.y >> M_ERR) & 1ull);
+    if (!sk0 && !sk1) { st2(e.mask + g, k0, k1); return; }
+    if (!sk0) e.mask[g] = k0;
+    if (!sk1) e.mask[g + 1] = k1;
+}
 
 // ---- general path: any mix of trick positions; the four slots of the game are in registers ----------------------
 template <bool RANDOM>
@@ -667,7 +699,7 @@ __device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u6
     } else {
         // append-only trick log (4 B, coalesced) instead of a scattered read-modify-write of the winner's pile;
         // k_score materialises the piles (and the Klop talon) from it
-        e.tricklog[(u64)(plays >> 2) * na + g] = log_entry((u32)(meta >> 32) & 0xFFFFFFu, pr.winner);   // 12 rows: 64-bit index
+        e.tricklog[(u64)(plays >> 2) * na + g] = log_entry((u32)(meta >> 32) & 0xFFFFFFu, pr.winner, (u32)meta);   // 12 rows: 64-bit index
         s3 = hand;                                                 // the trick closes from slot 3
         const u32 w = pr.winner_rel;                               // the winner's slot = its index in the trick
         if (w == 0u) {
@@ -697,7 +729,7 @@ __device__ __forceinline__ void step_pair_any(const Env& e, u32 g, ulonglong2& m
     if (a0) step_game_any<RANDOM>(e, g, m.x, s0.x, s1.x, s2.x, s3.x, act & 0xFFu, r0, k0);
     if (a1) step_game_any<RANDOM>(e, g + 1, m.y, s0.y, s1.y, s2.y, s3.y, act >> 8, r1, k1);
     st2(e.meta + g, m.x, m.y);
-    st2(e.mask + g, k0, k1);
+    store_masks<RANDOM>(e, g, m, a0, a1, k0, k1);
 }
 
 // General path for a lane pair.  HAVE = the trick position whose slots the caller has loaded already (a lock-step kernel
@@ -742,7 +774,7 @@ __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u
     if (POS < 3) {
         next_mask = legal_moves(n0, true, (u32)(meta >> 32) & 63u, kf);
     } else {
-        log_out = log_entry((u32)(meta >> 32) & 0xFFFFFFu, pr.winner);
+        log_out = log_entry((u32)(meta >> 32) & 0xFFFFFFu, pr.winner, (u32)meta);
         rotate4(n0, n1, n2, hm, pr.winner_rel);                    // slots 0..3 re-seated from the winner
         // the winner opens the next trick: everything it holds (minus the Klop-family pagat rule), nothing once finished
         next_mask = (((u32)meta >> M_PHASE) & 3u) == PH_PLAY ? legal_moves(n0, false, 0u, kf) : 0ull;
@@ -761,7 +793,8 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     if (POS == 3) { n1 = ld2(e.hands + (na + g)); n2 = ld2(e.hands + (2 * na + g)); }
     u32 act = 0;
     if (!RANDOM) act = load_actions(action, g, e.n);
-    const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
+    const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act & 0xFFu) != CARD_SKIP),
+               a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act >> 8) != CARD_SKIP);
     // plays sit in the top byte of the high word and the bits above them are clear for every live game
     const bool in_step = (!a0 || ((u32)(m.x >> 32) >> (M_PLAYS - 32)) == (u32)hint)
                       && (!a1 || ((u32)(m.y >> 32) >> (M_PLAYS - 32)) == (u32)hint);
@@ -786,13 +819,14 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
         else row[1] = l1;
     }
     st2(e.meta + g, m.x, m.y);
-    st2(e.mask + g, k0, k1);
+    store_masks<RANDOM>(e, g, m, a0, a1, k0, k1);
 }
 
 // `hint` = the number of plays every live game has made so far (lock-step pipelines know it on the host); POS = hint & 3
 // is compiled in (one kernel per trick position, each with its own register allocation); POS = -1: no hint.
 template <bool RANDOM, int POS>
-__global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restrict__ action, int hint) {
+__global__ void __launch_bounds__(CTA, RANDOM ? TK_STEP_BLOCKS_RANDOM : TK_STEP_BLOCKS_FORCED)
+k_step(Env e, const uint8_t* __restrict__ action, int hint) {
     pdl_launch_dependents();
     if constexpr (POS >= 0) {
         step_lock<RANDOM, POS>(e, action, hint);
@@ -802,7 +836,8 @@ __global__ void __launch_bounds__(CTA, 4) k_step(Env e, const uint8_t* __restric
         const ulonglong2 m = ld2(e.meta + g), z = {0, 0};
         u32 act = 0;
         if (!RANDOM) act = load_actions(action, g, e.n);
-        const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
+        const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act & 0xFFu) != CARD_SKIP),
+                   a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act >> 8) != CARD_SKIP);
         if (a0 || a1) step_pair_general<RANDOM, -1>(e, g, m, a0, a1, act, z, z, z, z);
     }
 }
@@ -874,7 +909,8 @@ __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __res
         if (!RANDOM) act = load_actions(action, g, e.n);
         mbar_wait(&full[s], (it >> 1) & 1u);
         ulonglong2 m = *reinterpret_cast<const ulonglong2*>(&stage[s].meta[l]);
-        const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY, a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY;
+        const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act & 0xFFu) != CARD_SKIP),
+                   a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act >> 8) != CARD_SKIP);
         if (a0 || a1) {
             const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(&stage[s].hands[0][l]),
                              s1 = *reinterpret_cast<const ulonglong2*>(&stage[s].hands[1][l]),
@@ -938,7 +974,8 @@ __device__ __forceinline__ void materialise(u64 meta, const uint2* log12, int wh
 // Roka.prestej is order independent -- sum(points) - 2 * floor(n / 3) - [n % 3 != 0] over the n cards of a pile
 // (Roka.py:55-98) -- so no bitboard is rebuilt: per trick one compare-and-add.
 //   Navadna / Solo (Navadna_igra.py:80-113): the team's points = the declarer's discards (`dpts`, k cards) + the tricks won by
-//     a seat of `ekipa`; the leftover talon joins them iff a lone declarer in a king game took the called king (Q7).
+//     a seat of `ekipa`; the leftover talon joins them iff a lone declarer in a king game took the called king (Q7) -- bit 31
+//     of the entry of the trick that held it.
 //   Klop (Klop.py:36-45): per seat; the talon card of tricks 1..6 (popped from the END, Klop.py:67-71) goes to the winner.
 //   Berac (Berac.py:33-44): the game stops on the declarer's first trick, so "the declarer took a trick" = "the last
 //     trick's winner is the declarer".
@@ -947,20 +984,21 @@ __device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int 
     const u32 contract = lo & 15u, decl = (lo >> M_DECL) & 3u, tricks = (lo >> M_TRICKS) & 15u;
     if (is_navadna(contract)) {
         const u32 team = (lo >> M_TEAM) & 15u, king = (lo >> M_KING) & 7u;
-        u32 pts = dpts, won = 0;
-        const bool lone = contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING;
-        const u32 kid = (king & 3u) * 8u + 7u;
-        bool took_king = false;
+        const u32 valid = (1u << tricks) - 1u;            // entries past the tricks played are stale
+        u32 pts = dpts, won = 0, kings = 0;
 #pragma unroll
         for (u32 k = 0; k < 12; k++) {
             const u32 entry = which ? log12[k].y : log12[k].x;
-            const bool mine = k < tricks && ((team >> ((entry >> 24) & 3u)) & 1u);
-            pts += mine ? (entry >> 26) & 31u : 0u;
-            won += mine ? 1u : 0u;
-            if (lone) took_king |= mine && trick_has(entry, kid);       // a lone declarer is the whole team
+            const u32 mine = (valid >> k) & (team >> ((entry >> 24) & 3u)) & 1u;     // a trick of the declarer's team
+            pts += mine * ((entry >> 26) & 31u);
+            won += mine;
+            kings |= mine ? entry : 0u;                                              // bit 31: the called king was in it
         }
         u32 n = 4u * won + (((lo >> M_GROUP) & 7u) != NO_GROUP ? talon_k(contract) : 0u);
-        if (lone && took_king) { pts += card_points(talon); n += (u32)__popcll(talon); }   // leftover talon (Q7)
+        // leftover talon to a lone declarer of a king game who took the called king (Q7); a lone declarer is the whole team
+        if (contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING && (kings >> 31)) {
+            pts += card_points(talon); n += (u32)__popcll(talon);
+        }
         return score_navadna_v(meta, prestej_pn((int)pts, (int)n));
     }
     if (is_berac(contract)) return score_berac(meta, ((lo >> M_WINNER) & 3u) == decl);
@@ -1050,7 +1088,7 @@ __device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, cons
     PlayResult pr;
     f.meta = play_card<false, J>(f.meta, hand, card, f.talon, f.order, pr);
     if (J == 3) {
-        if (log_row) *log_row = log_entry((u32)(f.meta >> 32) & 0xFFFFFFu, pr.winner);
+        if (log_row) *log_row = log_entry((u32)(f.meta >> 32) & 0xFFFFFFu, pr.winner, (u32)f.meta);
         const u64 b = pr.pile_bits;
         f.p0 |= pr.winner == 0 ? b : 0ull; f.p1 |= pr.winner == 1 ? b : 0ull;
         f.p2 |= pr.winner == 2 ? b : 0ull; f.p3 |= pr.winner == 3 ? b : 0ull;

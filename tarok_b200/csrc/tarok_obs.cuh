@@ -44,6 +44,81 @@ __global__ void __launch_bounds__(CTA) k_obs_shape(Env e, uint8_t* __restrict__ 
     rows_out[g] = live ? (uint8_t)padded_rows(history_len(meta)) : (uint8_t)0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Device-side bucket partition of the games waiting for a card -- what predict_igraj_karto does on the host with one
+// queue per net type (Igralec.py:316-342) for each of the four players of Tarok.paralel_start (player of seat s in game
+// i = (s + i) % 4, Tarok.py:34): key = (player, net type, T / 8 - 1), 4 x 4 x 7 = 112 buckets (+ key 127 = not waiting).
+// A stable counting sort in three launches: per-CTA histograms, one column scan per key, scatter.  The host reads the
+// 128 counts once per step (one small D2H) and then walks the non-empty ranges of `sel`.
+// ------------------------------------------------------------------------------------------------
+constexpr u32 BUCKETS = 128, BUCKET_DEAD = 127;
+
+__device__ __forceinline__ u32 bucket_key(const Env& e, u64 g, u32 players) {
+    if (g >= e.n) return BUCKET_DEAD;
+    const u64 meta = e.meta[g];
+    if (mget(meta, M_PHASE, 2) != PH_PLAY) return BUCKET_DEAD;
+    const u32 player = players > 1 ? (mover_of(meta) + (u32)(e.first_gid + g)) & 3u : 0u;
+    return player * 28u + net_type_of(mget(meta, M_CONTRACT, 4)) * 7u + (padded_rows(history_len(meta)) / 8u - 1u);
+}
+
+__global__ void __launch_bounds__(CTA) k_bucket_hist(Env e, u32 players, u32* __restrict__ cta_hist) {
+    __shared__ u32 sh[BUCKETS];
+    if (threadIdx.x < BUCKETS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 key = bucket_key(e, (u64)blockIdx.x * CTA + threadIdx.x, players);
+    // one shared atomic per distinct key per warp
+    const u32 peers = __match_any_sync(0xFFFFFFFFu, key);
+    if ((threadIdx.x & 31u) == (u32)__ffs(peers) - 1u) atomicAdd(&sh[key], (u32)__popc(peers));
+    __syncthreads();
+    if (threadIdx.x < BUCKETS) cta_hist[(u64)blockIdx.x * BUCKETS + threadIdx.x] = sh[threadIdx.x];
+}
+
+// One CTA of 128 threads: thread k turns column k of cta_hist into exclusive offsets (in CTA order) and its total into
+// counts[k]; then an exclusive scan over the keys gives the bucket bases, counts[128 + k] (counts[255] = all listed games),
+// and the bases in observation ROWS, counts[256 + k] = sum over earlier buckets of size * T (where a bucket's block of the
+// [rows, 3, 54] / [rows, 54] arenas starts).
+__global__ void __launch_bounds__(BUCKETS) k_bucket_scan(u32* __restrict__ cta_hist, u32 n_cta, u32* __restrict__ counts) {
+    __shared__ u32 tot[BUCKETS];
+    const u32 k = threadIdx.x;
+    u32 run = 0;
+    for (u32 c = 0; c < n_cta; c++) {
+        const u32 v = cta_hist[(u64)c * BUCKETS + k];
+        cta_hist[(u64)c * BUCKETS + k] = run;
+        run += v;
+    }
+    tot[k] = k == BUCKET_DEAD ? 0u : run;              // games not waiting for a card are not listed
+    __syncthreads();
+    if (k == 0) {
+        u32 base = 0, rows = 0;
+        for (u32 j = 0; j < BUCKETS; j++) {
+            const u32 v = tot[j];
+            counts[j] = v; counts[BUCKETS + j] = base; counts[2 * BUCKETS + j] = rows;
+            base += v; rows += v * 8u * (j % 7u + 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CTA) k_bucket_scatter(Env e, u32 players, const u32* __restrict__ cta_hist,
+                                                        const u32* __restrict__ counts, int* __restrict__ sel,
+                                                        uint8_t* __restrict__ selkey) {
+    __shared__ u32 warp_hist[CTA / 32][BUCKETS];
+    for (u32 i = threadIdx.x; i < (CTA / 32) * BUCKETS; i += CTA) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
+    const u32 key = bucket_key(e, g, players);
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 peers = __match_any_sync(0xFFFFFFFFu, key);
+    const u32 rank = (u32)__popc(peers & ((1u << lane) - 1u));                  // stable: lower lanes first
+    if (rank == 0) warp_hist[warp][key] = (u32)__popc(peers);
+    __syncthreads();
+    if (key == BUCKET_DEAD) return;
+    u32 before = 0;
+    for (u32 w = 0; w < warp; w++) before += warp_hist[w][key];
+    const u32 at = counts[BUCKETS + key] + cta_hist[(u64)blockIdx.x * BUCKETS + key] + before + rank;
+    sel[at] = (int)g;
+    if (selkey) selkey[at] = (uint8_t)key;
+}
+
 struct ObsOut {
     float* opp;      // [n_sel, T, 3, 54]
     float* hand;     // [n_sel, T, 54]
@@ -71,12 +146,8 @@ __device__ __forceinline__ void warp_bits(float* p, u64 bits, u32 lane) {       
 // `upto` < 0: the observation of the seat to move NOW.  `upto` = t >= 0: the observation the seat that made play t
 // had at that decision (history truncated to the first t plays) -- the `stanje` of a replay sample; the legal-mask
 // vector is not produced in that mode (it is not a network input, Igralec.py:333).
-__global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, const int* __restrict__ sel, u64 n_sel,
-                                                    ObsOut o, int upto) {
-    const u32 lane = threadIdx.x & 31u;
-    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;        // one warp per selected game
-    if (i >= n_sel) return;
-    const u64 g = sel ? (u64)sel[i] : i;
+// One warp expands one game; `o` points at THIS game's blocks (null = not wanted).
+__device__ __forceinline__ void obs_expand_game(const Env& e, u64 g, int net_type, u32 T, const ObsOut& o, int upto, u32 lane) {
     const u64 na = e.n_alloc;
     const bool in_range = g < e.n;
     u64 meta = in_range ? e.meta[g] : meta_pad();
@@ -92,16 +163,16 @@ __global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, 
     const u32 plays = mget(meta, M_PLAYS, 6);
     const bool match = mget(meta, M_PHASE, 2) == PH_PLAY && net_type_of(contract) == (u32)net_type
                     && padded_rows(history_len(meta)) == T;
-    float* opp = o.opp + i * (u64)T * 162u;
-    float* hand = o.hand + i * (u64)T * 54u;
+    float* opp = o.opp;
+    float* hand = o.hand;
     warp_zero4(opp, T * 162u, lane);                                 // T % 8 == 0: both blocks are 16-byte multiples
     warp_zero4(hand, T * 54u, lane);
-    if (o.talon && net_type != NET_BERAC) warp_zero(o.talon + i * (net_type == NET_KLOP ? 54u : 330u), net_type == NET_KLOP ? 54u : 330u, lane);
-    if (o.king && lane < 4) o.king[i * 4 + lane] = 0.f;
-    if (o.decl && lane < 4) o.decl[i * 4 + lane] = 0.f;
-    if (o.discard) warp_zero(o.discard + i * 54u, 54u, lane);
-    if (o.mozne) warp_zero(o.mozne + i * 54u, 54u, lane);
-    if (o.ok && lane == 0) o.ok[i] = match ? 1 : 0;
+    if (o.talon && net_type != NET_BERAC) warp_zero(o.talon, net_type == NET_KLOP ? 54u : 330u, lane);
+    if (o.king && lane < 4) o.king[lane] = 0.f;
+    if (o.decl && lane < 4) o.decl[lane] = 0.f;
+    if (o.discard) warp_zero(o.discard, 54u, lane);
+    if (o.mozne) warp_zero(o.mozne, 54u, lane);
+    if (o.ok && lane == 0) *o.ok = match ? 1 : 0;
     __syncwarp();                                                    // zero fill ordered before the ones below
     if (!match) return;
 
@@ -139,19 +210,63 @@ __global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, 
     const u64 order = e.torder[g];
     if (o.talon && net_type == NET_KLOP) {
         const u32 shown = min(mget(meta, M_TRICKS, 4), 6u);           // Klop.py:69 pops from the end
-        if (lane < shown) o.talon[i * 54u + ((order >> (6 * (5 - lane))) & 63ull)] = 1.f;
+        if (lane < shown) o.talon[(order >> (6 * (5 - lane))) & 63ull] = 1.f;
     } else if (o.talon && (net_type == NET_NAVADNA || net_type == NET_SOLO)) {
         const u32 grp = mget(meta, M_GROUP, 3), k = talon_k(contract);
         if (grp != NO_GROUP && lane < 6) {
-            float* row = o.talon + i * 330u + lane * 55u;
+            float* row = o.talon + lane * 55u;
             row[(order >> (6 * lane)) & 63ull] = 1.f;
             if (lane / k == grp) row[54] = 1.f;
         }
     }
-    if (o.king && lane == 0) { u32 kg = mget(meta, M_KING, 3); if (kg < 4) o.king[i * 4 + kg] = 1.f; }
-    if (o.decl && lane == 0) o.decl[i * 4 + (decl == self ? 3u : (decl < self ? decl : decl - 1))] = 1.f;
-    if (o.discard && self == decl && mget(meta, M_GROUP, 3) != NO_GROUP) warp_bits(o.discard + i * 54u, e.discard[g], lane);
-    if (o.mozne && upto < 0) warp_bits(o.mozne + i * 54u, e.mask[g], lane);
+    if (o.king && lane == 0) { u32 kg = mget(meta, M_KING, 3); if (kg < 4) o.king[kg] = 1.f; }
+    if (o.decl && lane == 0) o.decl[decl == self ? 3u : (decl < self ? decl : decl - 1)] = 1.f;
+    if (o.discard && self == decl && mget(meta, M_GROUP, 3) != NO_GROUP) warp_bits(o.discard, e.discard[g], lane);
+    if (o.mozne && upto < 0) warp_bits(o.mozne, e.mask[g], lane);
+}
+
+// One (net type, T) bucket: `o` holds the bases of the bucket's arrays, game i of the selection gets block i.
+__global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, const int* __restrict__ sel, u64 n_sel,
+                                                    ObsOut o, int upto) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;        // one warp per selected game
+    if (i >= n_sel) return;
+    const u64 g = sel ? (u64)sel[i] : i;
+    ObsOut m;
+    m.opp = o.opp + i * (u64)T * 162u;
+    m.hand = o.hand + i * (u64)T * 54u;
+    m.talon = o.talon ? o.talon + i * (net_type == NET_KLOP ? 54u : 330u) : nullptr;
+    m.king = o.king ? o.king + i * 4u : nullptr;
+    m.decl = o.decl ? o.decl + i * 4u : nullptr;
+    m.discard = o.discard ? o.discard + i * 54u : nullptr;
+    m.mozne = o.mozne ? o.mozne + i * 54u : nullptr;
+    m.ok = o.ok ? o.ok + i : nullptr;
+    obs_expand_game(e, g, net_type, T, m, upto, lane);
+}
+
+// EVERY bucket of a step in one launch (after tarok_obs_buckets): position i of `sel` belongs to bucket selkey[i] =
+// player * 28 + net * 7 + (T / 8 - 1); its rows go to the bucket's block of the arenas -- opp / hand at row counts[256 + key]
+// + (i - counts[128 + key]) * T, the per-game vectors at index i -- so that each bucket's inputs are contiguous tensors.
+struct ObsArena { float* opp; float* hand; float* talon; float* talon_klop; float* king; float* decl; float* discard; };
+
+__global__ void __launch_bounds__(CTA) k_obs_expand_all(Env e, const int* __restrict__ sel, const uint8_t* __restrict__ selkey,
+                                                        const u32* __restrict__ counts, u64 n_total, ObsArena a) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_total) return;
+    const u32 key = selkey[i];
+    const u32 net = (key % 28u) / 7u, T = 8u * (key % 7u + 1u);
+    const u64 row = (u64)counts[2 * BUCKETS + key] + (i - counts[BUCKETS + key]) * T;
+    ObsOut m;
+    m.opp = a.opp + row * 162u;
+    m.hand = a.hand + row * 54u;
+    m.talon = net == NET_KLOP ? a.talon_klop + i * 54u : net == NET_BERAC ? nullptr : a.talon + i * 330u;
+    m.king = net == NET_NAVADNA ? a.king + i * 4u : nullptr;
+    m.decl = net != NET_KLOP ? a.decl + i * 4u : nullptr;
+    m.discard = (net == NET_NAVADNA || net == NET_SOLO) ? a.discard + i * 54u : nullptr;
+    m.mozne = nullptr;
+    m.ok = nullptr;
+    obs_expand_game(e, (u64)sel[i], (int)net, T, m, -1, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -164,14 +279,8 @@ __global__ void __launch_bounds__(CTA) k_obs_expand(Env e, int net_type, u32 T, 
 // ------------------------------------------------------------------------------------------------
 enum : u32 { ST_EXPLORE = 8 };
 
-__global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __restrict__ q, const int* __restrict__ sel,
-                                                       u64 n_sel, u32 explore_threshold, uint8_t* __restrict__ card_out,
-                                                       float* __restrict__ qmax_out) {
-    const u32 lane = threadIdx.x & 31u;
-    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
-    if (i >= n_sel) return;
-    const u64 g = sel ? (u64)sel[i] : i;
-    if (g >= e.n) return;
+__device__ __forceinline__ void select_game(const Env& e, u64 g, const float* __restrict__ qrow, u32 explore_threshold,
+                                            uint8_t* __restrict__ card_out, float* __restrict__ qmax_out, u32 lane) {
     const u64 na = e.n_alloc;
     const u64 meta = e.meta[g];
     if (mget(meta, M_PHASE, 2) != PH_PLAY) { if (lane == 0) card_out[g] = 0xFF; return; }
@@ -196,7 +305,7 @@ __global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __res
                 for (u32 j = 0; j < 6; j++) if (((order >> (6 * j)) & 63ull) == c) tp = j;
                 key = 64u + tp;
             }
-            const float v = q[i * 54u + c];
+            const float v = qrow[c];
             if (v > best || (v == best && key < best_key)) { best = v; best_key = key; best_card = c; }
         }
     }
@@ -218,6 +327,35 @@ __global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __res
         if (qmax_out) qmax_out[g] = best;                         // next_Q_max = p[argmax card] (Igralec.py:351)
         if (e.qmax_hist) e.qmax_hist[(u64)mget(meta, M_PLAYS, 6) * na + g] = best;   // kept for the replay targets
     }
+}
+
+__global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __restrict__ q, const int* __restrict__ sel,
+                                                       u64 n_sel, u32 explore_threshold, uint8_t* __restrict__ card_out,
+                                                       float* __restrict__ qmax_out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_sel) return;
+    const u64 g = sel ? (u64)sel[i] : i;
+    if (g >= e.n) return;
+    select_game(e, g, q + i * 54u, explore_threshold, card_out, qmax_out, lane);
+}
+
+// The action selection of EVERY bucket of a step in one launch: qptr[key] = the [bucket size, 54] output of that bucket's
+// forward pass (a table of device pointers the host fills), thr4[player] = the player's epsilon as a 32-bit threshold.
+struct Thresholds4 { u32 t[4]; };
+__global__ void __launch_bounds__(CTA) k_select_action_all(Env e, const float* const* __restrict__ qptr,
+                                                           const int* __restrict__ sel, const uint8_t* __restrict__ selkey,
+                                                           const u32* __restrict__ counts, u64 n_total, Thresholds4 thr4,
+                                                           uint8_t* __restrict__ card_out, float* __restrict__ qmax_out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_total) return;
+    const u32 key = selkey[i];
+    const float* q = qptr[key];
+    if (!q) return;                                               // no forward was supplied for this bucket
+    const u32 p = key / 28u;
+    const u32 thr = p == 0 ? thr4.t[0] : p == 1 ? thr4.t[1] : p == 2 ? thr4.t[2] : thr4.t[3];
+    select_game(e, (u64)sel[i], q + (i - counts[BUCKETS + key]) * 54u, thr, card_out, qmax_out, lane);
 }
 
 // ------------------------------------------------------------------------------------------------

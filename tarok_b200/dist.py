@@ -49,8 +49,9 @@ def allreduce_stats(stats: torch.Tensor) -> torch.Tensor:
 
 
 class NcclComm:
-    """A raw NCCL communicator (ncclComm_t) for ``tarok_allreduce_stats``, bootstrapped over an initialised
-    ``torch.distributed`` group: rank 0's ncclUniqueId is broadcast, every rank calls ncclCommInitRank.  ctypes only."""
+    """A raw NCCL communicator (ncclComm_t) for ``tarok_allreduce_stats``.  With an initialised ``torch.distributed`` group
+    rank 0's ncclUniqueId is broadcast over it and every rank calls ncclCommInitRank; without one (a single process) it is a
+    one-rank communicator, so the C-ABI collective runs the same code path at every GPU count.  ctypes only."""
 
     def __init__(self, device: int):
         import ctypes as C
@@ -59,25 +60,30 @@ class NcclComm:
             _fields_ = [("internal", C.c_byte * 128)]
 
         self._C, self._nccl = C, C.CDLL("libnccl.so.2")
-        rank, world = dist.get_rank(), dist.get_world_size()
+        grouped = dist.is_available() and dist.is_initialized()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if grouped else (0, 1)
         uid = UniqueId()
         if rank == 0:
             self._ok(self._nccl.ncclGetUniqueId(C.byref(uid)))
-        buf = torch.tensor(list(bytes(uid.internal)), dtype=torch.uint8, device=torch.device("cuda", device))
-        dist.broadcast(buf, src=0)
-        C.memmove(C.byref(uid), bytes(buf.cpu().tolist()), 128)
+        if grouped and world > 1:
+            buf = torch.tensor(list(bytes(uid.internal)), dtype=torch.uint8, device=torch.device("cuda", device))
+            dist.broadcast(buf, src=0)
+            C.memmove(C.byref(uid), bytes(buf.cpu().tolist()), 128)
         self.comm = C.c_void_p()
         torch.cuda.set_device(device)
         self._nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
         self._ok(self._nccl.ncclCommInitRank(C.byref(self.comm), world, uid, rank))
+        self.world = world
 
     def _ok(self, rc):
         if rc != 0:
             raise RuntimeError("NCCL error %d" % rc)
 
-    def allreduce_stats(self, env) -> torch.Tensor:
-        """Sum of ``env``'s statistics vector over all ranks (int64 [32] on the device), via the C ABI."""
-        out = torch.empty(32, dtype=torch.int64, device=env.torch_device)
+    def allreduce_stats(self, env, out: torch.Tensor = None) -> torch.Tensor:
+        """Sum of ``env``'s statistics vector over all ranks (int64 [32] on the device), via the C ABI; enqueued on the
+        current stream, no synchronisation."""
+        if out is None:
+            out = torch.empty(32, dtype=torch.int64, device=env.torch_device)
         env._check(env._lib.tarok_allreduce_stats(env._h, self.comm, self._C.c_void_p(out.data_ptr()), env._stream()))
         return out
 

@@ -59,14 +59,14 @@ def _host_ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def pack_records(perm, contract, declarer, king=None, out=None):
+def pack_records(perm, contract, declarer, king=None, out=None, threads: int = 1):
     """Serialises permutation rows (uint8 [n,54], ``Igra.razdeli`` order) + forced contracts (uint8 [n] each) into
-    24-byte deal records (uint64 [n,3]) on the host.  Returns (records, number of invalid rows)."""
+    24-byte deal records (uint64 [n,3]) on the host, on ``threads`` host threads.  Returns (records, number of invalid rows)."""
     n = int(perm.shape[0])
     if out is None:
         out = torch.empty((n, 3), dtype=torch.int64).pin_memory() if torch.cuda.is_available() else torch.empty((n, 3), dtype=torch.int64)
-    bad = _lib.load().tarok_pack_records(_host_ptr(perm), _host_ptr(contract), _host_ptr(declarer), _host_ptr(king), n,
-                                         _host_ptr(out))
+    bad = _lib.load().tarok_pack_records_mt(_host_ptr(perm), _host_ptr(contract), _host_ptr(declarer), _host_ptr(king), n,
+                                            _host_ptr(out), int(threads))
     if bad < 0:
         raise ValueError("pack_records: perm, contract and declarer are required")
     return out, int(bad)
@@ -93,6 +93,7 @@ class TarokEnv:
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._views.clear()
+            self._bk = None
             rc = self._lib.tarok_destroy(self._h)
             if rc == 0:
                 self._h = C.c_void_p()
@@ -284,6 +285,15 @@ class TarokEnv:
             self._h, hp(perm), hp(contract), hp(declarer), hp(king), int(first_game_id), 1 if fused else 0,
             hp(scores_out), hp(stats_out), self._stream()))
 
+    def rollout_host_packed(self, perm, contract, declarer, king, scores_out, stats_out, first_game_id: int = 0,
+                            threads: int = 1):
+        """``rollout_host(fused=True)`` with the rows serialised into 24-byte records by ``threads`` host threads inside the
+        call, chunk by chunk ahead of each upload (PCIe carries 24 instead of 57 bytes per deal)."""
+        hp = _host_ptr
+        self._check(self._lib.tarok_rollout_host_packed(
+            self._h, hp(perm), hp(contract), hp(declarer), hp(king), int(first_game_id), int(threads),
+            hp(scores_out), hp(stats_out), self._stream()))
+
     def rollout_records(self, records, scores_out, stats_out, first_game_id: int = 0):
         """``rollout_host(fused=True)`` fed with 24-byte deal records (``pack_records``; layout in include/tarok_b200.h):
         the same deals, contracts and scores for 2.4x fewer bytes over PCIe."""
@@ -298,6 +308,47 @@ class TarokEnv:
         r = torch.empty(self.n, dtype=torch.uint8, device=self.torch_device)
         self._check(self._lib.tarok_obs_shape(self._h, C.c_void_p(t.data_ptr()), C.c_void_p(r.data_ptr()), self._stream()))
         return t, r
+
+    def obs_buckets(self, players: int = 4):
+        """Device-side bucketing of the games waiting for a card by (player, net type, T) -- ``predict_igraj_karto``'s
+        queues of the ``players`` (1 or 4) players of ``Tarok.paralel_start``.  Returns (sel int32 [n] on the device: game
+        indices grouped by key, counts: numpy uint32 [384] on the host = 128 bucket sizes, 128 offsets into ``sel`` (entry
+        255 = games listed), 128 offsets in observation rows); key = player * 28 + net_type * 7 + (T / 8 - 1).
+        One small device-to-host copy: the only synchronisation of a self-play step."""
+        if getattr(self, "_bk", None) is None:
+            self._bk = (torch.empty(self.n_alloc, dtype=torch.int32, device=self.torch_device),
+                        torch.zeros(384, dtype=torch.int32, device=self.torch_device),
+                        torch.zeros(384, dtype=torch.int32).pin_memory(),
+                        torch.empty(self.n_alloc, dtype=torch.uint8, device=self.torch_device),
+                        torch.zeros(128, dtype=torch.int64).pin_memory(),
+                        torch.zeros(128, dtype=torch.int64, device=self.torch_device))
+        sel, cnt, host, selkey = self._bk[:4]
+        self._check(self._lib.tarok_obs_buckets(self._h, int(players), C.c_void_p(sel.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                                C.c_void_p(selkey.data_ptr()), self._stream()))
+        host.copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream(self.torch_device).synchronize()
+        return sel, host.numpy().view(np.uint32)
+
+    def obs_expand_buckets(self, n_total: int, opp, hand, talon, talon_klop, king, decl, discard):
+        """ONE launch for every bucket of the last ``obs_buckets``: the arenas (flat fp32 CUDA tensors, capacities n * 56
+        rows / n entries) receive each bucket's inputs as contiguous blocks (layout in include/tarok_b200.h)."""
+        sel, cnt, _, selkey = self._bk[:4]
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._check(self._lib.tarok_obs_expand_buckets(self._h, p(sel), p(selkey), p(cnt), int(n_total), p(opp), p(hand), p(talon),
+                                                       p(talon_klop), p(king), p(decl), p(discard), self._stream()))
+
+    def select_action_buckets(self, n_total: int, q_by_key: dict, random_card4, cards, qmax=None):
+        """ONE launch of ``select_action`` for every bucket: ``q_by_key[key]`` = that bucket's [size, 54] fp32 network output
+        (contiguous CUDA tensors, kept alive by the caller until the stream has run the launch)."""
+        sel, cnt, _, selkey, ptr_h, ptr_d = self._bk
+        ptr_h.zero_()
+        for k, q in q_by_key.items():
+            ptr_h[k] = q.data_ptr()
+        ptr_d.copy_(ptr_h, non_blocking=True)
+        eps = (C.c_float * 4)(*[float(x) for x in random_card4])
+        p = lambda t: C.c_void_p(t.data_ptr())
+        self._check(self._lib.tarok_select_action_buckets(self._h, p(ptr_d), p(sel), p(selkey), p(cnt), int(n_total), eps, p(cards),
+                                                          p(qmax) if qmax is not None else None, self._stream()))
 
     def obs_expand(self, net_type: int, rows: int, sel=None, play=None):
         """The network inputs of ``Nevronski_igralec.stanje_v_vektor_rek_navadna`` for the seat to move of the
@@ -386,14 +437,15 @@ class TarokEnv:
                                                  C.c_void_p(game.data_ptr()), C.c_void_p(ok.data_ptr()), self._stream()))
         return [hand, talon, game], ok
 
-    def select_exchange(self, p, sel=None, random_card: float = 0.0):
-        """``menjaj_iz_talona`` (Igralec.py:365-385) from the exchange net's 60 outputs: (group uint8 [n], discard int64 [n])."""
+    def select_exchange(self, p, sel=None, random_card: float = 0.0, group_out=None, discard_out=None):
+        """``menjaj_iz_talona`` (Igralec.py:365-385) from the exchange net's 60 outputs: (group uint8 [n], discard int64 [n]);
+        ``group_out`` / ``discard_out`` let several calls (one per player) fill the same arrays."""
         n_sel, sel_ptr, keep = self._sel(sel)
         p = p.to(device=self.torch_device, dtype=torch.float32).contiguous()
         if tuple(p.shape) != (n_sel, 60):
             raise ValueError("p must have shape (n_sel, 60)")
-        group = torch.full((self.n,), 0xFF, dtype=torch.uint8, device=self.torch_device)
-        discard = torch.zeros(self.n, dtype=torch.int64, device=self.torch_device)
+        group = group_out if group_out is not None else torch.full((self.n,), 0xFF, dtype=torch.uint8, device=self.torch_device)
+        discard = discard_out if discard_out is not None else torch.zeros(self.n, dtype=torch.int64, device=self.torch_device)
         self._check(self._lib.tarok_select_exchange(self._h, C.c_void_p(p.data_ptr()), sel_ptr, n_sel, float(random_card),
                                                     C.c_void_p(group.data_ptr()), C.c_void_p(discard.data_ptr()), self._stream()))
         return group, discard

@@ -56,8 +56,9 @@ class Partije:
     players are called with."""
 
     def __init__(self, sedezi: List[List[Igralec]], ids: List[int], device: int = 0, seed: Optional[int] = None,
-                 prvi_id: int = 0):
+                 prvi_id: int = 0, reference_lockstep_quirks: bool = False):
         self.sedezi, self.ids, self.n = sedezi, list(ids), len(sedezi)
+        self.quirks = bool(reference_lockstep_quirks)
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")      # the reference is unseeded (main.py:174)
         self.env = E.TarokEnv(self.n, seed=seed, device=device, history=False)
@@ -221,12 +222,15 @@ class Partije:
             raise Exception("tarok_b200: player's hand and device hand differ")
         return mozne
 
-    def pripravi_poteze(self):
+    def pripravi_poteze(self, samo=None):
+        """``pripravi_igraj_karto`` for the seat to move of every live game (of the games in ``samo`` only, if given)."""
         m = self._beri_meta()
         maske = _u64(self.env.mask[: self.n])
         self._mozne = {}
         for g in np.nonzero(m["faza"] == E.PH_PLAY)[0]:
             g = int(g)
+            if samo is not None and g not in samo:
+                continue
             idg, igralci = self.ids[g], self.sedezi[g]
             if self.tip[g] == Tip_igre.Odprti_berac and m["stihi"][g] == 1 and m["pos"][g] == 0:
                 berac = igralci[self.kdo[g]]
@@ -240,7 +244,9 @@ class Partije:
             igralec.pripravi_igraj_karto(deepcopy(self.stih[g]), mozne, self.zgodovina[g], idg)
 
     def igraj_poteze(self):
-        karte = np.zeros(self.n, np.uint8)
+        """``igraj_karto`` for every game prepared by the last ``pripravi_poteze``; the other live games keep their state
+        (TAROK_CARD_SKIP)."""
+        karte = np.full(self.n, 0xFE, np.uint8)
         for g, (igralec, mozne, kopija) in self._mozne.items():
             idg = self.ids[g]
             karta = igralec.igraj_karto(deepcopy(self.stih[g]), mozne, self.zgodovina[g], idg)
@@ -282,16 +288,30 @@ class Partije:
     def zive(self) -> bool:
         return bool((self._meta["faza"] == E.PH_PLAY).any())
 
+    def _solo_brez(self):
+        return {g for g in range(self.n) if self.tip[g] == Tip_igre.Solo_brez}
+
     def faze(self):
         """Generator over the lock-step phases; yields the reference's marker strings and finally the
-        list of per-game result dicts."""
+        list of per-game result dicts.
+
+        ``reference_lockstep_quirks``: in the reference a Solo_brez game yields one item fewer (Navadna_igra.py:48,59-68: no
+        'Pripravljen menjat'), so under ``Tarok.paralel_start`` (Tarok.py:42-56) it runs ONE STEP AHEAD of every other game:
+        its first card is prepared while the others prepare the talon exchange and played while they exchange, and it
+        finishes one iteration early.  With the flag the phases reproduce exactly that interleaving (which
+        callbacks fall between which predict_* calls); without it every game plays card t in iteration t."""
         self.razdeli()
         self.pripravi_licitiranje()
         yield "Pripravljen_licitirat"
         self.licitacija()
         self.pripravi_menjavo()
+        naprej = self._solo_brez() if self.quirks else set()
+        if naprej:
+            self.pripravi_poteze(samo=naprej)            # Tarok.py:42: next(inner) of a Solo_brez game reaches its first card
         yield "Pripravljen menjat"
         self.menjaj()
+        if naprej:
+            self.igraj_poteze()                          # Tarok.py:45: ... and plays it while the others exchange
         self.pripravi_poteze()
         while self.zive():
             yield "Pripravljen igrat karto"
@@ -385,8 +405,10 @@ class Tarok:
 
     izpis = True
 
-    def __init__(self, igralci, st_iger=None, device=0, seed=None):
+    def __init__(self, igralci, st_iger=None, device=0, seed=None, reference_lockstep_quirks=False):
         assert len({i.ime for i in igralci}) == 4
+        #: reproduce the reference scheduler's Solo_brez one-step lead (see Partije.faze)
+        self.reference_lockstep_quirks = bool(reference_lockstep_quirks)
         self.igralci = igralci
         self.rezultati = {i: 0 for i in igralci}
         self.radelci = {i: 0 for i in igralci}
@@ -434,7 +456,8 @@ class Tarok:
             self._na_napravi(self.st_iger, rotacija=True)
         else:
             sedezi = [self.igralci[i % 4:] + self.igralci[:i % 4] for i in self.stream()]
-            r = _pozeni(Partije(sedezi, list(range(self.st_iger)), device=self.device, seed=self.seed), self.igralci)
+            r = _pozeni(Partije(sedezi, list(range(self.st_iger)), device=self.device, seed=self.seed,
+                                reference_lockstep_quirks=self.reference_lockstep_quirks), self.igralci)
             for d in r:
                 for k, v in d.items():
                     self.rezultati[k] += v
