@@ -99,7 +99,7 @@ class ClockSampler:
                 self.samples.append((sm, self.mx, rs, ut))
             except Exception:
                 break
-            time.sleep(0.025)          # 40 Hz: NVML queries share the driver with the CUDA calls of the e2e legs
+            time.sleep(0.05)           # 20 Hz: NVML queries share the driver with the CUDA calls of the e2e legs
 
     def _nvml_result(self):
         import pynvml as N

@@ -26,6 +26,7 @@ struct tarok_env {
     int pdl;                                   // chain play_step launches with programmatic dependent launch
     int lockstep;                              // pass the lock-step hint to play_step (specialised per trick position)
     int lock_plays;                            // plays made by every live game since the last deal, -1 = unknown
+    int lazy_mask;                             // chains of random steps write legal masks in their last launch only (default on)
     int materialise;                           // tarok_score writes the materialised piles / talon back (default on)
     int chunks;                                // upload/compute/download pipeline depth of the host-buffer entries
     u32 flags;
@@ -102,7 +103,7 @@ struct DeviceGuard {
 // play_step launcher.  Default: the plain kernel, one 512-game tile per CTA, compiled per trick position for lock-step
 // batches (the hint) with programmatic dependent launch; TAROK_OPT_STEP_IMPL=2 selects the persistent TMA-staged variant
 // (one CTA per resident slot, 4 per SM), which measures slower on B200 and is kept for comparison (tools/step_ab.py).
-template <bool RANDOM>
+template <bool RANDOM, bool MASK = true>
 static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     const unsigned tiles = grid2(h->e.n_alloc);
     const unsigned resident = (unsigned)h->sm_count * 4u;
@@ -121,16 +122,27 @@ static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     else {
         const int hint = h->lockstep ? h->lock_plays : -1;
         switch (hint >= 0 ? (hint & 3) : 4) {
-            case 0: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 0>, h->e, action, hint); break;
-            case 1: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 1>, h->e, action, hint); break;
-            case 2: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 2>, h->e, action, hint); break;
-            case 3: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 3>, h->e, action, hint); break;
-            default: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, -1>, h->e, action, hint); break;
+            case 0: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 0, MASK>, h->e, action, hint); break;
+            case 1: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 1, MASK>, h->e, action, hint); break;
+            case 2: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 2, MASK>, h->e, action, hint); break;
+            case 3: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 3, MASK>, h->e, action, hint); break;
+            default: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, -1, MASK>, h->e, action, hint); break;
         }
     }
     // lock-step bookkeeping (only a hint to the kernel, which verifies it per warp): every live game has made
     // `lock_plays` plays since the last deal; one more after this launch
     if (h->lock_plays >= 0) h->lock_plays = h->lock_plays < 47 ? h->lock_plays + 1 : -1;
+}
+
+// `count` back-to-back in-kernel random steps.  Only the last launch writes legal masks (nobody can observe the interior
+// ones); with the TMA-staged implementation or the eager-mask option every launch does.
+static int random_chain(tarok_env* h, uint32_t count, cudaStream_t s) {
+    for (uint32_t t = 0; t < count; t++) {
+        if (t + 1 < count && h->lazy_mask && h->step_impl != 2) launch_step<true, false>(h, nullptr, s);
+        else launch_step<true, true>(h, nullptr, s);
+        TK_LAUNCH_OK(h);
+    }
+    return 0;
 }
 
 extern "C" {
@@ -141,6 +153,7 @@ int tarok_set_option(tarok_t* h, int option, int64_t value) {
     if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
     if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
     if (option == TAROK_OPT_MATERIALISE && (value == 0 || value == 1)) { h->materialise = (int)value; return 0; }
+    if (option == TAROK_OPT_LAZY_MASK && (value == 0 || value == 1)) { h->lazy_mask = (int)value; return 0; }
     if (option == TAROK_OPT_CHUNKS && value >= 1 && value <= TK_MAX_CHUNKS) { h->chunks = (int)value; return 0; }
     return fail(h, -1, "unknown option %d / value %lld", option, (long long)value);
 }
@@ -162,7 +175,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     tarok_env* h = new (std::nothrow) tarok_env();
     if (!h) return fail(nullptr, -4, "out of host memory");
     memset(&h->e, 0, sizeof(h->e));
-    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->materialise = 1; h->chunks = 8; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
+    h->device = device; h->sm_count = prop.multiProcessorCount; h->step_impl = 0; h->pdl = 1; h->lockstep = 1; h->lock_plays = -1; h->lazy_mask = 1; h->materialise = 1; h->chunks = 8; h->flags = flags; h->launches = 0; h->exports = 0; h->err[0] = 0;
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     h->s_up = h->s_down = nullptr; h->ev_fork = h->ev_join = nullptr; h->staging_ready = 0;
     memset(h->ev_up, 0, sizeof(h->ev_up)); memset(h->ev_done, 0, sizeof(h->ev_done));
@@ -377,11 +390,7 @@ int tarok_step_random(tarok_t* h, void* stream) {
 int tarok_steps_random(tarok_t* h, uint32_t count, void* stream) {
     TK_CHECK_HANDLE(h);
     DeviceGuard dg(h->device);
-    for (uint32_t t = 0; t < count; t++) {
-        launch_step<true>(h, nullptr, S(stream));
-        TK_LAUNCH_OK(h);
-    }
-    return 0;
+    return random_chain(h, count, S(stream));
 }
 
 // ---- score / stats ----------------------------------------------------------------------------------
@@ -442,10 +451,7 @@ int tarok_allreduce_stats(tarok_t* h, void* nccl_comm, int64_t* out_dev, void* s
 static int play_out_stepwise(tarok_t* h, uint32_t random_group, void* stream) {
     tk::k_exchange<true><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, random_group, nullptr, nullptr);
     TK_LAUNCH_OK(h);
-    for (int t = 0; t < 48; t++) {
-        launch_step<true>(h, nullptr, S(stream));
-        TK_LAUNCH_OK(h);
-    }
+    if (int rc = random_chain(h, 48, S(stream))) return rc;
     if (h->materialise) tk::k_score<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
     else tk::k_score<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
     TK_LAUNCH_OK(h);
@@ -470,10 +476,7 @@ int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game
     int rc = tarok_setup_synth(h, mode, first_global_game_id, stream);
     if (rc) return rc;
     DeviceGuard dg(h->device);
-    for (int t = 0; t < 48; t++) {
-        launch_step<true>(h, nullptr, S(stream));
-        TK_LAUNCH_OK(h);
-    }
+    if (int rc = random_chain(h, 48, S(stream))) return rc;
     if (h->materialise) tk::k_score<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
     else tk::k_score<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
     TK_LAUNCH_OK(h);

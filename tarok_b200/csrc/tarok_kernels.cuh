@@ -18,16 +18,19 @@
 
 namespace tk {
 
-constexpr int CTA = 256;
+#ifndef TK_CTA
+#define TK_CTA 256
+#endif
+constexpr int CTA = TK_CTA;
 constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane kernels
 
 // Resident CTAs per SM the register allocation is bounded for (A/B-measured on B200, profiles/r02/occupancy_ab.md; the
 // macros exist so that a variant library can be built with other bounds: python -m tarok_b200.build --variant ...).
 #ifndef TK_STEP_BLOCKS_RANDOM
-#define TK_STEP_BLOCKS_RANDOM 4
+#define TK_STEP_BLOCKS_RANDOM 5   // 48 registers (a few spilled words at the trick-closing position): 69.2 -> 66.1 us at 8 M deals, = at 1 M
 #endif
 #ifndef TK_STEP_BLOCKS_FORCED
-#define TK_STEP_BLOCKS_FORCED 4
+#define TK_STEP_BLOCKS_FORCED 5   // 46-48 registers: 8.63 -> 8.22 us per launch at 1 M deals (6 blocks = 40 registers spills and loses)
 #endif
 #ifndef TK_SETUP_BLOCKS
 #define TK_SETUP_BLOCKS 3
@@ -190,7 +193,9 @@ __host__ __device__ constexpr u64 deal_bounds8(int w) {
 struct DealWalk { u32 T, acc; u32 rev[7]; };
 
 __device__ __forceinline__ void deal_place(DealWalk& d, int c, u32 r) {             // c is a compile-time constant at every call
-    const u32 q = ((r * 0xFEFEFEFFu + d.T) >> 7) & 0x01010101u;                     // byte j = (r < T_j)
+    // byte j = (r < T_j); the shift by 7 is written as a multiply-high by 2^25: the integer ALU pipe is what bounds this
+    // kernel, the FMA pipe (IMAD / IMAD.HI) has room
+    const u32 q = __umulhi(r * 0xFEFEFEFFu + d.T, 1u << 25) & 0x01010101u;
     d.T -= q;
     d.acc = d.acc * 2u + q;
     if ((c & 7) == 7) { d.rev[c >> 3] = __brev(d.acc); d.acc = 0; }                 // byte 3 - j: bit jj = q_j of card 8 * (c >> 3) + jj
@@ -662,8 +667,15 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // The masks of a game pair after a step.  A live game that was told to skip (CARD_SKIP) keeps the mask it has; that
 // can only happen with externally supplied cards, and then the pair is written with scalar stores.
-template <bool RANDOM>
+// MASK = false (interior launches of a chain of in-kernel random steps, whose masks nobody can observe): nothing is
+// computed or stored, except that a game FINISHING in this launch gets its mask cleared -- no later launch touches it.
+template <bool RANDOM, bool MASK>
 __device__ __forceinline__ void store_masks(const Env& e, u32 g, const ulonglong2& m, bool a0, bool a1, u64 k0, u64 k1) {
+    if (!MASK) {
+        if (a0 && (((u32)m.x >> M_PHASE) & 3u) != PH_PLAY) e.mask[g] = 0ull;
+        if (a1 && (((u32)m.y >> M_PHASE) & 3u) != PH_PLAY) e.mask[g + 1] = 0ull;
+        return;
+    }
     const bool sk0 = !RANDOM && !a0 && (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && !((m.x >> M_ERR) & 1ull),
                sk1 = !RANDOM && !a1 && (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && !((m.y >> M_ERR) & 1ull);
     if (!sk0 && !sk1) { st2(e.mask + g, k0, k1); return; }
@@ -672,7 +684,7 @@ __device__ __forceinline__ void store_masks(const Env& e, u32 g, const ulonglong
 }
 
 // ---- general path: any mix of trick positions; the four slots of the game are in registers ----------------------
-template <bool RANDOM>
+template <bool RANDOM, bool MASK>
 __device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u64 s0, u64 s1, u64 s2, u64 s3, u32 card,
                                               const Words4& rnd, u64& next_mask) {
     const u32 na = (u32)e.n_alloc;
@@ -695,7 +707,7 @@ __device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u6
     if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
     if (!pr.trick_done) {                                          // same trick goes on: next slot follows the same lead
         e.hands[pos * na + g] = hand;
-        next_mask = legal_moves(sel4(s0, s1, s2, s3, (pos + 1u) & 3u), true, (u32)(meta >> 32) & 63u, kf);
+        if (MASK) next_mask = legal_moves(sel4(s0, s1, s2, s3, (pos + 1u) & 3u), true, (u32)(meta >> 32) & 63u, kf);
     } else {
         // append-only trick log (4 B, coalesced) instead of a scattered read-modify-write of the winner's pile;
         // k_score materialises the piles (and the Klop talon) from it
@@ -708,7 +720,7 @@ __device__ __forceinline__ void step_game_any(const Env& e, u32 g, u64& meta, u6
             rotate4(s0, s1, s2, s3, w);
             e.hands[g] = s0; e.hands[na + g] = s1; e.hands[2 * na + g] = s2; e.hands[3 * na + g] = s3;
         }
-        next_mask = mask_for_mover(meta, s0);
+        if (MASK) next_mask = mask_for_mover(meta, s0);
     }
 }
 
@@ -720,38 +732,40 @@ __device__ __forceinline__ void pair_blocks(const Env& e, u32 g, u32 t0, u32 t1,
     if (((gid & 1ull) || t0 != t1) && a1) r1 = play_block(e.rng, gid + 1, t1);
 }
 
-template <bool RANDOM>
+template <bool RANDOM, bool MASK = true>
 __device__ __forceinline__ void step_pair_any(const Env& e, u32 g, ulonglong2& m, bool a0, bool a1, ulonglong2 s0,
                                               ulonglong2 s1, ulonglong2 s2, ulonglong2 s3, u32 act) {
     Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
     if (RANDOM) pair_blocks(e, g, ((u32)(m.x >> 32) >> (M_PLAYS - 30)) & 15u, ((u32)(m.y >> 32) >> (M_PLAYS - 30)) & 15u, a1, r0, r1);
     u64 k0 = 0, k1 = 0;
-    if (a0) step_game_any<RANDOM>(e, g, m.x, s0.x, s1.x, s2.x, s3.x, act & 0xFFu, r0, k0);
-    if (a1) step_game_any<RANDOM>(e, g + 1, m.y, s0.y, s1.y, s2.y, s3.y, act >> 8, r1, k1);
+    if (a0) step_game_any<RANDOM, MASK>(e, g, m.x, s0.x, s1.x, s2.x, s3.x, act & 0xFFu, r0, k0);
+    if (a1) step_game_any<RANDOM, MASK>(e, g + 1, m.y, s0.y, s1.y, s2.y, s3.y, act >> 8, r1, k1);
     st2(e.meta + g, m.x, m.y);
-    store_masks<RANDOM>(e, g, m, a0, a1, k0, k1);
+    store_masks<RANDOM, MASK>(e, g, m, a0, a1, k0, k1);
 }
 
 // General path for a lane pair.  HAVE = the trick position whose slots the caller has loaded already (a lock-step kernel
 // whose warp vote failed: slot HAVE in `hm`, slot HAVE + 1 in `n0`, for HAVE == 3 also slots 1, 2 in `n1`, `n2`), or -1.
 // Using them here also keeps those loads above the vote: one memory round trip on the lock-step side.
-template <bool RANDOM, int HAVE>
+// MASK = false: the caller did not load the next seat's slot (n0) for HAVE < 3; it is fetched here.
+template <bool RANDOM, int HAVE, bool MASK = true>
 __device__ __forceinline__ void step_pair_general(const Env& e, u32 g, ulonglong2 m, bool a0, bool a1, u32 act,
                                                   ulonglong2 hm, ulonglong2 n0, ulonglong2 n1, ulonglong2 n2) {
     const u32 na = (u32)e.n_alloc;
     ulonglong2 s0, s1, s2, s3;
+    if (HAVE >= 0 && HAVE < 3 && !MASK) n0 = ld2(e.hands + ((HAVE + 1) * na + g));
     if (HAVE == 0) { s0 = hm; s1 = n0; s2 = ld2(e.hands + (2 * na + g)); s3 = ld2(e.hands + (3 * na + g)); }
     else if (HAVE == 1) { s1 = hm; s2 = n0; s0 = ld2(e.hands + g); s3 = ld2(e.hands + (3 * na + g)); }
     else if (HAVE == 2) { s2 = hm; s3 = n0; s0 = ld2(e.hands + g); s1 = ld2(e.hands + (na + g)); }
     else if (HAVE == 3) { s3 = hm; s0 = n0; s1 = n1; s2 = n2; }
     else { s0 = ld2(e.hands + g); s1 = ld2(e.hands + (na + g)); s2 = ld2(e.hands + (2 * na + g)); s3 = ld2(e.hands + (3 * na + g)); }
-    step_pair_any<RANDOM>(e, g, m, a0, a1, s0, s1, s2, s3, act);
+    step_pair_any<RANDOM, MASK>(e, g, m, a0, a1, s0, s1, s2, s3, act);
 }
 
 // ---- lock-step path: every live game of the warp has made `hint` plays, so the trick position POS = hint & 3 is a
 // compile-time constant: the mover is slot POS for everybody, the trick-position arithmetic and the trick-end branch fold.
 // hm = slot POS (the mover's hand); POS < 3: n0 = slot POS + 1 (the next seat); POS == 3: n0, n1, n2 = slots 0, 1, 2.
-template <bool RANDOM, int POS>
+template <bool RANDOM, int POS, bool MASK>
 __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u64& hm, u64& n0, u64& n1, u64& n2, u32 card,
                                                const Words4& rnd, u64& next_mask, u32& log_out) {
     const u32 na = (u32)e.n_alloc;
@@ -772,16 +786,16 @@ __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u
     }
     if (e.hist) e.hist[(u64)plays * na + g] = (uint8_t)((mover << 6) | card);
     if (POS < 3) {
-        next_mask = legal_moves(n0, true, (u32)(meta >> 32) & 63u, kf);
+        if (MASK) next_mask = legal_moves(n0, true, (u32)(meta >> 32) & 63u, kf);
     } else {
         log_out = log_entry((u32)(meta >> 32) & 0xFFFFFFu, pr.winner, (u32)meta);
         rotate4(n0, n1, n2, hm, pr.winner_rel);                    // slots 0..3 re-seated from the winner
         // the winner opens the next trick: everything it holds (minus the Klop-family pagat rule), nothing once finished
-        next_mask = (((u32)meta >> M_PHASE) & 3u) == PH_PLAY ? legal_moves(n0, false, 0u, kf) : 0ull;
+        if (MASK) next_mask = (((u32)meta >> M_PHASE) & 3u) == PH_PLAY ? legal_moves(n0, false, 0u, kf) : 0ull;
     }
 }
 
-template <bool RANDOM, int POS>
+template <bool RANDOM, int POS, bool MASK>
 __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restrict__ action, int hint) {
     const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
     const u32 na = (u32)e.n_alloc;                 // the grid covers n_alloc exactly: no partial warps
@@ -789,7 +803,8 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     // every load is issued before the first use: one memory round trip per step
     ulonglong2 m = ld2(e.meta + g);
     ulonglong2 hm = ld2(e.hands + (POS * na + g));
-    ulonglong2 n0 = ld2(e.hands + (((POS + 1) & 3) * na + g)), n1 = {0, 0}, n2 = {0, 0};
+    ulonglong2 n0 = {0, 0}, n1 = {0, 0}, n2 = {0, 0};
+    if (MASK || POS == 3) n0 = ld2(e.hands + (((POS + 1) & 3) * na + g));     // the next seat's slot is only read for its mask
     if (POS == 3) { n1 = ld2(e.hands + (na + g)); n2 = ld2(e.hands + (2 * na + g)); }
     u32 act = 0;
     if (!RANDOM) act = load_actions(action, g, e.n);
@@ -800,14 +815,14 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
                       && (!a1 || ((u32)(m.y >> 32) >> (M_PLAYS - 32)) == (u32)hint);
     const bool lock = __all_sync(0xFFFFFFFFu, in_step);            // the hint is only a hint: each warp checks it
     if (!a0 && !a1) return;
-    if (!lock) { step_pair_general<RANDOM, POS>(e, g, m, a0, a1, act, hm, n0, n1, n2); return; }
+    if (!lock) { step_pair_general<RANDOM, POS, MASK>(e, g, m, a0, a1, act, hm, n0, n1, n2); return; }
     Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
     // the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used
     if (RANDOM) pair_blocks(e, g, (u32)hint >> 2, (u32)hint >> 2, a1, r0, r1);
     u64 k0 = 0, k1 = 0;
     u32 l0 = 0, l1 = 0;                            // trick-log entries (POS == 3); 0 = nothing to append
-    if (a0) step_game_lock<RANDOM, POS>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, r0, k0, l0);
-    if (a1) step_game_lock<RANDOM, POS>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, r1, k1, l1);
+    if (a0) step_game_lock<RANDOM, POS, MASK>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, r0, k0, l0);
+    if (a1) step_game_lock<RANDOM, POS, MASK>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, r1, k1, l1);
     st2(e.hands + (POS * na + g), hm.x, hm.y);     // a game that did not move gets its slot back unchanged
     if (POS == 3) {
         st2(e.hands + g, n0.x, n0.y); st2(e.hands + (na + g), n1.x, n1.y); st2(e.hands + (2 * na + g), n2.x, n2.y);
@@ -819,17 +834,21 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
         else row[1] = l1;
     }
     st2(e.meta + g, m.x, m.y);
-    store_masks<RANDOM>(e, g, m, a0, a1, k0, k1);
+    store_masks<RANDOM, MASK>(e, g, m, a0, a1, k0, k1);
 }
 
 // `hint` = the number of plays every live game has made so far (lock-step pipelines know it on the host); POS = hint & 3
 // is compiled in (one kernel per trick position, each with its own register allocation); POS = -1: no hint.
-template <bool RANDOM, int POS>
+// MASK = write the legal mask of the next seat to move (the stepwise API: every launch a caller can observe).  A CHAIN of
+// in-kernel random steps (tarok_steps_random, the stepwise rollouts) launches its interior steps with MASK = false: no
+// caller can see those masks, so the next seat's slot is neither read nor its legal set computed or stored -- 16 of the
+// 48 bytes a step moves at trick positions 0-2 -- and only the chain's last launch produces the masks.
+template <bool RANDOM, int POS, bool MASK = true>
 __global__ void __launch_bounds__(CTA, RANDOM ? TK_STEP_BLOCKS_RANDOM : TK_STEP_BLOCKS_FORCED)
 k_step(Env e, const uint8_t* __restrict__ action, int hint) {
     pdl_launch_dependents();
     if constexpr (POS >= 0) {
-        step_lock<RANDOM, POS>(e, action, hint);
+        step_lock<RANDOM, POS, MASK>(e, action, hint);
     } else {
         const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
         pdl_wait();
@@ -838,7 +857,7 @@ k_step(Env e, const uint8_t* __restrict__ action, int hint) {
         if (!RANDOM) act = load_actions(action, g, e.n);
         const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act & 0xFFu) != CARD_SKIP),
                    a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act >> 8) != CARD_SKIP);
-        if (a0 || a1) step_pair_general<RANDOM, -1>(e, g, m, a0, a1, act, z, z, z, z);
+        if (a0 || a1) step_pair_general<RANDOM, -1, MASK>(e, g, m, a0, a1, act, z, z, z, z);
     }
 }
 

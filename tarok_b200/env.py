@@ -167,6 +167,10 @@ class TarokEnv:
         """Whether ``score()`` writes the full piles / Klop talon back (default) or only produces scores + statistics."""
         self._check(self._lib.tarok_set_option(self._h, 4, 1 if on else 0))
 
+    def set_lazy_mask(self, on: bool):
+        """Chains of in-kernel random steps write the legal masks in their last launch only (default on)."""
+        self._check(self._lib.tarok_set_option(self._h, 6, 1 if on else 0))
+
     def set_lockstep(self, on: bool):
         """Trick-position-specialised play_step for lock-step batches (default on; the kernel verifies the hint)."""
         self._check(self._lib.tarok_set_option(self._h, 3, 1 if on else 0))

@@ -217,6 +217,34 @@ def test_fused_rollout_writes_the_replay_inputs(mode):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("mode", [17, 16, 0])
+def test_chain_of_random_steps_with_lazy_masks_leaves_the_same_state(mode):
+    """A chain of in-kernel random steps writes the legal masks in its last launch only (TAROK_OPT_LAZY_MASK, default on):
+    after every chain -- whatever its length, also with games finishing inside it (Berac early stops in mode 17) and with
+    warps that fall back to the general path -- masks, meta, hands and the trick-derived scores equal those of a run
+    whose every launch writes its masks."""
+    import tarok_b200.env as E
+    n, seed, gid0 = 50021, 2718, 3
+    a, b = _env(n, seed=seed), _env(n, seed=seed)
+    b.set_lazy_mask(False)
+    a.deal(gid0); b.deal(gid0)
+    if mode == 17:
+        a.auction_synth(17); b.auction_synth(17)
+        a.step_random(2); b.step_random(2)                       # the contracts without an exchange run ahead: general path later
+        a.exchange_synth(True); b.exchange_synth(True)
+    else:
+        a.force_contract_synth(mode); b.force_contract_synth(mode)
+        a.exchange_synth(False); b.exchange_synth(False)
+    for chunk in (1, 2, 5, 3, 13, 1, 30):
+        a.step_random(chunk); b.step_random(chunk)
+        for f in ("mask", "meta", "hand_slots"):
+            assert (u64(getattr(a, f)) == u64(getattr(b, f))).all(), (f, chunk)
+        assert (u64(a.legal_mask()) == u64(a.mask[:n])).all()    # and they are the masks of the state
+    assert (a.score().cpu().numpy() == b.score().cpu().numpy()).all()
+    assert (a.stats()[:21] == b.stats()[:21]).all()
+    a.close(); b.close()
+
+
 def test_desynchronised_batch_takes_the_general_path(oracle):
     """Games that start playing at different times (here: the contracts without a talon exchange play three cards before
     the others have exchanged) break the lock-step hint inside most warps; the per-warp vote must then send them through

@@ -28,6 +28,9 @@ def main():
     rec.close()
     env = TarokEnv(n, seed=1)
     env.set_materialise(False)
+    if os.environ.get("TAROK_LAZY_MASK") == "0":
+        env.set_lazy_mask(False)
+        out["lazy_mask"] = 0
     out["setup_us"] = timed(lambda: env.setup_synth(mode, 0))
 
     def steps(forced):
