@@ -39,7 +39,7 @@ constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane 
 struct Env {
     u64* hands; u64* piles; u64* talon; u64* torder; u64* meta; u64* mask; u64* scores;
     uint8_t* hist; u64* hands0; u64* discard; float* qmax_hist; long long* stats;
-    u32* tricklog;                         // [12][n_alloc]: trick k of game g = 4 cards (24 bit, play order) | winner << 24 | card points << 26
+    u32* tricklog;                         // [12][n_alloc]: trick k of game g = 4 cards (24 bit, play order) | card points << 24 | called-king flag << 29 | winner << 30
     uint8_t* dpts;                         // [n_alloc]: card points of the declarer's discards (scoring reads this instead of the piles)
     u64 n, n_alloc, first_gid;
     Rng rng;                               // seed + precomputed Philox round keys
@@ -193,9 +193,7 @@ __host__ __device__ constexpr u64 deal_bounds8(int w) {
 struct DealWalk { u32 T, acc; u32 rev[7]; };
 
 __device__ __forceinline__ void deal_place(DealWalk& d, int c, u32 r) {             // c is a compile-time constant at every call
-    // byte j = (r < T_j); the shift by 7 is written as a multiply-high by 2^25: the integer ALU pipe is what bounds this
-    // kernel, the FMA pipe (IMAD / IMAD.HI) has room
-    const u32 q = __umulhi(r * 0xFEFEFEFFu + d.T, 1u << 25) & 0x01010101u;
+    const u32 q = ((r * 0xFEFEFEFFu + d.T) >> 7) & 0x01010101u;                     // byte j = (r < T_j)
     d.T -= q;
     d.acc = d.acc * 2u + q;
     if ((c & 7) == 7) { d.rev[c >> 3] = __brev(d.acc); d.acc = 0; }                 // byte 3 - j: bit jj = q_j of card 8 * (c >> 3) + jj
@@ -982,7 +980,7 @@ __device__ __forceinline__ void materialise(u64 meta, const uint2* log12, int wh
             const u32 entry = which ? log12[k].y : log12[k].x;
             u64 tc;
             const u64 b = trick_bits(entry, k, klop, order, tc);
-            const u32 w = (entry >> 24) & 3u;
+            const u32 w = entry >> 30;
             p0 |= w == 0 ? b : 0ull; p1 |= w == 1 ? b : 0ull; p2 |= w == 2 ? b : 0ull; p3 |= w == 3 ? b : 0ull;
             talon &= ~tc;
         }
@@ -993,7 +991,7 @@ __device__ __forceinline__ void materialise(u64 meta, const uint2* log12, int wh
 // Roka.prestej is order independent -- sum(points) - 2 * floor(n / 3) - [n % 3 != 0] over the n cards of a pile
 // (Roka.py:55-98) -- so no bitboard is rebuilt: per trick one compare-and-add.
 //   Navadna / Solo (Navadna_igra.py:80-113): the team's points = the declarer's discards (`dpts`, k cards) + the tricks won by
-//     a seat of `ekipa`; the leftover talon joins them iff a lone declarer in a king game took the called king (Q7) -- bit 31
+//     a seat of `ekipa`; the leftover talon joins them iff a lone declarer in a king game took the called king (Q7) -- bit 29
 //     of the entry of the trick that held it.
 //   Klop (Klop.py:36-45): per seat; the talon card of tricks 1..6 (popped from the END, Klop.py:67-71) goes to the winner.
 //   Berac (Berac.py:33-44): the game stops on the declarer's first trick, so "the declarer took a trick" = "the last
@@ -1008,14 +1006,14 @@ __device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int 
 #pragma unroll
         for (u32 k = 0; k < 12; k++) {
             const u32 entry = which ? log12[k].y : log12[k].x;
-            const u32 mine = (valid >> k) & (team >> ((entry >> 24) & 3u)) & 1u;     // a trick of the declarer's team
-            pts += mine * ((entry >> 26) & 31u);
+            const u32 mine = (valid >> k) & (team >> (entry >> 30)) & 1u;            // a trick of the declarer's team
+            pts += mine * ((entry >> 24) & 31u);
             won += mine;
-            kings |= mine ? entry : 0u;                                              // bit 31: the called king was in it
+            kings |= mine & (entry >> 29);                                           // bit 0: the called king was in it
         }
         u32 n = 4u * won + (((lo >> M_GROUP) & 7u) != NO_GROUP ? talon_k(contract) : 0u);
         // leftover talon to a lone declarer of a king game who took the called king (Q7); a lone declarer is the whole team
-        if (contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING && (kings >> 31)) {
+        if (contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING && (kings & 1u)) {
             pts += card_points(talon); n += (u32)__popcll(talon);
         }
         return score_navadna_v(meta, prestej_pn((int)pts, (int)n));
@@ -1028,9 +1026,9 @@ __device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int 
     for (u32 k = 0; k < 12; k++) {
         if (k < tricks) {
             const u32 entry = which ? log12[k].y : log12[k].x;
-            u32 p = (entry >> 26) & 31u, c = 4u;
+            u32 p = (entry >> 24) & 31u, c = 4u;
             if (k < 6) { p += card_points1((u32)(order >> (6 * (5 - k))) & 63u); c = 5u; }
-            const u32 sh = 8u * ((entry >> 24) & 3u);
+            const u32 sh = 8u * (entry >> 30);
             acc += p << sh; cnt += c << sh;
         }
     }

@@ -348,12 +348,13 @@ __device__ __forceinline__ bool trick_has(u32 f, u32 id) {
     const u32 z = ((x & 0x7DF7DFu) + 0x7DF7DFu) | x;                 // bit 5 of a field set iff the field is non-zero
     return (~z & 0x820820u) != 0u;
 }
-// Trick-log entry: the four cards in play order (24 bits) | winner seat << 24 | trick_points << 26 (5 bits) | bit 31: the
-// trick contains the CALLED king (king games only; Navadna_igra.py:87 asks whether that card ended in the declarer's pile).
+// Trick-log entry: the four cards in play order (bits 0-23) | trick_points (24-28) | bit 29: the trick contains the CALLED
+// king (king games only; Navadna_igra.py:87 asks whether that card ended in the declarer's pile) | winner seat (30-31, so
+// that scoring reads it with one shift).
 __device__ __forceinline__ u32 log_entry(u32 t24, u32 winner, u32 meta_lo) {
     const u32 king = (meta_lo >> M_KING) & 7u;
-    const u32 kf = (king != NO_KING && trick_has(t24, king * 8u + 7u)) ? 0x80000000u : 0u;
-    return t24 | (winner << 24) | (trick_points(t24) << 26) | kf;
+    const u32 kf = (king != NO_KING && trick_has(t24, king * 8u + 7u)) ? (1u << 29) : 0u;
+    return t24 | (trick_points(t24) << 24) | kf | (winner << 30);
 }
 // Trick-log entry, continued.  The bitboard the winner collected in
 // trick k: its four cards, plus in Klop the talon card popped from the END of the ordered talon in tricks 1..6

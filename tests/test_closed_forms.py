@@ -52,7 +52,7 @@ def test_trick_points_closed_form():
     pc = sum(((tr >> u(6 * j + 5)) & u(1)) for j in range(4))
     got = u(4) + (((v * u(0x041041)) >> u(18)) & u(0x3F)) + u(4) * pc
     assert (got == _points(g).sum(1)).all()
-    assert int(got.max()) == 20                                   # fits the 5 bits of the trick-log entry
+    assert int(got.max()) == 20                                   # fits the 5 bits (24-28) of the trick-log entry
 
 
 def test_trick_has_closed_form():
