@@ -95,8 +95,7 @@ class ClockSampler:
             try:
                 sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
                 rs = N.nvmlDeviceGetCurrentClocksEventReasons(h)
-                ut = N.nvmlDeviceGetUtilizationRates(h).gpu
-                self.samples.append((sm, self.mx, rs, ut))
+                self.samples.append((sm, self.mx, rs))
             except Exception:
                 break
             time.sleep(0.05)           # 20 Hz: NVML queries share the driver with the CUDA calls of the e2e legs
@@ -250,6 +249,11 @@ def run_reference(args, rank):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
+    # libnccl prints its version banner on stdout when NCCL_DEBUG asks for it: everything this process (and the libraries
+    # it loads) writes to fd 1 goes to stderr, the ONE JSON line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -266,15 +270,7 @@ def run_ours(args, rank, world, local_rank):
     n, mode, total = args.games, args.mode, args.games * world
     env = TarokEnv(n, seed=SEED, device=local_rank)
     env.set_materialise(False)      # the rollout's outputs are scores + statistics (Tarok.rezultati); piles stay in the trick log
-    sys.stdout.flush()
-    keep = os.dup(1)                # libnccl may print its version banner on stdout: the JSON line must stay alone there
-    os.dup2(2, 1)
-    try:
-        comm = NcclComm(local_rank)     # raw ncclComm_t for the C-ABI collective (a one-rank communicator at N = 1)
-    finally:
-        sys.stdout.flush()
-        os.dup2(keep, 1)
-        os.close(keep)
+    comm = NcclComm(local_rank)     # raw ncclComm_t for the C-ABI collective (a one-rank communicator at N = 1)
     auction = mode in (17, 18)
     flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     stats_ring = torch.zeros((args.warmup + args.steps + 1, 32), dtype=torch.int64, device=dev)
@@ -599,7 +595,8 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu, "clocks": clocks,
         }
         out.update(sub)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
