@@ -61,7 +61,7 @@ __device__ __forceinline__ u64 rotl64(u64 x, u32 r) { return r ? (x << r) | (x >
 
 template <int NG>
 __device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, const GameStat (&gs)[NG]) {
-    __shared__ long long sh[S_USED];
+    __shared__ int sh[S_USED];                         // a CTA's sums fit 32 bits (<= 512 games x |score| <= 135, x 48 plays)
     if (threadIdx.x < S_USED) sh[threadIdx.x] = 0;
     __syncthreads();
     const unsigned full = 0xFFFFFFFFu;
@@ -108,10 +108,10 @@ __device__ __forceinline__ void accumulate_stats(long long* __restrict__ stats, 
         if (lane == S_STEPS) mine = b;
         if (lane == S_ERRORS) mine = (int)(a >> 16);
     }
-    if (lane < S_USED && mine != 0) atomicAdd((unsigned long long*)&sh[lane], (unsigned long long)(long long)mine);
+    if (lane < S_USED && mine != 0) atomicAdd(&sh[lane], mine);
     __syncthreads();
     if (threadIdx.x < S_USED && sh[threadIdx.x] != 0)
-        atomicAdd((unsigned long long*)&stats[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+        atomicAdd((unsigned long long*)&stats[threadIdx.x], (unsigned long long)(long long)sh[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -611,36 +611,43 @@ __global__ void __launch_bounds__(CTA, TK_SETUP_BLOCKS) k_setup_synth(Env e, u32
     const u64 na = e.n_alloc;
     if (g >= na) return;
     Dealt d = {0, 0, 0, 0, 0, 0};
-    u64 meta = meta_pad(), mask = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0, dout = 0;
-    u64 s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    u64 meta = meta_pad(), mask = 0, dout = 0, hand = 0;
+    u32 decl = 0;
+    bool exchanged = false;
     if (g < e.n) {
         const u64 gid = e.first_gid + g;
         d = deal_philox(e.rng, gid);
-        s0 = d.h0; s1 = d.h1; s2 = d.h2; s3 = d.h3;
+        if (e.hands0) { e.hands0[g] = d.h0; e.hands0[na + g] = d.h1; e.hands0[2 * na + g] = d.h2; e.hands0[3 * na + g] = d.h3; }
         u32 contract, declarer, king;
         const Words4 sb = setup_block(e.rng, gid);
         resolve_contract<SRC_SYNTH>(e.rng, gid, mode, nullptr, nullptr, nullptr, g, sb, contract, declarer, king);
         meta = begin_contract(meta_fresh(), contract, declarer, king, d.h0, d.h1, d.h2, d.h3);
+        decl = mget(meta, M_DECL, 2);
         if (mget(meta, M_PHASE, 2) == PH_EXCHANGE) {
-            const u32 decl = mget(meta, M_DECL, 2);
-            u64 hand = sel4(d.h0, d.h1, d.h2, d.h3, decl), pile = 0;
-            if (exchange_game<true>(e.rng, gid, mode == 17u, sb, meta, hand, pile, d.talon, d.order, 0u, 0ull, dout)) {
-                d.h0 = decl == 0 ? hand : d.h0; d.h1 = decl == 1 ? hand : d.h1;
-                d.h2 = decl == 2 ? hand : d.h2; d.h3 = decl == 3 ? hand : d.h3;
-                p0 = decl == 0 ? pile : 0ull; p1 = decl == 1 ? pile : 0ull;
-                p2 = decl == 2 ? pile : 0ull; p3 = decl == 3 ? pile : 0ull;
-            } else {
-                meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
-            }
+            u64 pile = 0;
+            hand = sel4(d.h0, d.h1, d.h2, d.h3, decl);
+            exchanged = exchange_game<true>(e.rng, gid, mode == 17u, sb, meta, hand, pile, d.talon, d.order, 0u, 0ull, dout);
+            if (!exchanged) meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
         }
         if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
-        mask = mask_for_mover(meta, sel4(d.h0, d.h1, d.h2, d.h3, mover_of(meta)));
-        seats_to_slots(d.h0, d.h1, d.h2, d.h3, leader_of(meta));
+        // the opening seat's legal set; only Berac opens from another seat than 0, and then the four slots are re-seated
+        const u32 leader = leader_of(meta);
+        u64 opener = d.h0;
+        if (leader != 0u) {
+            opener = sel4(d.h0, d.h1, d.h2, d.h3, leader);
+            seats_to_slots(d.h0, d.h1, d.h2, d.h3, leader);
+        }
+        if (exchanged && decl == leader) opener = hand;
+        mask = mask_for_mover(meta, opener);
+    } else if (e.hands0) {
+        e.hands0[g] = 0; e.hands0[na + g] = 0; e.hands0[2 * na + g] = 0; e.hands0[3 * na + g] = 0;
     }
+    // the hands as dealt (leader-relative), empty piles; an exchange then overwrites the declarer's two words -- the
+    // contracts that exchange all open from seat 0, so the declarer's slot is its seat
     e.hands[g] = d.h0; e.hands[na + g] = d.h1; e.hands[2 * na + g] = d.h2; e.hands[3 * na + g] = d.h3;
-    e.piles[g] = p0; e.piles[na + g] = p1; e.piles[2 * na + g] = p2; e.piles[3 * na + g] = p3;
+    e.piles[g] = 0; e.piles[na + g] = 0; e.piles[2 * na + g] = 0; e.piles[3 * na + g] = 0;
+    if (exchanged) { e.hands[decl * na + g] = hand; e.piles[decl * na + g] = dout; }
     e.talon[g] = d.talon; e.torder[g] = d.order; e.meta[g] = meta; e.mask[g] = mask;
-    if (e.hands0) { e.hands0[g] = s0; e.hands0[na + g] = s1; e.hands0[2 * na + g] = s2; e.hands0[3 * na + g] = s3; }
     if (e.discard) e.discard[g] = dout;
     e.dpts[g] = (uint8_t)card_points(dout);
 }

@@ -34,11 +34,9 @@ __device__ __forceinline__ bool is_king_game(u32 c) { return c >= C_TRI && c <= 
 __device__ __forceinline__ bool is_berac(u32 c) { return c == C_BERAC || c == C_ODPRTI_BERAC; }
 // Klop.mozne_karte is inherited by Berac (Berac.py:4)
 __device__ __forceinline__ bool klop_rules(u32 c) { return c == C_KLOP || is_berac(c); }
-// st_kart_za_menjat / korak (Navadna_igra.py:36-58); 0 = no exchange
-__device__ __forceinline__ u32 talon_k(u32 c) {
-    return (c == C_TRI || c == C_SOLO_TRI) ? 3u : (c == C_DVE || c == C_SOLO_DVE) ? 2u
-         : (c == C_ENA || c == C_SOLO_ENA) ? 1u : 0u;
-}
+// st_kart_za_menjat / korak (Navadna_igra.py:36-58); 0 = no exchange.  Two bits per contract code in one constant:
+// Tri / Solo_tri 3, Dve / Solo_dve 2, Ena / Solo_ena 1, everything else (incl. code 15 = none) 0.
+__device__ __forceinline__ u32 talon_k(u32 c) { return (0x1B6Cu >> (2u * (c & 15u))) & 3u; }
 
 // ---- meta word layout -----------------------------------------------------------------------
 // Fields never straddle the 32-bit halves, so every update is 32-bit integer work.
@@ -239,13 +237,14 @@ __device__ __forceinline__ u64 begin_contract(u64 meta, u32 contract, u32 declar
         if (is_berac(contract)) leader = declarer;
         if (talon_k(contract) != 0) phase = PH_EXCHANGE;
     }
-    meta = mset(meta, M_CONTRACT, 4, bad ? (u32)C_NONE : contract);
-    meta = mset(meta, M_DECL, 2, declarer & 3u);
-    meta = mset(meta, M_KING, 3, king);
-    meta = mset(meta, M_TEAM, 4, team);
-    meta = mset(meta, M_LEADER, 2, leader);
-    meta = mset(meta, M_PHASE, 2, bad ? (u32)PH_DONE : phase);
-    meta = mset(meta, M_KLOPFAM, 1, (!bad && klop_rules(contract)) ? 1u : 0u);
+    // every field this function owns sits in the low word; the rest of the word (trick leader / position / counters,
+    // error bit, chosen group) is kept
+    constexpr u32 OWNED = (15u << M_CONTRACT) | (3u << M_DECL) | (7u << M_KING) | (15u << M_TEAM) | (3u << M_LEADER)
+                        | (3u << M_PHASE) | (1u << M_KLOPFAM);
+    const u32 lo = ((u32)meta & ~OWNED) | ((bad ? (u32)C_NONE : contract) << M_CONTRACT) | ((declarer & 3u) << M_DECL)
+                 | ((king & 7u) << M_KING) | (team << M_TEAM) | (leader << M_LEADER) | ((bad ? (u32)PH_DONE : phase) << M_PHASE)
+                 | (((!bad && klop_rules(contract)) ? 1u : 0u) << M_KLOPFAM);
+    meta = (meta & 0xFFFFFFFF00000000ull) | lo;
     if (bad) meta |= 1ull << M_ERR;
     return meta;
 }
