@@ -187,6 +187,11 @@ int64_t tarok_pack_records(const uint8_t* perm_host, const uint8_t* contract_hos
    OMP_NUM_THREADS=1, so the count is explicit). */
 int64_t tarok_pack_records_mt(const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
                               const uint8_t* king_host /* or NULL */, uint64_t n, uint64_t* records_host, int threads);
+/* The serialiser picks an AVX-512 implementation at run time where the CPU has it (one-hot words eight ids at a time), else
+   scalar code (BMI2 clone where available); both produce identical records.  tarok_pack_uses_avx512 tells which one runs,
+   tarok_pack_force_scalar(1) pins the scalar one (returns the previous setting; a testing aid). */
+int tarok_pack_uses_avx512(void);
+int tarok_pack_force_scalar(int on);
 /* tarok_rollout_host(fused = 1) that serialises the rows itself: each chunk of the upload/compute/download pipeline is
    packed into records by `threads` host threads (a pool kept in the handle, pinned scratch owned by the handle) right
    before its upload, so the caller keeps handing over what Igra.shuffle produces (Igra.py:65-73) and PCIe carries

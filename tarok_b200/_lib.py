@@ -47,6 +47,8 @@ SIGNATURES = {
     "tarok_pack_records": (C.c_int64, [_VP, _VP, _VP, _VP, _U64, _VP]),
     "tarok_rollout_records": (_I, [_VP, _VP, _U64, _VP, _VP, _VP]),
     "tarok_pack_records_mt": (C.c_int64, [_VP, _VP, _VP, _VP, _U64, _VP, _I]),
+    "tarok_pack_uses_avx512": (_I, []),
+    "tarok_pack_force_scalar": (_I, [_I]),
     "tarok_rollout_host_packed": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _I, _VP, _VP, _VP]),
     "tarok_obs_shape": (_I, [_VP, _VP, _VP, _VP]),
     "tarok_obs_buckets": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),

@@ -5,6 +5,8 @@
 // host-buffer entries are launched by torchrun with OMP_NUM_THREADS=1, so the thread count is an explicit argument).
 #include "../../include/tarok_b200.h"
 
+#include <immintrin.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
@@ -59,12 +61,75 @@ __attribute__((always_inline)) inline bool pack_row(const uint8_t* row, unsigned
 // Built twice (function multi-versioning, resolved once at load time): with BMI2 the variable shifts are single SHLX
 // micro-ops instead of the three-uop SHL-by-CL and the eleven popcounts are instructions instead of library calls.
 __attribute__((target_clones("default", "arch=x86-64-v3")))
-int64_t pack_range(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king, uint64_t a,
-                   uint64_t b, uint64_t* records) {
+int64_t pack_range_scalar(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king, uint64_t a,
+                          uint64_t b, uint64_t* records) {
     int64_t bad = 0;
     for (uint64_t g = a; g < b; g++)
         bad += pack_row(perm + g * 54, contract[g], declarer[g], king ? king[g] : 7u, records + g * 3) ? 0 : 1;
     return bad;
+}
+
+// AVX-512 version: the row's 54 ids become one-hot 64-bit words eight at a time (VPMOVZXBQ + VPSLLVQ; a shift count >= 64
+// gives 0, so an out-of-range id can only LOSE a bit and the cover / count checks below reject the row), the words are OR-ed
+// per owner -- the twelve cards of a seat are one and a half vectors, hence the lane masks -- and reduced two owners at a time.
+#define TK_AVX512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,bmi2,popcnt")))
+TK_AVX512 static inline __m128i or_reduce_pair(__m512i a, __m512i b) {          // -> [OR of a's lanes, OR of b's lanes]
+    const __m512i t = _mm512_or_si512(_mm512_unpacklo_epi64(a, b), _mm512_unpackhi_epi64(a, b));   // per 128-bit lane [a, b]
+    const __m256i u = _mm256_or_si256(_mm512_castsi512_si256(t), _mm512_extracti64x4_epi64(t, 1));
+    return _mm_or_si128(_mm256_castsi256_si128(u), _mm256_extracti128_si256(u, 1));
+}
+TK_AVX512 static inline __m512i one_hot8(const uint8_t* p) {                    // eight ids -> eight one-hot 64-bit words
+    return _mm512_sllv_epi64(_mm512_set1_epi64(1), _mm512_cvtepu8_epi64(_mm_loadl_epi64((const __m128i*)p)));
+}
+TK_AVX512 static inline bool pack_row_avx512(const uint8_t* row, unsigned contract, unsigned declarer, unsigned king, uint64_t* w) {
+    const __m512i one = _mm512_set1_epi64(1);
+    const __m512i v0 = one_hot8(row), v1 = one_hot8(row + 8), v2 = one_hot8(row + 16), v3 = one_hot8(row + 24),
+                  v4 = one_hot8(row + 32), v5 = one_hot8(row + 40);
+    // the six talon ids: a masked load (never reads past the row: the last row of a buffer ends there)
+    const __m128i t6 = _mm_maskz_loadu_epi8((__mmask16)0x3F, row + 48);
+    const __m512i v6 = _mm512_maskz_sllv_epi64((__mmask8)0x3F, one, _mm512_cvtepu8_epi64(t6));
+    const __m512i a0 = _mm512_or_si512(v0, _mm512_maskz_mov_epi64((__mmask8)0x0F, v1));            // seat 0: ids 0..11
+    const __m512i a1 = _mm512_or_si512(_mm512_maskz_mov_epi64((__mmask8)0xF0, v1), v2);            // seat 1: ids 12..23
+    const __m512i a2 = _mm512_or_si512(v3, _mm512_maskz_mov_epi64((__mmask8)0x0F, v4));            // seat 2
+    const __m512i a3 = _mm512_or_si512(_mm512_maskz_mov_epi64((__mmask8)0xF0, v4), v5);            // seat 3
+    const __m128i r01 = or_reduce_pair(a0, a1), r23 = or_reduce_pair(a2, a3), r4 = or_reduce_pair(v6, v6);
+    const uint64_t h0 = (uint64_t)_mm_cvtsi128_si64(r01), h1 = (uint64_t)_mm_extract_epi64(r01, 1);
+    const uint64_t h2 = (uint64_t)_mm_cvtsi128_si64(r23), h3 = (uint64_t)_mm_extract_epi64(r23, 1);
+    const uint64_t talon = (uint64_t)_mm_cvtsi128_si64(r4);
+    uint64_t ranks = 0;
+    for (int i = 0; i < 6; i++) {                         // position in the talon of its cards taken in ascending id
+        const unsigned c = row[48 + i];
+        const int below = __builtin_popcountll(_bzhi_u64(talon, c < 64 ? c : 0));
+        ranks |= (uint64_t)i << (3 * below);
+    }
+    const bool perm_ok = (h0 | h1 | h2 | h3 | talon) == ALL54 && __builtin_popcountll(h0) == 12
+        && __builtin_popcountll(h1) == 12 && __builtin_popcountll(h2) == 12 && __builtin_popcountll(h3) == 12
+        && __builtin_popcountll(talon) == 6;
+    const bool ok = perm_ok && contract <= 15u && declarer <= 3u;
+    uint64_t w0 = h1 | h3, w1 = h2 | h3, w2 = talon;
+    if (!ok) w0 = w1 = w2 = ALL54;
+    const unsigned k = king < 7u ? king : 7u;
+    w[0] = w0 | (ranks & 0x1FF) << 54;
+    w[1] = w1 | ((ranks >> 9) & 0x1FF) << 54;
+    w[2] = w2 | (uint64_t)(contract & 15u) << 54 | (uint64_t)(declarer & 3u) << 58 | (uint64_t)(k & 7u) << 60;
+    return ok;
+}
+TK_AVX512 static int64_t pack_range_avx512(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer,
+                                           const uint8_t* king, uint64_t a, uint64_t b, uint64_t* records) {
+    int64_t bad = 0;
+    for (uint64_t g = a; g < b; g++)
+        bad += pack_row_avx512(perm + g * 54, contract[g], declarer[g], king ? king[g] : 7u, records + g * 3) ? 0 : 1;
+    return bad;
+}
+
+std::atomic<int> g_force_scalar{0};
+
+int64_t pack_range(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king, uint64_t a,
+                   uint64_t b, uint64_t* records) {
+    static const bool wide = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")
+                          && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("bmi2");
+    return (wide && !g_force_scalar.load(std::memory_order_relaxed)) ? pack_range_avx512(perm, contract, declarer, king, a, b, records)
+                : pack_range_scalar(perm, contract, declarer, king, a, b, records);
 }
 
 }  // namespace
@@ -171,6 +236,14 @@ int64_t tarok_pack_records_mt(const uint8_t* perm, const uint8_t* contract, cons
     for (auto& th : pool) th.join();
     for (int64_t v : bad) total += v;
     return total;
+}
+
+int tarok_pack_force_scalar(int on) { return g_force_scalar.exchange(on ? 1 : 0); }
+
+int tarok_pack_uses_avx512(void) {
+    if (g_force_scalar.load()) return 0;
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl")
+        && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("bmi2");
 }
 
 int64_t tarok_pack_records(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king,

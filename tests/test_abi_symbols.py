@@ -102,3 +102,40 @@ def test_pack_records_is_the_documented_layout():
         assert int(w[g, 2] >> np.uint64(60)) & 7 == king[g]
     perm[0, 0] = perm[0, 1]
     assert pack_records(perm, contract, declarer, None)[1] == 1
+
+
+def test_pack_records_vector_and_scalar_serialisers_agree():
+    """The AVX-512 serialiser (taken at run time where the CPU has it) and the scalar one produce identical records and reject
+    the same rows: duplicates, ids 54..63, ids >= 64, out-of-range contract / declarer -- also on several threads and on the
+    very last row of a buffer (the vector code must not read past it)."""
+    import numpy as np
+    from tarok_b200 import _lib
+    from tarok_b200.env import pack_records
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    n = 50021
+    perm = np.stack([rng.permutation(54) for _ in range(n)]).astype(np.uint8)
+    contract = rng.integers(0, 10, n).astype(np.uint8)
+    declarer = rng.integers(0, 4, n).astype(np.uint8)
+    king = rng.integers(0, 8, n).astype(np.uint8)
+    perm[5, 3] = perm[5, 4]                     # duplicate inside a hand
+    perm[77, 50] = 60                           # id 54..63 in the talon
+    perm[99, 0] = 200                           # id >= 64
+    perm[100, 47], perm[100, 48] = 53, 53       # duplicate across hand and talon
+    perm[n - 1, 53] = perm[n - 1, 52]           # the last row
+    contract[11] = 99
+    declarer[12] = 7
+    out = {}
+    prev = lib.tarok_pack_force_scalar(0)
+    try:
+        for scalar in (0, 1):
+            lib.tarok_pack_force_scalar(scalar)
+            for threads in (1, 3):
+                rec, bad = pack_records(perm, contract, declarer, king, threads=threads)
+                out[(scalar, threads)] = (rec.numpy().copy(), bad)
+    finally:
+        lib.tarok_pack_force_scalar(prev)
+    ref, bad = out[(1, 1)]
+    assert bad == 7
+    for k, (rec, b) in out.items():
+        assert b == bad and np.array_equal(rec, ref), k
