@@ -50,7 +50,7 @@ __attribute__((always_inline)) inline bool pack_row(const uint8_t* row, unsigned
         && __builtin_popcountll(h[3]) == 12 && __builtin_popcountll(talon) == 6;
     const bool ok = perm_ok && contract <= 15u && declarer <= 3u;
     uint64_t w0 = h[1] | h[3], w1 = h[2] | h[3], w2 = talon;
-    if (!ok) w0 = w1 = w2 = ALL54;                        // decodes to an error game, like the row itself would
+    if (!ok) { w0 = w1 = w2 = ALL54; ranks = 0; }         // decodes to an error game, like the row itself would
     const unsigned k = king < 7u ? king : 7u;
     w[0] = w0 | (ranks & 0x1FF) << 54;
     w[1] = w1 | ((ranks >> 9) & 0x1FF) << 54;
@@ -107,7 +107,7 @@ TK_AVX512 static inline bool pack_row_avx512(const uint8_t* row, unsigned contra
         && __builtin_popcountll(talon) == 6;
     const bool ok = perm_ok && contract <= 15u && declarer <= 3u;
     uint64_t w0 = h1 | h3, w1 = h2 | h3, w2 = talon;
-    if (!ok) w0 = w1 = w2 = ALL54;
+    if (!ok) { w0 = w1 = w2 = ALL54; ranks = 0; }
     const unsigned k = king < 7u ? king : 7u;
     w[0] = w0 | (ranks & 0x1FF) << 54;
     w[1] = w1 | ((ranks >> 9) & 0x1FF) << 54;

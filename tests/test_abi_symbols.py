@@ -122,6 +122,7 @@ def test_pack_records_vector_and_scalar_serialisers_agree():
     perm[77, 50] = 60                           # id 54..63 in the talon
     perm[99, 0] = 200                           # id >= 64
     perm[100, 47], perm[100, 48] = 53, 53       # duplicate across hand and talon
+    perm[101, 49] = 130                         # id >= 64 in the talon
     perm[n - 1, 53] = perm[n - 1, 52]           # the last row
     contract[11] = 99
     declarer[12] = 7
@@ -136,6 +137,6 @@ def test_pack_records_vector_and_scalar_serialisers_agree():
     finally:
         lib.tarok_pack_force_scalar(prev)
     ref, bad = out[(1, 1)]
-    assert bad == 7
+    assert bad == 8
     for k, (rec, b) in out.items():
         assert b == bad and np.array_equal(rec, ref), k
