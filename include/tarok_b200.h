@@ -173,11 +173,11 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
 
 /* Deal records: the same inputs as tarok_rollout_host in 24 instead of 57 bytes per deal (the host-buffer path is
    PCIe-bound, so the bytes are the cost).  One record = three little-endian uint64 words w0,w1,w2:
-     bits 0..53 of w0/w1/w2 = bit planes 0/1/2 of each card's owner code (bit i = card id i; code 0-3 = seat whose
-                              twelve cards of Igra.razdeli (Igra.py:65-73) hold the card, 4 = talon, 5-7 invalid);
-     w0 bits 54..62, w1 bits 54..62 = positions 0..5 within the ordered talon (karte[48:54]) of its six cards taken in
-                              ascending card id, 3 bits each (cards 0-2 in w0, 3-5 in w1);
-     w2 bits 54..57 contract code, 58..59 declarer seat, 60..62 king suit (7 = none): the arguments of tarok_force_contract.
+     bits 0..53 of w0/w1     = bit planes 0/1 of the seat (0-3) whose twelve cards of Igra.razdeli (Igra.py:65-73) hold
+                               card id i (bit i = card id i); the six talon cards carry 0 in both planes;
+     w2 bits 0..35           = the six talon ids in talon order (karte[48:54]), 6 bits each, first card lowest;
+     w2 bits 36..39 contract code, 40..41 declarer seat, 42..44 king suit (7 = none): the arguments of tarok_force_contract;
+     every other bit is 0.
    tarok_pack_records is the host-side serialiser (plain CPU code; returns the number of rows that are not permutations
    or carry an out-of-range contract/declarer -- those become records that decode to error games -- or -1 on NULL). */
 #define TAROK_RECORD_BYTES 24
@@ -187,8 +187,8 @@ int64_t tarok_pack_records(const uint8_t* perm_host, const uint8_t* contract_hos
    OMP_NUM_THREADS=1, so the count is explicit). */
 int64_t tarok_pack_records_mt(const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
                               const uint8_t* king_host /* or NULL */, uint64_t n, uint64_t* records_host, int threads);
-/* The serialiser picks an AVX-512 implementation at run time where the CPU has it (one-hot words eight ids at a time), else
-   scalar code (BMI2 clone where available); both produce identical records.  tarok_pack_uses_avx512 tells which one runs,
+/* The serialiser picks an AVX-512 implementation at run time where the CPU has it (eight rows at a time, one per 64-bit
+   lane), else scalar code (BMI2 clone where available); both produce identical records.  tarok_pack_uses_avx512 tells which one runs,
    tarok_pack_force_scalar(1) pins the scalar one (returns the previous setting; a testing aid). */
 int tarok_pack_uses_avx512(void);
 int tarok_pack_force_scalar(int on);

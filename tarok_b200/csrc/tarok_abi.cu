@@ -610,36 +610,14 @@ int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t fir
                               stats_host, s);
 }
 
-// Third form of the host-buffer entry: the caller hands over permutation ROWS (what Igra.shuffle produces), the library
-// serialises each chunk into 24-byte deal records with `threads` host threads right before that chunk's upload, so PCIe
-// carries 24 instead of 57 bytes per deal and the packing of chunk c+1 overlaps the upload / play / download of chunk c.
-int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
-                              const uint8_t* king_host, uint64_t first_global_game_id, int threads, int16_t* scores_host,
-                              int64_t* stats_host, void* stream) {
-    TK_CHECK_HANDLE(h);
-    if (!perm_host || !contract_host || !declarer_host) return fail(h, -1, "perm/contract/declarer host pointers are required");
-    if (threads < 1 || threads > 256) return fail(h, -1, "threads must be in 1..256");
-    DeviceGuard dg(h->device);
-    if (int rc = ensure_staging(h)) return rc;
-    if (!h->pin_rec) TK_CUDA(h, cudaHostAlloc((void**)&h->pin_rec, h->e.n_alloc * TAROK_RECORD_BYTES, cudaHostAllocDefault));
-    if (h->pool && tarok_pack_pool_threads(h->pool) != threads) { tarok_pack_pool_destroy(h->pool); h->pool = nullptr; }
-    if (!h->pool) h->pool = tarok_pack_pool_create(threads);
-    if (!h->pool) return fail(h, -4, "could not create the pack pool");
-    cudaStream_t s = S(stream);
-    TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
-    h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
-    const u64 n = h->e.n, want = (u64)h->chunks;
-    const u64 chunk = (n >= (1ull << 18)) ? (((n + want - 1) / want + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
-    const int nchunks = (int)((n + chunk - 1) / chunk);
+// Upload / play / download of the chunks of tarok_rollout_host_packed, each as soon as the pool has packed it.
+static int packed_pipeline(tarok_t* h, u64 n, u64 chunk, int nchunks, int16_t* scores_host, int64_t* stats_host, cudaStream_t s) {
     TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
     TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));
     TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_fork, 0));
     for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
         const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
-        // the previous call's upload of this part of the pinned scratch must have left the host before it is overwritten
-        if (h->pack_used[c]) TK_CUDA(h, cudaEventSynchronize(h->ev_up[c]));
-        tarok_pack_pool_run(h->pool, perm_host, contract_host, declarer_host, king_host, b, e_, h->pin_rec);
+        tarok_pack_pool_wait_chunk(h->pool, c);
         TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * TAROK_RECORD_BYTES, (const uint8_t*)h->pin_rec + b * TAROK_RECORD_BYTES,
                                    len * TAROK_RECORD_BYTES, cudaMemcpyHostToDevice, h->s_up));
         TK_CUDA(h, cudaEventRecord(h->ev_up[c], h->s_up));
@@ -660,6 +638,40 @@ int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_
     TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     if (stats_host) TK_CUDA(h, cudaMemcpyAsync(stats_host, h->e.stats, TAROK_STATS_LEN * 8, cudaMemcpyDeviceToHost, s));
     return 0;
+}
+
+// Third form of the host-buffer entry: the caller hands over permutation ROWS (what Igra.shuffle produces), the library
+// serialises each chunk into 24-byte deal records with `threads` host threads right before that chunk's upload, so PCIe
+// carries 24 instead of 57 bytes per deal and the packing of chunk c+1 overlaps the upload / play / download of chunk c.
+int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
+                              const uint8_t* king_host, uint64_t first_global_game_id, int threads, int16_t* scores_host,
+                              int64_t* stats_host, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!perm_host || !contract_host || !declarer_host) return fail(h, -1, "perm/contract/declarer host pointers are required");
+    if (threads < 1 || threads > 256) return fail(h, -1, "threads must be in 1..256");
+    DeviceGuard dg(h->device);
+    if (int rc = ensure_staging(h)) return rc;
+    if (!h->pin_rec) TK_CUDA(h, cudaHostAlloc((void**)&h->pin_rec, h->e.n_alloc * TAROK_RECORD_BYTES, cudaHostAllocDefault));
+    if (h->pool && tarok_pack_pool_threads(h->pool) != threads) { tarok_pack_pool_destroy(h->pool); h->pool = nullptr; }
+    if (!h->pool) h->pool = tarok_pack_pool_create(threads);
+    if (!h->pool) return fail(h, -4, "could not create the pack pool");
+    cudaStream_t s = S(stream);
+    TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
+    h->lock_plays = 0;
+    h->e.first_gid = first_global_game_id;
+    const u64 n = h->e.n, want = (u64)h->chunks;
+    // the previous call's uploads must have left the pinned scratch before it is overwritten
+    for (int c = 0; c < TK_MAX_CHUNKS; c++)
+        if (h->pack_used[c]) { TK_CUDA(h, cudaEventSynchronize(h->ev_up[c])); h->pack_used[c] = 0; }
+    // the pool packs the whole batch block by block in the background; chunk c is uploaded as soon as its blocks are done
+    tarok_pack_pool_begin(h->pool, perm_host, contract_host, declarer_host, king_host, n,
+                          (n >= (1ull << 18)) ? (n + want - 1) / want : h->e.n_alloc, h->pin_rec);
+    const u64 chunk = tarok_pack_pool_chunk_rows(h->pool);                   // whole pack blocks (a multiple of the CTA tile)
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    const int rc = packed_pipeline(h, n, chunk, nchunks, scores_host, stats_host, s);
+    if (rc)                                                 // the workers still read the caller's rows: let them finish
+        for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) tarok_pack_pool_wait_chunk(h->pool, c);
+    return rc;
 }
 
 // ---- observations ------------------------------------------------------------------------

@@ -334,29 +334,28 @@ __global__ void __launch_bounds__(CTA) k_set_deals(Env e, const uint8_t* __restr
     e.dpts[g] = 0;
 }
 
-// Compact deal record (24 B = three u64 words; include/tarok_b200.h "deal records"): three bit planes over the 54 card
-// ids give each card's owner code (0-3 seat, 4 talon), the ten spare bits of each word carry the talon order and the
-// forced contract.  Decoding is a handful of bitwise ops, no per-card loop except the six talon cards.
+// Compact deal record (24 B = three u64 words; include/tarok_b200.h "deal records"): two bit planes over the 54 card
+// ids give the seat of every hand card, w2 carries the six talon ids in talon order (= `torder` as it stands) and the
+// forced contract.  Decoding is a handful of bitwise ops plus six shifts for the talon set.
 struct DealRecord { u32 contract, declarer, king; };
 __device__ __forceinline__ Dealt deal_from_record(u64 w0, u64 w1, u64 w2, DealRecord& r, bool& ok) {
-    const u64 p0 = w0 & ALL54, p1 = w1 & ALL54, p2 = w2 & ALL54;
+    const u64 p0 = w0 & ALL54, p1 = w1 & ALL54;
     Dealt d;
-    d.h0 = ALL54 & ~(p0 | p1 | p2); d.h1 = p0 & ~p1 & ~p2; d.h2 = p1 & ~p0 & ~p2; d.h3 = p0 & p1 & ~p2;
-    d.talon = p2; d.order = 0;
-    ok = !(p2 & (p0 | p1)) && __popcll(d.h0) == 12 && __popcll(d.h1) == 12 && __popcll(d.h2) == 12 && __popcll(d.h3) == 12;
-    const u32 ranks = ((u32)(w0 >> 54) & 0x1FFu) | (((u32)(w1 >> 54) & 0x1FFu) << 9);
-    u64 t = p2;
-    u32 seen = 0;
+    d.order = w2 & ((1ull << 36) - 1ull);
+    u64 t = 0;
+    u32 top = 0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) {                         // talon cards in ascending id, each with its position 0..5
-        const u32 c = t ? (u32)__ffsll((long long)t) - 1u : 0u;
-        t &= t - 1;
-        const u32 pos = (ranks >> (3 * i)) & 7u;
-        seen |= 1u << pos;
-        d.order |= (u64)c << (6u * (pos < 6u ? pos : 0u));
+    for (int i = 0; i < 6; i++) {
+        const u32 c = (u32)(d.order >> (6 * i)) & 63u;
+        top = max(top, c);
+        t |= 1ull << c;
     }
-    ok = ok && seen == 0x3Fu;                              // (12,12,12,12) + six distinct positions => exactly six talon cards
-    r.contract = (u32)(w2 >> 54) & 15u; r.declarer = (u32)(w2 >> 58) & 3u; r.king = (u32)(w2 >> 60) & 7u;
+    d.talon = t;
+    d.h0 = ALL54 & ~(p0 | p1 | t); d.h1 = p0 & ~p1; d.h2 = p1 & ~p0; d.h3 = p0 & p1;
+    // two planes partition the ids into four classes; (12,12,12,12) + six distinct talon ids outside classes 1-3 <=> a deal
+    ok = top < 54u && !(t & (p0 | p1)) && __popcll(t) == 6 && __popcll(d.h0) == 12 && __popcll(d.h1) == 12
+         && __popcll(d.h2) == 12 && __popcll(d.h3) == 12;
+    r.contract = (u32)(w2 >> 36) & 15u; r.declarer = (u32)(w2 >> 40) & 3u; r.king = (u32)(w2 >> 42) & 7u;
     return d;
 }
 

@@ -87,19 +87,17 @@ def test_pack_records_is_the_documented_layout():
     assert bad == 0
     w = rec.numpy().view(np.uint64)
     for g in range(n):
-        code = [int((w[g, 0] >> np.uint64(c)) & np.uint64(1)) | int((w[g, 1] >> np.uint64(c)) & np.uint64(1)) << 1
-                | int((w[g, 2] >> np.uint64(c)) & np.uint64(1)) << 2 for c in range(54)]
+        w0, w1, w2 = (int(x) for x in w[g])
+        assert w0 >> 54 == 0 and w1 >> 54 == 0 and w2 >> 45 == 0
+        talon = [(w2 >> (6 * i)) & 63 for i in range(6)]
+        assert talon == perm[g, 48:].tolist()
+        code = [((w0 >> c) & 1) | ((w1 >> c) & 1) << 1 for c in range(54)]
+        assert all(code[c] == 0 for c in talon)
         for s in range(4):
-            assert sorted(c for c in range(54) if code[c] == s) == sorted(perm[g, 12 * s:12 * s + 12].tolist())
-        talon = [c for c in range(54) if code[c] == 4]
-        ranks = (int(w[g, 0] >> np.uint64(54)) & 0x1FF) | (int(w[g, 1] >> np.uint64(54)) & 0x1FF) << 9
-        order = [None] * 6
-        for i, c in enumerate(talon):
-            order[(ranks >> (3 * i)) & 7] = c
-        assert order == perm[g, 48:].tolist()
-        assert int(w[g, 2] >> np.uint64(54)) & 15 == contract[g]
-        assert int(w[g, 2] >> np.uint64(58)) & 3 == declarer[g]
-        assert int(w[g, 2] >> np.uint64(60)) & 7 == king[g]
+            assert sorted(c for c in range(54) if code[c] == s and c not in talon) == sorted(perm[g, 12 * s:12 * s + 12].tolist())
+        assert (w2 >> 36) & 15 == contract[g]
+        assert (w2 >> 40) & 3 == declarer[g]
+        assert (w2 >> 42) & 7 == king[g]
     perm[0, 0] = perm[0, 1]
     assert pack_records(perm, contract, declarer, None)[1] == 1
 
@@ -134,6 +132,14 @@ def test_pack_records_vector_and_scalar_serialisers_agree():
             for threads in (1, 3):
                 rec, bad = pack_records(perm, contract, declarer, king, threads=threads)
                 out[(scalar, threads)] = (rec.numpy().copy(), bad)
+        lib.tarok_pack_force_scalar(0)
+        import torch
+        for shift in (0, 1, 5):                  # 64-byte aligned output (non-temporal stores) and two unaligned ones
+            buf = torch.zeros(n * 3 + 16, dtype=torch.int64)
+            off = (-buf.data_ptr() % 64) // 8 + shift
+            view = buf[off:off + n * 3].view(n, 3)
+            rec, bad = pack_records(perm, contract, declarer, king, out=view, threads=2)
+            out[("vector, output shifted", shift)] = (rec.numpy().copy(), bad)
     finally:
         lib.tarok_pack_force_scalar(prev)
     ref, bad = out[(1, 1)]
