@@ -88,6 +88,8 @@ const char* tarok_last_error(const tarok_t* h);/* h may be NULL: last error of a
 #define TAROK_OPT_PDL 2        /* 1 (default): chain play_step launches with programmatic dependent launch */
 #define TAROK_OPT_MATERIALISE 4 /* 1 (default): tarok_score writes the full piles / Klop talon back; 0: scores + stats only */
 #define TAROK_OPT_CHUNKS 5      /* 1..32 (default 8): chunks of the upload/compute/download pipeline of tarok_rollout_host/_records */
+#define TAROK_OPT_DRAW_CACHE 7  /* trick positions whose in-kernel random draws are read from the cache the position-0 launch leaves behind
+                                   instead of recomputed: 0 off, 2 positions 1-2, 3 positions 1-3, -1 default by batch size; results identical */
 #define TAROK_OPT_LAZY_MASK 6   /* 1 (default): a chain of in-kernel random steps (tarok_steps_random, the stepwise rollouts) writes
                                    TAROK_F_MASK in its LAST launch only -- the interior masks cannot be observed; 0: every launch */
 #define TAROK_OPT_LOCKSTEP 3   /* 1 (default): play_step variants specialised per trick position for lock-step batches */

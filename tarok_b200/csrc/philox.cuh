@@ -143,26 +143,42 @@ __device__ __forceinline__ Words4 play_block(const Rng& rng, u64 gid, u32 trick)
     return philox_block(rng, gid >> 1, ST_PLAY, trick);
 }
 
-// POS >= 0: position in the trick known at compile time (lock-step batches): the lane pick becomes one select.
+// The 16-bit lane of (game, position in the trick) within the pair's block.
 template <int POS = -1>
-__device__ __forceinline__ u32 play_draw(const Words4& b, const Rng& rng, u64 gid, u32 t, u32 n) {
-    u32 w, x;
-    if (POS >= 0) {
+__device__ __forceinline__ u32 play_lane(const Words4& b, u64 gid, u32 t) {
+    u32 w;
+    if (POS >= 0) {                                        // position known at compile time (lock-step batches): one select
         w = ((u32)gid & 1u) ? b.w[2 + (POS >> 1)] : b.w[POS >> 1];
-        x = (POS & 1) ? (w >> 16) : (w & 0xFFFFu);
-    } else {
-        const u32 lane = ((u32)gid & 1u) * 4u + (t & 3u);
-        w = (lane >> 1) == 0 ? b.w[0] : (lane >> 1) == 1 ? b.w[1] : (lane >> 1) == 2 ? b.w[2] : b.w[3];
-        x = (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
+        return (POS & 1) ? (w >> 16) : (w & 0xFFFFu);
     }
+    const u32 lane = ((u32)gid & 1u) * 4u + (t & 3u);
+    w = (lane >> 1) == 0 ? b.w[0] : (lane >> 1) == 1 ? b.w[1] : (lane >> 1) == 2 ? b.w[2] : b.w[3];
+    return (lane & 1u) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+// Uniform draw on [0, n) from the 16-bit lane x (n <= 12 on this path).
+__device__ __forceinline__ u32 play_pick(u32 x, const Rng& rng, u64 gid, u32 t, u32 n) {
     const u32 m = x * n;
     const u32 lo = m & 0xFFFFu;
     if (__builtin_expect(lo < n, 0)) {
-        // 65536 % n for n = 0..15, four bits each (n <= 12 on this path)
+        // 65536 % n for n = 0..15, four bits each
         const u32 rem = (u32)((0x1234967024101000ull >> (4u * (n & 15u))) & 15ull);
         if (lo < rem) return draw_loop(rng.seed, gid, ST_PLAY_RETRY, t, n, 0u);
     }
     return m >> 16;
+}
+
+template <int POS = -1>
+__device__ __forceinline__ u32 play_draw(const Words4& b, const Rng& rng, u64 gid, u32 t, u32 n) {
+    return play_pick(play_lane<POS>(b, gid, t), rng, gid, t, n);
+}
+
+// The lanes of trick positions 1..3 for the two games of a pair (even game in the low half): what the position-0 launch
+// of a lock-step chain leaves behind for the three launches that follow (tarok_kernels.cuh "draw cache").
+__device__ __forceinline__ u32 play_lanes_of_pair(const Words4& b, int pos) {
+    return pos == 1 ? (b.w[0] >> 16) | (b.w[2] & 0xFFFF0000u)
+         : pos == 2 ? (b.w[1] & 0xFFFFu) | (b.w[3] << 16)
+                    : (b.w[1] >> 16) | (b.w[3] & 0xFFFF0000u);
 }
 
 }  // namespace tk

@@ -26,6 +26,7 @@ struct tarok_env {
     int pdl;                                   // chain play_step launches with programmatic dependent launch
     int lockstep;                              // pass the lock-step hint to play_step (specialised per trick position)
     int lock_plays;                            // plays made by every live game since the last deal, -1 = unknown
+    uint32_t epoch;                            // draw-cache epoch (set_first_gid)
     int lazy_mask;                             // chains of random steps write legal masks in their last launch only (default on)
     int materialise;                           // tarok_score writes the materialised piles / talon back (default on)
     int chunks;                                // upload/compute/download pipeline depth of the host-buffer entries
@@ -87,6 +88,19 @@ static void free_staging(tarok_env* h) {
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     h->staging_ready = 0;
 }
+
+// Every change of the first global game id starts a new epoch of the draw cache (tarok_kernels.cuh, step_lock): entries
+// written under another id can never match a tag again.  28 bits of epoch, 4 bits of trick index.
+static inline void set_first_gid(tarok_env* h, u64 first_gid) {
+    h->e.first_gid = first_gid;
+    h->epoch = (h->epoch % 0x0FFFFFFFu) + 1u;                 // 1 .. 2^28 - 1: never 0, the value of a cleared entry
+    h->e.rc_epoch = h->epoch << 4;
+}
+
+// Draw cache policy: all three positions while the state a chain of steps touches stays inside the 126 MB L2 (the cache
+// adds 12 B per game to it); beyond that the trick-closing launch is HBM-bound and computes its own block, positions 1-2
+// (ALU-bound) keep reading theirs.
+static inline u32 default_draw_cache_rows(u64 n_alloc) { return n_alloc <= (3ull << 20) ? 3u : 2u; }
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline unsigned grid1(u64 n_alloc) { return (unsigned)(n_alloc / tk::CTA); }        // one game per lane
@@ -154,6 +168,10 @@ int tarok_set_option(tarok_t* h, int option, int64_t value) {
     if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
     if (option == TAROK_OPT_MATERIALISE && (value == 0 || value == 1)) { h->materialise = (int)value; return 0; }
     if (option == TAROK_OPT_LAZY_MASK && (value == 0 || value == 1)) { h->lazy_mask = (int)value; return 0; }
+    if (option == TAROK_OPT_DRAW_CACHE && (value == -1 || value == 0 || value == 2 || value == 3)) {
+        h->e.rc_rows = value >= 0 ? (u32)value : default_draw_cache_rows(h->e.n_alloc);
+        return 0;
+    }
     if (option == TAROK_OPT_CHUNKS && value >= 1 && value <= TK_MAX_CHUNKS) { h->chunks = (int)value; return 0; }
     return fail(h, -1, "unknown option %d / value %lld", option, (long long)value);
 }
@@ -181,7 +199,8 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     memset(h->ev_up, 0, sizeof(h->ev_up)); memset(h->ev_done, 0, sizeof(h->ev_done));
     h->cta_hist = nullptr; h->pool = nullptr; h->pin_rec = nullptr; memset(h->pack_used, 0, sizeof(h->pack_used));
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
-    h->e.n = n_games; h->e.n_alloc = na; h->e.first_gid = 0;
+    h->e.n = n_games; h->e.n_alloc = na; h->epoch = 0; set_first_gid(h, 0);
+    h->e.rc_rows = default_draw_cache_rows(na);
     tk::philox_keys_init(h->e.rng, seed);
 #define TK_ALLOC(ptr, bytes)                                                       \
     do {                                                                           \
@@ -204,6 +223,8 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     cudaMemset(h->e.tricklog, 0, 12 * na * 4);
     TK_ALLOC(h->e.dpts, na);
     cudaMemset(h->e.dpts, 0, na);
+    TK_ALLOC(h->e.rcache, 3 * (na / 2) * sizeof(uint2));
+    cudaMemset(h->e.rcache, 0, 3 * (na / 2) * sizeof(uint2));
     if (flags & TAROK_FLAG_HISTORY) {
         TK_ALLOC(h->e.hist, 48 * na);
         TK_ALLOC(h->e.hands0, 4 * na * 8);
@@ -237,7 +258,7 @@ int tarok_destroy(tarok_t* h) {
     DeviceGuard dg(h->device);
     cudaFree(h->e.hands); cudaFree(h->e.piles); cudaFree(h->e.talon); cudaFree(h->e.torder);
     cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats); cudaFree(h->e.tricklog);
-    cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist); cudaFree(h->e.dpts);
+    cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist); cudaFree(h->e.dpts); cudaFree(h->e.rcache);
     free_staging(h);
     cudaFree(h->cta_hist);
     tarok_pack_pool_destroy(h->pool);
@@ -261,7 +282,7 @@ int tarok_deal(tarok_t* h, uint64_t first_global_game_id, void* stream) {
     TK_CHECK_HANDLE(h);
     DeviceGuard dg(h->device);
     h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
+    set_first_gid(h, first_global_game_id);
     clear_hist(h, stream);
     tk::k_deal<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e);
     TK_LAUNCH_OK(h);
@@ -273,7 +294,7 @@ int tarok_set_deals(tarok_t* h, const uint8_t* perm_dev, uint64_t first_global_g
     if (!perm_dev) return fail(h, -1, "perm_dev is null");
     DeviceGuard dg(h->device);
     h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
+    set_first_gid(h, first_global_game_id);
     clear_hist(h, stream);
     tk::k_set_deals<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, perm_dev);
     TK_LAUNCH_OK(h);
@@ -464,7 +485,7 @@ int tarok_setup_synth(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, 
         return fail(h, -1, "bad mode %u", mode);
     DeviceGuard dg(h->device);
     h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
+    set_first_gid(h, first_global_game_id);
     clear_hist(h, stream);
     tk::k_setup_synth<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode);
     TK_LAUNCH_OK(h);
@@ -489,7 +510,7 @@ int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id
         return fail(h, -1, "bad mode %u", mode);
     DeviceGuard dg(h->device);
     h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
+    set_first_gid(h, first_global_game_id);
     clear_hist(h, stream);
     tk::k_rollout_fused<tk::DEALS_PHILOX><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode, nullptr, nullptr, nullptr, nullptr,
                                                                            h->e.scores, 1, 0ull);
@@ -578,7 +599,7 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
     cudaStream_t s = S(stream);
     TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
     h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
+    set_first_gid(h, first_global_game_id);
     if (fused) return rollout_host_fused(h, perm_host, 54, contract_host, declarer_host, king_host, scores_host, stats_host, s);
     TK_CUDA(h, cudaMemcpyAsync(h->st_perm, perm_host, n * 54, cudaMemcpyHostToDevice, s));
     TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, s));
@@ -605,7 +626,7 @@ int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t fir
     cudaStream_t s = S(stream);
     TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
     h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
+    set_first_gid(h, first_global_game_id);
     return rollout_host_fused(h, (const uint8_t*)records_host, TAROK_RECORD_BYTES, nullptr, nullptr, nullptr, scores_host,
                               stats_host, s);
 }
@@ -658,7 +679,7 @@ int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_
     cudaStream_t s = S(stream);
     TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
     h->lock_plays = 0;
-    h->e.first_gid = first_global_game_id;
+    set_first_gid(h, first_global_game_id);
     const u64 n = h->e.n, want = (u64)h->chunks;
     // the previous call's uploads must have left the pinned scratch before it is overwritten
     for (int c = 0; c < TK_MAX_CHUNKS; c++)

@@ -29,6 +29,9 @@ constexpr int TILE = 2 * CTA;          // games per CTA in the 2-games-per-lane 
 #ifndef TK_STEP_BLOCKS_RANDOM
 #define TK_STEP_BLOCKS_RANDOM 5   // 48 registers (a few spilled words at the trick-closing position): 69.2 -> 66.1 us at 8 M deals, = at 1 M
 #endif
+#ifndef TK_STEP_BLOCKS_RANDOM_012
+#define TK_STEP_BLOCKS_RANDOM_012 TK_STEP_BLOCKS_RANDOM   // trick positions 0-2 (lighter than the trick-closing one)
+#endif
 #ifndef TK_STEP_BLOCKS_FORCED
 #define TK_STEP_BLOCKS_FORCED 5   // 46-48 registers: 8.63 -> 8.22 us per launch at 1 M deals (6 blocks = 40 registers spills and loses)
 #endif
@@ -41,6 +44,9 @@ struct Env {
     uint8_t* hist; u64* hands0; u64* discard; float* qmax_hist; long long* stats;
     u32* tricklog;                         // [12][n_alloc]: trick k of game g = 4 cards (24 bit, play order) | card points << 24 | called-king flag << 29 | winner << 30
     uint8_t* dpts;                         // [n_alloc]: card points of the declarer's discards (scoring reads this instead of the piles)
+    uint2* rcache;                         // [3][n_alloc / 2] draw cache: {tag, the pair's 16-bit lanes of trick position 1 + row}
+    u32 rc_epoch;                          // high bits of a valid tag: bumped whenever first_gid is (re)set; low 4 bits = trick
+    u32 rc_rows;                           // trick positions 1..rc_rows use the cache (0 = off, 2, 3): TAROK_OPT_DRAW_CACHE
     u64 n, n_alloc, first_gid;
     Rng rng;                               // seed + precomputed Philox round keys
 };
@@ -766,12 +772,37 @@ __device__ __forceinline__ void step_pair_general(const Env& e, u32 g, ulonglong
     step_pair_any<RANDOM, MASK>(e, g, m, a0, a1, s0, s1, s2, s3, act);
 }
 
+// Cold paths of the lock-step kernels, kept out of line so that their registers and code do not weigh on the hot path:
+// the warp whose vote failed, and the draw-cache miss at trick positions 1-3.
+#ifndef TK_SEL8_LATE
+#define TK_SEL8_LATE 0
+#endif
+#ifndef TK_COLD_NOINLINE
+#define TK_COLD_NOINLINE 0   // out of line measured slower (profiles/r02/step_ab_run6.txt): 8.78 vs 7.98 us per launch at 1 M deals
+#endif
+#if TK_COLD_NOINLINE
+#define TK_COLD __noinline__
+#else
+#define TK_COLD __forceinline__
+#endif
+template <bool RANDOM, int HAVE, bool MASK>
+__device__ TK_COLD void step_pair_general_cold(const Env& e, u32 g, ulonglong2 m, bool a0, bool a1, u32 act,
+                                                    ulonglong2 hm, ulonglong2 n0, ulonglong2 n1, ulonglong2 n2) {
+    step_pair_general<RANDOM, HAVE, MASK>(e, g, m, a0, a1, act, hm, n0, n1, n2);
+}
+template <int POS>
+__device__ TK_COLD u32 pair_lanes_cold(const Env& e, u32 g, u32 trick, bool a1) {
+    Words4 r0, r1;
+    pair_blocks(e, g, trick, trick, a1, r0, r1);
+    return play_lane<POS>(r0, e.first_gid + g, (u32)POS) | (play_lane<POS>(r1, e.first_gid + g + 1, (u32)POS) << 16);
+}
+
 // ---- lock-step path: every live game of the warp has made `hint` plays, so the trick position POS = hint & 3 is a
 // compile-time constant: the mover is slot POS for everybody, the trick-position arithmetic and the trick-end branch fold.
 // hm = slot POS (the mover's hand); POS < 3: n0 = slot POS + 1 (the next seat); POS == 3: n0, n1, n2 = slots 0, 1, 2.
 template <bool RANDOM, int POS, bool MASK>
 __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u64& hm, u64& n0, u64& n1, u64& n2, u32 card,
-                                               const Words4& rnd, u64& next_mask, u32& log_out) {
+                                               u32 x16, u64& next_mask, u32& log_out, const uint8_t* __restrict__ sel8) {
     const u32 na = (u32)e.n_alloc;
     const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 leader = (lo >> M_LEADER) & 3u, kf = (lo >> M_KLOPFAM) & 1u;
@@ -779,7 +810,7 @@ __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u
     const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
     if (RANDOM) {
         const u64 legal = legal_moves(hm, POS != 0, hi & 63u, kf);
-        card = nth_set_bit(legal, play_draw<POS>(rnd, e.rng, e.first_gid + g, plays, (u32)__popcll(legal)));
+        card = nth_set_bit_lut(legal, play_pick(x16, e.rng, e.first_gid + g, plays, (u32)__popcll(legal)), sel8);
     }
     PlayResult pr;
     meta = play_card<!RANDOM, POS, false>(meta, hm, card, 0ull, 0ull, pr);
@@ -803,6 +834,12 @@ template <bool RANDOM, int POS, bool MASK>
 __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restrict__ action, int hint) {
     const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
     const u32 na = (u32)e.n_alloc;                 // the grid covers n_alloc exactly: no partial warps
+    __shared__ __align__(16) uint8_t sel8[RANDOM ? SELECT8_SMEM : 16];
+    uint2 sel8_mine = {0u, 0u};                    // this thread's 8 bytes of the byte-select table (tarok_rules.cuh): independent of
+    if (RANDOM) sel8_mine = select8_fetch();       // the previous launch, so the load is issued before the dependency wait
+#if !TK_SEL8_LATE
+    if (RANDOM) { select8_store(sel8, sel8_mine); __syncthreads(); }
+#endif
     pdl_wait();                                    // the previous step's writes are visible from here on
     // every load is issued before the first use: one memory round trip per step
     ulonglong2 m = ld2(e.meta + g);
@@ -812,6 +849,22 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     if (POS == 3) { n1 = ld2(e.hands + (na + g)); n2 = ld2(e.hands + (2 * na + g)); }
     u32 act = 0;
     if (!RANDOM) act = load_actions(action, g, e.n);
+    // draw cache: the pair's Philox block is computed by the position-0 launch of a trick, which leaves the lanes of
+    // positions 1-3 behind ({tag, lanes}, 8 B per pair and position); the three launches that follow read 8 B instead of
+    // running the ten rounds again.  The tag (epoch of first_gid | trick) makes a stale or never-written entry harmless:
+    // the block is then computed here as before.  Lanes straddle two pairs when first_gid is odd: no cache then.
+    constexpr u32 UPOS = POS > 0 ? (u32)POS : 0u;
+    bool cached = RANDOM && e.rc_rows != 0u && !((u32)e.first_gid & 1u);
+    if constexpr (POS > 0) cached = cached && UPOS <= e.rc_rows;
+    const u32 tag = e.rc_epoch | ((u32)hint >> 2);
+    uint2 rc = {0u, 0u};
+    if (cached && POS > 0) rc = e.rcache[(UPOS > 0u ? UPOS - 1u : 0u) * (na >> 1) + (g >> 1)];
+#if TK_SEL8_LATE
+    if (RANDOM) {                                  // behind the state loads in program order: all of them are in flight together
+        select8_store(sel8, sel8_mine);
+        __syncthreads();
+    }
+#endif
     const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act & 0xFFu) != CARD_SKIP),
                a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act >> 8) != CARD_SKIP);
     // plays sit in the top byte of the high word and the bits above them are clear for every live game
@@ -819,14 +872,32 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
                       && (!a1 || ((u32)(m.y >> 32) >> (M_PLAYS - 32)) == (u32)hint);
     const bool lock = __all_sync(0xFFFFFFFFu, in_step);            // the hint is only a hint: each warp checks it
     if (!a0 && !a1) return;
-    if (!lock) { step_pair_general<RANDOM, POS, MASK>(e, g, m, a0, a1, act, hm, n0, n1, n2); return; }
-    Words4 r0 = {{0, 0, 0, 0}}, r1 = {{0, 0, 0, 0}};
-    // the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used
-    if (RANDOM) pair_blocks(e, g, (u32)hint >> 2, (u32)hint >> 2, a1, r0, r1);
+    if (!lock) { step_pair_general_cold<RANDOM, POS, MASK>(e, g, m, a0, a1, act, hm, n0, n1, n2); return; }
+    u32 x0 = 0, x1 = 0;                            // the two games' 16-bit lanes of this play
+    if (RANDOM) {
+        if (POS > 0 && cached && rc.x == tag) {
+            x0 = rc.y & 0xFFFFu; x1 = rc.y >> 16;
+        } else if (POS > 0 && cached) {            // a miss (stale or never-written entry): rare, out of line
+            const u32 x = pair_lanes_cold<POS>(e, g, (u32)hint >> 2, a1);
+            x0 = x & 0xFFFFu; x1 = x >> 16;
+        } else {
+            // the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used
+            Words4 r0, r1;
+            pair_blocks(e, g, (u32)hint >> 2, (u32)hint >> 2, a1, r0, r1);
+            x0 = play_lane<POS>(r0, e.first_gid + g, (u32)hint);
+            x1 = play_lane<POS>(r1, e.first_gid + g + 1, (u32)hint);
+            if (POS == 0 && cached) {
+                uint2* rcp = e.rcache + (g >> 1);
+                rcp[0] = make_uint2(tag, play_lanes_of_pair(r0, 1));
+                rcp[na >> 1] = make_uint2(tag, play_lanes_of_pair(r0, 2));
+                if (e.rc_rows > 2u) rcp[na] = make_uint2(tag, play_lanes_of_pair(r0, 3));
+            }
+        }
+    }
     u64 k0 = 0, k1 = 0;
     u32 l0 = 0, l1 = 0;                            // trick-log entries (POS == 3); 0 = nothing to append
-    if (a0) step_game_lock<RANDOM, POS, MASK>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, r0, k0, l0);
-    if (a1) step_game_lock<RANDOM, POS, MASK>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, r1, k1, l1);
+    if (a0) step_game_lock<RANDOM, POS, MASK>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, x0, k0, l0, sel8);
+    if (a1) step_game_lock<RANDOM, POS, MASK>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, x1, k1, l1, sel8);
     st2(e.hands + (POS * na + g), hm.x, hm.y);     // a game that did not move gets its slot back unchanged
     if (POS == 3) {
         st2(e.hands + g, n0.x, n0.y); st2(e.hands + (na + g), n1.x, n1.y); st2(e.hands + (2 * na + g), n2.x, n2.y);
@@ -838,7 +909,8 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
         else row[1] = l1;
     }
     st2(e.meta + g, m.x, m.y);
-    store_masks<RANDOM, MASK>(e, g, m, a0, a1, k0, k1);
+    // an in-kernel pick is always legal and only the trick-closing play can end a game: nothing to clear at positions 0-2
+    if (MASK || !RANDOM || POS == 3) store_masks<RANDOM, MASK>(e, g, m, a0, a1, k0, k1);
 }
 
 // `hint` = the number of plays every live game has made so far (lock-step pipelines know it on the host); POS = hint & 3
@@ -848,8 +920,9 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
 // caller can see those masks, so the next seat's slot is neither read nor its legal set computed or stored -- 16 of the
 // 48 bytes a step moves at trick positions 0-2 -- and only the chain's last launch produces the masks.
 template <bool RANDOM, int POS, bool MASK = true>
-__global__ void __launch_bounds__(CTA, RANDOM ? TK_STEP_BLOCKS_RANDOM : TK_STEP_BLOCKS_FORCED)
-k_step(Env e, const uint8_t* __restrict__ action, int hint) {
+__global__ void __launch_bounds__(CTA, RANDOM ? ((POS >= 0 && POS < 3) ? TK_STEP_BLOCKS_RANDOM_012 : TK_STEP_BLOCKS_RANDOM) : TK_STEP_BLOCKS_FORCED)
+k_step(const __grid_constant__ Env e, const uint8_t* __restrict__ action, int hint) {   // __grid_constant__: the out-of-line cold
+                                                                                         // paths take `e` by reference without a stack copy
     pdl_launch_dependents();
     if constexpr (POS >= 0) {
         step_lock<RANDOM, POS, MASK>(e, action, hint);
@@ -1102,11 +1175,11 @@ struct FusedGame { u64 h0, h1, h2, h3, p0, p1, p2, p3, talon, order, meta; };   
 // registers are re-seated from the winner when the trick closes.
 template <int J>
 __device__ __forceinline__ void fused_play(FusedGame& f, const Words4& blk, const Rng& rng, u64 gid, u32 trick, bool klop,
-                                           uint8_t* hist_row, u64 na, u32* log_row = nullptr) {
+                                           uint8_t* hist_row, u64 na, const uint8_t* __restrict__ sel8, u32* log_row = nullptr) {
     u64& hand = J == 0 ? f.h0 : J == 1 ? f.h1 : J == 2 ? f.h2 : f.h3;
     const u64 legal = legal_moves(hand, J != 0, (u32)(f.meta >> 32) & 63u, klop);
     const u32 n = (u32)__popcll(legal);
-    const u32 card = nth_set_bit(legal, play_draw<J>(blk, rng, gid, trick * 4 + J, n));
+    const u32 card = nth_set_bit_lut(legal, play_draw<J>(blk, rng, gid, trick * 4 + J, n), sel8);
     if (hist_row) hist_row[(u64)J * na] = (uint8_t)((((((u32)f.meta >> M_LEADER) + (u32)J) & 3u) << 6) | card);
     PlayResult pr;
     f.meta = play_card<false, J>(f.meta, hand, card, f.talon, f.order, pr);
@@ -1128,6 +1201,8 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
                                                        const uint8_t* __restrict__ fk, u64* __restrict__ out, int write_state,
                                                        u64 g0) {
     extern __shared__ __align__(16) uint8_t shp[];
+    __shared__ __align__(16) uint8_t sel8[SELECT8_SMEM];  // byte-select table of the uniform picks (tarok_rules.cuh)
+    select8_to_shared(sel8);                              // made visible by the barrier below (DEALS_PERM) or the one that follows
     const u64 base = g0 + (u64)blockIdx.x * CTA;          // g0: first game of this launch (chunked host pipeline)
     u64 g = base + threadIdx.x;
     const u64 na = e.n_alloc;
@@ -1140,8 +1215,8 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
             if (vec_ok && b + 16 <= total) *reinterpret_cast<uint4*>(shp + v * 16) = *reinterpret_cast<const uint4*>(perm + b);
             else for (int k = 0; k < 16; k++) shp[v * 16 + k] = (b + k < total) ? perm[b + k] : 0xFF;
         }
-        __syncthreads();
     }
+    __syncthreads();
     bool live = g < e.n, err = false;
     u64 meta = meta_pad(), packed = 0;
     u64 h0 = 0, h1 = 0, h2 = 0, h3 = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0, talon = 0, order = 0;
@@ -1190,10 +1265,10 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         for (u32 trick = 0; trick < 12 && mget(fg.meta, M_PHASE, 2) == PH_PLAY; trick++) {
             Words4 blk = play_block(e.rng, gid, trick);                // 4 plays = half of one Philox block
             uint8_t* hrow = (e.hist && write_state) ? e.hist + (u64)(trick * 4) * na + g : nullptr;
-            fused_play<0>(fg, blk, e.rng, gid, trick, klop, hrow, na);
-            fused_play<1>(fg, blk, e.rng, gid, trick, klop, hrow, na);
-            fused_play<2>(fg, blk, e.rng, gid, trick, klop, hrow, na);
-            fused_play<3>(fg, blk, e.rng, gid, trick, klop, hrow, na, write_state ? e.tricklog + (u64)trick * na + g : nullptr);
+            fused_play<0>(fg, blk, e.rng, gid, trick, klop, hrow, na, sel8);
+            fused_play<1>(fg, blk, e.rng, gid, trick, klop, hrow, na, sel8);
+            fused_play<2>(fg, blk, e.rng, gid, trick, klop, hrow, na, sel8);
+            fused_play<3>(fg, blk, e.rng, gid, trick, klop, hrow, na, sel8, write_state ? e.tricklog + (u64)trick * na + g : nullptr);
         }
         h0 = fg.h0; h1 = fg.h1; h2 = fg.h2; h3 = fg.h3; p0 = fg.p0; p1 = fg.p1; p2 = fg.p2; p3 = fg.p3;
         talon = fg.talon; meta = fg.meta;

@@ -80,6 +80,40 @@ __device__ __forceinline__ u32 nth_set_bit(u64 m, u32 r) {
     pos += (r >= (w & 1u)) ? 1u : 0u;
     return pos;
 }
+// The last three levels of that descent as a table: SELECT8[8 * v + r] = position of the r-th set bit of the byte v
+// (r < popc(v); 0 otherwise).  2 KB, built at compile time; the hot kernels copy it into shared memory once per CTA
+// (select8_to_shared) and finish the descent with one LDS instead of ~20 integer instructions -- the integer ALU pipe is
+// what bounds play_step.
+struct Select8 { uint8_t v[2048]; };
+constexpr Select8 make_select8() {
+    Select8 t{};
+    for (int v = 0; v < 256; v++) {
+        int r = 0;
+        for (int b = 0; b < 8; b++)
+            if ((v >> b) & 1) t.v[8 * v + r++] = (uint8_t)b;
+    }
+    return t;
+}
+__device__ const Select8 SELECT8 = make_select8();
+constexpr int SELECT8_SMEM = 2048 + 16;                   // the slack keeps a stray index (r up to 11 on a garbage lane) inside
+// All threads of the CTA (CTA == 256: 8 bytes each), then a barrier before the first lookup.
+__device__ __forceinline__ uint2 select8_fetch() { return reinterpret_cast<const uint2*>(SELECT8.v)[threadIdx.x]; }
+__device__ __forceinline__ void select8_store(uint8_t* sh, uint2 mine) {
+    reinterpret_cast<uint2*>(sh)[threadIdx.x] = mine;
+    if (threadIdx.x < 4) reinterpret_cast<u32*>(sh + 2048)[threadIdx.x] = 0u;
+}
+__device__ __forceinline__ void select8_to_shared(uint8_t* sh) { select8_store(sh, select8_fetch()); }
+__device__ __forceinline__ u32 nth_set_bit_lut(u64 m, u32 r, const uint8_t* __restrict__ sel8) {
+    const u32 lo = (u32)m, hi = (u32)(m >> 32);
+    const u32 cl = __popc(lo);
+    const bool up = r >= cl;
+    u32 w = up ? hi : lo;
+    r -= up ? cl : 0u;
+    u32 pos = up ? 32u : 0u, c;
+    c = __popc(w & 0xFFFFu); if (r >= c) { r -= c; w >>= 16; pos += 16; }
+    c = __popc(w & 0xFFu);   if (r >= c) { r -= c; w >>= 8;  pos += 8; }
+    return pos + sel8[(w & 0xFFu) * 8u + r];
+}
 __device__ __forceinline__ u64 suit_mask_of(u32 card) {
     return card >= 32 ? TAROKS : (0xFFull << (card & 24u));
 }

@@ -171,6 +171,11 @@ class TarokEnv:
         """Chains of in-kernel random steps write the legal masks in their last launch only (default on)."""
         self._check(self._lib.tarok_set_option(self._h, 6, 1 if on else 0))
 
+    def set_draw_cache(self, rows: int):
+        """Trick positions (1..rows) whose in-kernel random draws are read from the cache the position-0 launch of a trick
+        leaves behind instead of recomputed: 0 off, 2, 3; -1 = the default for this batch size.  Results are identical."""
+        self._check(self._lib.tarok_set_option(self._h, 7, int(rows)))
+
     def set_lockstep(self, on: bool):
         """Trick-position-specialised play_step for lock-step batches (default on; the kernel verifies the hint)."""
         self._check(self._lib.tarok_set_option(self._h, 3, 1 if on else 0))

@@ -245,6 +245,46 @@ def test_chain_of_random_steps_with_lazy_masks_leaves_the_same_state(mode):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("gid0,rows", [(6, 3), (6, 2), (7, 3), (6, 0)])
+def test_draw_cache_never_changes_a_draw(gid0, rows):
+    """The position-0 launch of a trick leaves the pair's random lanes of positions 1-3 behind for the next three launches
+    (the draw cache).  Whatever the interleaving -- the opening card supplied from outside (nothing cached for that trick: the
+    entry carries the previous trick's tag), a supplied card in the middle of a cached trick, single launches and chains,
+    the same handle re-dealt under another first game id (another epoch) and back -- every in-kernel draw must be the one a
+    plain random rollout makes, because a draw depends on (seed, game id, play index) only."""
+    import torch
+    n, seed = 30011, 99
+    a = _env(n, seed=seed, history=True)
+    a.rollout(16, first_game_id=gid0, fused=False)
+    want = a.hist[:, :n].clone()                                  # [48, n] seat << 6 | card
+    want_scores = a.scores[:n].cpu().numpy().copy()
+    b = _env(n, seed=seed, history=True)
+    b.set_draw_cache(rows)                                        # positions 1..rows read the cache (a is on the default, 3)
+    b.rollout(16, first_game_id=gid0 + 2 * n, fused=False)        # fills the cache under another epoch and other game ids
+    b.deal(gid0)
+    b.force_contract_synth(16)
+    b.exchange_synth(False)
+    supplied = {0, 5, 10, 15, 16, 17, 18, 19, 24, 30, 33, 44}
+    t = 0
+    while t < 48:
+        if t in supplied:
+            b.step((want[t] & 63).contiguous())
+            t += 1
+        else:
+            run = 1
+            while t + run < 48 and (t + run) not in supplied and run < 3 + (t % 5):
+                run += 1
+            b.step_random(run)
+            t += run
+        assert (b.hist[:t, :n] == want[:t]).all(), t
+    assert (b.score().cpu().numpy() == want_scores).all()
+    # back to the first handle: same ids again (a new epoch on a cache holding the same blocks), chained
+    a.reset_stats()
+    a.rollout(16, first_game_id=gid0, fused=False)
+    assert (a.hist[:, :n] == want).all() and (a.scores[:n].cpu().numpy() == want_scores).all()
+    a.close(); b.close()
+
+
 def test_desynchronised_batch_takes_the_general_path(oracle):
     """Games that start playing at different times (here: the contracts without a talon exchange play three cards before
     the others have exchanged) break the lock-step hint inside most warps; the per-warp vote must then send them through

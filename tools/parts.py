@@ -28,6 +28,9 @@ def main():
     rec.close()
     env = TarokEnv(n, seed=1)
     env.set_materialise(False)
+    if os.environ.get("TAROK_DRAW_CACHE"):
+        env.set_draw_cache(int(os.environ["TAROK_DRAW_CACHE"]))
+        out["draw_cache"] = int(os.environ["TAROK_DRAW_CACHE"])
     if os.environ.get("TAROK_LAZY_MASK") == "0":
         env.set_lazy_mask(False)
         out["lazy_mask"] = 0
