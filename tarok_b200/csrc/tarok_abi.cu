@@ -18,6 +18,7 @@ using tk::u64;
 using tk::u32;
 
 #define TK_MAX_CHUNKS 32
+#define TK_GRAPH_MODES 20                       /* contracts 0..9, synthetic modes 16..18 */
 
 struct tarok_env {
     int device;
@@ -27,6 +28,11 @@ struct tarok_env {
     int lockstep;                              // pass the lock-step hint to play_step (specialised per trick position)
     int lock_plays;                            // plays made by every live game since the last deal, -1 = unknown
     uint32_t epoch;                            // draw-cache epoch (set_first_gid)
+    int use_graph;                             // tarok_rollout_stepwise replays a captured CUDA graph (TAROK_OPT_GRAPH, default on)
+    cudaGraphExec_t graphs[TK_GRAPH_MODES];    // one per rollout mode, captured on first use; dropped when an option changes
+    cudaStream_t s_cap;                        // private stream the graphs are captured on
+    tk::RunParams* run_dev;                    // {first_gid, rc_epoch} the GRAPH kernel variants read (rewritten before every replay)
+    int capturing;                             // launch the GRAPH variants (set while a rollout graph is being captured)
     int lazy_mask;                             // chains of random steps write legal masks in their last launch only (default on)
     int materialise;                           // tarok_score writes the materialised piles / talon back (default on)
     int chunks;                                // upload/compute/download pipeline depth of the host-buffer entries
@@ -117,7 +123,7 @@ struct DeviceGuard {
 // play_step launcher.  Default: the plain kernel, one 512-game tile per CTA, compiled per trick position for lock-step
 // batches (the hint) with programmatic dependent launch; TAROK_OPT_STEP_IMPL=2 selects the persistent TMA-staged variant
 // (one CTA per resident slot, 4 per SM), which measures slower on B200 and is kept for comparison (tools/step_ab.py).
-template <bool RANDOM, bool MASK = true>
+template <bool RANDOM, bool MASK = true, bool GRAPH = false>
 static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     const unsigned tiles = grid2(h->e.n_alloc);
     const unsigned resident = (unsigned)h->sm_count * 4u;
@@ -136,11 +142,11 @@ static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     else {
         const int hint = h->lockstep ? h->lock_plays : -1;
         switch (hint >= 0 ? (hint & 3) : 4) {
-            case 0: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 0, MASK>, h->e, action, hint); break;
-            case 1: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 1, MASK>, h->e, action, hint); break;
-            case 2: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 2, MASK>, h->e, action, hint); break;
-            case 3: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 3, MASK>, h->e, action, hint); break;
-            default: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, -1, MASK>, h->e, action, hint); break;
+            case 0: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 0, MASK, GRAPH>, h->e, action, hint); break;
+            case 1: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 1, MASK, GRAPH>, h->e, action, hint); break;
+            case 2: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 2, MASK, GRAPH>, h->e, action, hint); break;
+            case 3: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, 3, MASK, GRAPH>, h->e, action, hint); break;
+            default: cudaLaunchKernelEx(&cfg, tk::k_step<RANDOM, -1, MASK, GRAPH>, h->e, action, hint); break;
         }
     }
     // lock-step bookkeeping (only a hint to the kernel, which verifies it per warp): every live game has made
@@ -152,8 +158,14 @@ static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
 // ones); with the TMA-staged implementation or the eager-mask option every launch does.
 static int random_chain(tarok_env* h, uint32_t count, cudaStream_t s) {
     for (uint32_t t = 0; t < count; t++) {
-        if (t + 1 < count && h->lazy_mask && h->step_impl != 2) launch_step<true, false>(h, nullptr, s);
-        else launch_step<true, true>(h, nullptr, s);
+        const bool lazy = t + 1 < count && h->lazy_mask && h->step_impl != 2;
+        if (h->capturing) {                                // kernels of a rollout graph: run parameters from device memory
+            if (lazy) launch_step<true, false, true>(h, nullptr, s);
+            else launch_step<true, true, true>(h, nullptr, s);
+        } else {
+            if (lazy) launch_step<true, false>(h, nullptr, s);
+            else launch_step<true, true>(h, nullptr, s);
+        }
         TK_LAUNCH_OK(h);
     }
     return 0;
@@ -161,8 +173,16 @@ static int random_chain(tarok_env* h, uint32_t count, cudaStream_t s) {
 
 extern "C" {
 
+// The captured graphs freeze every option (kernel variant, launch attributes, parameters): any change drops them.
+static void drop_graphs(tarok_env* h) {
+    for (int m = 0; m < TK_GRAPH_MODES; m++)
+        if (h->graphs[m]) { cudaGraphExecDestroy(h->graphs[m]); h->graphs[m] = nullptr; }
+}
+
 int tarok_set_option(tarok_t* h, int option, int64_t value) {
     TK_CHECK_HANDLE(h);
+    drop_graphs(h);
+    if (option == TAROK_OPT_GRAPH && (value == 0 || value == 1)) { h->use_graph = (int)value; return 0; }
     if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 2) { h->step_impl = (int)value; return 0; }
     if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
     if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
@@ -197,6 +217,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     h->s_up = h->s_down = nullptr; h->ev_fork = h->ev_join = nullptr; h->staging_ready = 0;
     memset(h->ev_up, 0, sizeof(h->ev_up)); memset(h->ev_done, 0, sizeof(h->ev_done));
+    h->use_graph = 1; memset(h->graphs, 0, sizeof(h->graphs)); h->s_cap = nullptr; h->run_dev = nullptr; h->capturing = 0; h->e.run_ptr = nullptr;
     h->cta_hist = nullptr; h->pool = nullptr; h->pin_rec = nullptr; memset(h->pack_used, 0, sizeof(h->pack_used));
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->epoch = 0; set_first_gid(h, 0);
@@ -223,6 +244,8 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     cudaMemset(h->e.tricklog, 0, 12 * na * 4);
     TK_ALLOC(h->e.dpts, na);
     cudaMemset(h->e.dpts, 0, na);
+    TK_ALLOC(h->run_dev, sizeof(tk::RunParams));
+    h->e.run_ptr = h->run_dev;
     TK_ALLOC(h->e.rcache, 3 * (na / 2) * sizeof(uint2));
     cudaMemset(h->e.rcache, 0, 3 * (na / 2) * sizeof(uint2));
     if (flags & TAROK_FLAG_HISTORY) {
@@ -260,6 +283,9 @@ int tarok_destroy(tarok_t* h) {
     cudaFree(h->e.meta); cudaFree(h->e.mask); cudaFree(h->e.scores); cudaFree(h->e.stats); cudaFree(h->e.tricklog);
     cudaFree(h->e.hist); cudaFree(h->e.hands0); cudaFree(h->e.discard); cudaFree(h->e.qmax_hist); cudaFree(h->e.dpts); cudaFree(h->e.rcache);
     free_staging(h);
+    drop_graphs(h);
+    if (h->s_cap) cudaStreamDestroy(h->s_cap);
+    cudaFree(h->run_dev);
     cudaFree(h->cta_hist);
     tarok_pack_pool_destroy(h->pool);
     if (h->pin_rec) cudaFreeHost(h->pin_rec);
@@ -487,21 +513,76 @@ int tarok_setup_synth(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, 
     h->lock_plays = 0;
     set_first_gid(h, first_global_game_id);
     clear_hist(h, stream);
-    tk::k_setup_synth<<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode);
+    tk::k_setup_synth<false><<<grid1(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, mode);
     TK_LAUNCH_OK(h);
+    return 0;
+}
+
+// setup -> 48 x play_step -> score, enqueued on `s` with the environment `env` (h->e, or its copy that reads the run
+// parameters from device memory while a graph is being captured).
+static int enqueue_rollout_stepwise(tarok_t* h, uint32_t mode, cudaStream_t s) {
+    h->lock_plays = 0;
+    clear_hist(h, s);
+    if (h->capturing) tk::k_setup_synth<true><<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, mode);
+    else tk::k_setup_synth<false><<<grid1(h->e.n_alloc), tk::CTA, 0, s>>>(h->e, mode);
+    TK_LAUNCH_OK(h);
+    if (int rc = random_chain(h, 48, s)) return rc;
+    const unsigned grid = grid2(h->e.n_alloc);
+    if (h->capturing) {
+        if (h->materialise) tk::k_score<true, true><<<grid, tk::CTA, 0, s>>>(h->e, h->e.scores, h->e.n_alloc);
+        else tk::k_score<false, true><<<grid, tk::CTA, 0, s>>>(h->e, h->e.scores, h->e.n_alloc);
+    } else {
+        if (h->materialise) tk::k_score<true><<<grid, tk::CTA, 0, s>>>(h->e, h->e.scores, h->e.n_alloc);
+        else tk::k_score<false><<<grid, tk::CTA, 0, s>>>(h->e, h->e.scores, h->e.n_alloc);
+    }
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+// Captures the rollout of `mode` once (on a private stream: the caller's may be the legacy default stream, which cannot be
+// captured) with the GRAPH kernel variants, which read first_gid / the draw-cache epoch from h->run_dev.
+static int capture_rollout_graph(tarok_t* h, uint32_t mode) {
+    if (!h->s_cap) TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    const uint64_t launches0 = h->launches;
+    TK_CUDA(h, cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal));
+    h->capturing = 1;
+    const int rc = enqueue_rollout_stepwise(h, mode, h->s_cap);
+    h->capturing = 0;
+    const cudaError_t ce = cudaStreamEndCapture(h->s_cap, &g);
+    h->launches = launches0;                               // nothing ran yet
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) return fail(h, -2, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&h->graphs[mode], g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { h->graphs[mode] = nullptr; return fail(h, -2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
     return 0;
 }
 
 int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream) {
     TK_CHECK_HANDLE(h);
-    int rc = tarok_setup_synth(h, mode, first_global_game_id, stream);
-    if (rc) return rc;
+    if (!(mode <= TAROK_ODPRTI_BERAC || (mode >= TAROK_MODE_NAVADNA_MIX && mode <= TAROK_MODE_AUCTION_BOT)))
+        return fail(h, -1, "bad mode %u", mode);
     DeviceGuard dg(h->device);
-    if (int rc = random_chain(h, 48, S(stream))) return rc;
-    if (h->materialise) tk::k_score<true><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
-    else tk::k_score<false><<<grid2(h->e.n_alloc), tk::CTA, 0, S(stream)>>>(h->e, h->e.scores, h->e.n_alloc);
-    TK_LAUNCH_OK(h);
-    return 0;
+    cudaStream_t s = S(stream);
+    set_first_gid(h, first_global_game_id);
+    // 50 launches cost more host time than a small batch takes on the GPU: the whole rollout is replayed as ONE graph
+    // launch (+ a one-thread kernel that hands over this call's first_gid and draw-cache epoch).  Not while the caller is
+    // capturing `stream` itself (the launches below are then captured as they are), nor with the TMA-staged variant.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (h->use_graph && h->step_impl != 2 && mode < TK_GRAPH_MODES
+        && cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+        if (!h->graphs[mode])
+            if (int rc = capture_rollout_graph(h, mode)) return rc;
+        tk::k_set_run<<<1, 1, 0, s>>>(h->run_dev, h->e.first_gid, h->e.rc_epoch);
+        TK_LAUNCH_OK(h);
+        TK_CUDA(h, cudaGraphLaunch(h->graphs[mode], s));
+        h->launches += 50;                                 // the graph's kernels: setup + 48 play_steps + score (+ k_set_run above)
+        h->lock_plays = -1;
+        return 0;
+    }
+    cudaGetLastError();                                    // a failed capture query must not stick
+    return enqueue_rollout_stepwise(h, mode, s);
 }
 
 int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id, void* stream) {

@@ -49,7 +49,21 @@ struct Env {
     u32 rc_rows;                           // trick positions 1..rc_rows use the cache (0 = off, 2, 3): TAROK_OPT_DRAW_CACHE
     u64 n, n_alloc, first_gid;
     Rng rng;                               // seed + precomputed Philox round keys
+    const struct RunParams* run_ptr;       // device record the GRAPH kernel variants take first_gid / rc_epoch from
 };
+
+// What changes from one rollout to the next.  Kernel parameters are frozen into a captured CUDA graph, so the kernels of a
+// graph-backed rollout (tarok_rollout_stepwise, TAROK_OPT_GRAPH; template parameter GRAPH) read these two from a 16-byte
+// device record that a one-thread kernel (k_set_run) rewrites in stream order before every replay.
+struct RunParams { u64 first_gid; u32 rc_epoch; u32 pad; };
+// GRAPH kernels overwrite their own copy of the two fields first thing (kernel parameters are ordinary local variables), so
+// every helper below keeps reading e.first_gid / e.rc_epoch and the plain kernels carry no trace of the indirection.
+__device__ __forceinline__ void load_run_params(Env& e) {
+    const uint4 rp = __ldg(reinterpret_cast<const uint4*>(e.run_ptr));
+    e.first_gid = (u64)rp.x | ((u64)rp.y << 32);
+    e.rc_epoch = rp.z;
+}
+__global__ void k_set_run(RunParams* r, u64 first_gid, u32 rc_epoch) { r->first_gid = first_gid; r->rc_epoch = rc_epoch; r->pad = 0u; }
 
 enum : int { S_SEAT = 0, S_PLAYER = 4, S_CONTRACT = 8, S_FINISHED = 18, S_STEPS = 19, S_ERRORS = 20, S_USED = 21, S_ERR_EVENTS = 21 };
 
@@ -494,8 +508,9 @@ __global__ void __launch_bounds__(CTA) k_begin(Env e, u32 mode, const uint8_t* _
     u64 h0 = e.hands[g], h1 = e.hands[na + g], h2 = e.hands[2 * na + g], h3 = e.hands[3 * na + g];
     u32 contract, declarer, king;
     Words4 sb = {{0, 0, 0, 0}};
-    if (SRC == SRC_SYNTH) sb = setup_block(e.rng, e.first_gid + g);
-    resolve_contract<SRC>(e.rng, e.first_gid + g, mode, a, b, c, g, sb, contract, declarer, king);
+    const u64 gid = e.first_gid + g;
+    if (SRC == SRC_SYNTH) sb = setup_block(e.rng, gid);
+    resolve_contract<SRC>(e.rng, gid, mode, a, b, c, g, sb, contract, declarer, king);
     slots_to_seats(h0, h1, h2, h3, leader_of(meta));             // identity in practice: a dealt game has leader 0
     meta = begin_contract(meta, contract, declarer, king, h0, h1, h2, h3);
     if ((meta >> M_ERR) & 1ull) atomicAdd((unsigned long long*)&e.stats[S_ERR_EVENTS], 1ull);
@@ -578,8 +593,9 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
     u64 pile = e.piles[decl * na + g];
     u64 talon = e.talon[g], order = e.torder[g], dout = 0;
     Words4 sb = {{0, 0, 0, 0}};
-    if (SYNTH) sb = setup_block(e.rng, e.first_gid + g);
-    bool ok = exchange_game<SYNTH>(e.rng, e.first_gid + g, random_group, sb, meta, hand, pile, talon, order,
+    const u64 gid = e.first_gid + g;
+    if (SYNTH) sb = setup_block(e.rng, gid);
+    bool ok = exchange_game<SYNTH>(e.rng, gid, random_group, sb, meta, hand, pile, talon, order,
                                    SYNTH ? 0u : (u32)group[g], SYNTH ? 0ull : discard[g], dout);
     if (!ok) {
         meta = mset(meta, M_PHASE, 2, PH_DONE) | (1ull << M_ERR);
@@ -611,7 +627,9 @@ __global__ void __launch_bounds__(CTA) k_exchange(Env e, u32 random_group, const
 // Philox draws as k_deal + k_begin<SYNTH> + k_exchange<SYNTH>, so the resulting state is bit-identical; the
 // state is written once instead of written, re-read and patched twice.
 // ------------------------------------------------------------------------------------------------
+template <bool GRAPH = false>
 __global__ void __launch_bounds__(CTA, TK_SETUP_BLOCKS) k_setup_synth(Env e, u32 mode) {
+    if constexpr (GRAPH) load_run_params(e);
     const u64 g = (u64)blockIdx.x * CTA + threadIdx.x;
     const u64 na = e.n_alloc;
     if (g >= na) return;
@@ -794,7 +812,8 @@ template <int POS>
 __device__ TK_COLD u32 pair_lanes_cold(const Env& e, u32 g, u32 trick, bool a1) {
     Words4 r0, r1;
     pair_blocks(e, g, trick, trick, a1, r0, r1);
-    return play_lane<POS>(r0, e.first_gid + g, (u32)POS) | (play_lane<POS>(r1, e.first_gid + g + 1, (u32)POS) << 16);
+    const u64 gid = e.first_gid + g;
+    return play_lane<POS>(r0, gid, (u32)POS) | (play_lane<POS>(r1, gid + 1, (u32)POS) << 16);
 }
 
 // ---- lock-step path: every live game of the warp has made `hint` plays, so the trick position POS = hint & 3 is a
@@ -802,7 +821,7 @@ __device__ TK_COLD u32 pair_lanes_cold(const Env& e, u32 g, u32 trick, bool a1) 
 // hm = slot POS (the mover's hand); POS < 3: n0 = slot POS + 1 (the next seat); POS == 3: n0, n1, n2 = slots 0, 1, 2.
 template <bool RANDOM, int POS, bool MASK>
 __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u64& hm, u64& n0, u64& n1, u64& n2, u32 card,
-                                               u32 x16, u64& next_mask, u32& log_out, const uint8_t* __restrict__ sel8) {
+                                               u32 x16, u64& next_mask, u32& log_out, const uint8_t* __restrict__ sel8, u64 fgid) {
     const u32 na = (u32)e.n_alloc;
     const u32 lo = (u32)meta, hi = (u32)(meta >> 32);
     const u32 leader = (lo >> M_LEADER) & 3u, kf = (lo >> M_KLOPFAM) & 1u;
@@ -810,7 +829,7 @@ __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u
     const u32 plays = (hi >> (M_PLAYS - 32)) & 63u;
     if (RANDOM) {
         const u64 legal = legal_moves(hm, POS != 0, hi & 63u, kf);
-        card = nth_set_bit_lut(legal, play_pick(x16, e.rng, e.first_gid + g, plays, (u32)__popcll(legal)), sel8);
+        card = nth_set_bit_lut(legal, play_pick(x16, e.rng, fgid + g, plays, (u32)__popcll(legal)), sel8);
     }
     PlayResult pr;
     meta = play_card<!RANDOM, POS, false>(meta, hm, card, 0ull, 0ull, pr);
@@ -837,6 +856,9 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     __shared__ __align__(16) uint8_t sel8[RANDOM ? SELECT8_SMEM : 16];
     uint2 sel8_mine = {0u, 0u};                    // this thread's 8 bytes of the byte-select table (tarok_rules.cuh): independent of
     if (RANDOM) sel8_mine = select8_fetch();       // the previous launch, so the load is issued before the dependency wait
+    // the run parameters (constant memory slot inside a replayed graph, else launch parameters)
+    const u64 fgid = RANDOM ? e.first_gid : 0ull;
+    const u32 tag = (RANDOM ? e.rc_epoch : 0u) | ((u32)hint >> 2);
 #if !TK_SEL8_LATE
     if (RANDOM) { select8_store(sel8, sel8_mine); __syncthreads(); }
 #endif
@@ -854,11 +876,11 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     // running the ten rounds again.  The tag (epoch of first_gid | trick) makes a stale or never-written entry harmless:
     // the block is then computed here as before.  Lanes straddle two pairs when first_gid is odd: no cache then.
     constexpr u32 UPOS = POS > 0 ? (u32)POS : 0u;
-    bool cached = RANDOM && e.rc_rows != 0u && !((u32)e.first_gid & 1u);
-    if constexpr (POS > 0) cached = cached && UPOS <= e.rc_rows;
-    const u32 tag = e.rc_epoch | ((u32)hint >> 2);
+    bool in_rows = RANDOM && e.rc_rows != 0u;      // a launch parameter: the entry is fetched whatever first_gid turns out to be
+    if constexpr (POS > 0) in_rows = in_rows && UPOS <= e.rc_rows;
+    const bool cached = in_rows && !((u32)fgid & 1u);
     uint2 rc = {0u, 0u};
-    if (cached && POS > 0) rc = e.rcache[(UPOS > 0u ? UPOS - 1u : 0u) * (na >> 1) + (g >> 1)];
+    if (in_rows && POS > 0) rc = e.rcache[(UPOS > 0u ? UPOS - 1u : 0u) * (na >> 1) + (g >> 1)];
 #if TK_SEL8_LATE
     if (RANDOM) {                                  // behind the state loads in program order: all of them are in flight together
         select8_store(sel8, sel8_mine);
@@ -884,8 +906,8 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
             // the trick index is the (uniform) hint -- a finished neighbour's own counter is stale and must not be used
             Words4 r0, r1;
             pair_blocks(e, g, (u32)hint >> 2, (u32)hint >> 2, a1, r0, r1);
-            x0 = play_lane<POS>(r0, e.first_gid + g, (u32)hint);
-            x1 = play_lane<POS>(r1, e.first_gid + g + 1, (u32)hint);
+            x0 = play_lane<POS>(r0, fgid + g, (u32)hint);
+            x1 = play_lane<POS>(r1, fgid + g + 1, (u32)hint);
             if (POS == 0 && cached) {
                 uint2* rcp = e.rcache + (g >> 1);
                 rcp[0] = make_uint2(tag, play_lanes_of_pair(r0, 1));
@@ -896,8 +918,8 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     }
     u64 k0 = 0, k1 = 0;
     u32 l0 = 0, l1 = 0;                            // trick-log entries (POS == 3); 0 = nothing to append
-    if (a0) step_game_lock<RANDOM, POS, MASK>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, x0, k0, l0, sel8);
-    if (a1) step_game_lock<RANDOM, POS, MASK>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, x1, k1, l1, sel8);
+    if (a0) step_game_lock<RANDOM, POS, MASK>(e, g, m.x, hm.x, n0.x, n1.x, n2.x, act & 0xFFu, x0, k0, l0, sel8, fgid);
+    if (a1) step_game_lock<RANDOM, POS, MASK>(e, g + 1, m.y, hm.y, n0.y, n1.y, n2.y, act >> 8, x1, k1, l1, sel8, fgid);
     st2(e.hands + (POS * na + g), hm.x, hm.y);     // a game that did not move gets its slot back unchanged
     if (POS == 3) {
         st2(e.hands + g, n0.x, n0.y); st2(e.hands + (na + g), n1.x, n1.y); st2(e.hands + (2 * na + g), n2.x, n2.y);
@@ -919,11 +941,11 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
 // in-kernel random steps (tarok_steps_random, the stepwise rollouts) launches its interior steps with MASK = false: no
 // caller can see those masks, so the next seat's slot is neither read nor its legal set computed or stored -- 16 of the
 // 48 bytes a step moves at trick positions 0-2 -- and only the chain's last launch produces the masks.
-template <bool RANDOM, int POS, bool MASK = true>
+template <bool RANDOM, int POS, bool MASK = true, bool GRAPH = false>
 __global__ void __launch_bounds__(CTA, RANDOM ? ((POS >= 0 && POS < 3) ? TK_STEP_BLOCKS_RANDOM_012 : TK_STEP_BLOCKS_RANDOM) : TK_STEP_BLOCKS_FORCED)
-k_step(const __grid_constant__ Env e, const uint8_t* __restrict__ action, int hint) {   // __grid_constant__: the out-of-line cold
-                                                                                         // paths take `e` by reference without a stack copy
+k_step(Env e, const uint8_t* __restrict__ action, int hint) {
     pdl_launch_dependents();
+    if constexpr (GRAPH) load_run_params(e);       // written before the graph started: no need to wait for the previous kernel
     if constexpr (POS >= 0) {
         step_lock<RANDOM, POS, MASK>(e, action, hint);
     } else {
@@ -1120,8 +1142,9 @@ __device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int 
 // MAT = also write the materialised piles / talon back (the exported fields then hold the full piles); without it only the
 // scores and statistics are produced (pipelines that, like Tarok.paralel_start, only need the results): what is read is
 // meta 8 + trick log 48 + talon 8 + discard points 1 (+ the talon order for Klop), 8 B of scores written.
-template <bool MAT>
+template <bool MAT, bool GRAPH = false>
 __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64 out_n) {
+    if constexpr (GRAPH) load_run_params(e);
     u64 g = ((u64)blockIdx.x * CTA + threadIdx.x) * 2;
     const u64 na = e.n_alloc;
     u64 s0 = 0, s1 = 0;
@@ -1159,7 +1182,8 @@ __global__ void __launch_bounds__(CTA) k_score(Env e, u64* __restrict__ out, u64
         else if (g < out_n) out[g] = s0;
     }
     // two games per lane: folded per lane before the warp reductions
-    GameStat gs[2] = {{f0, e0, s0, c0, pl0, e.first_gid + g}, {f1, e1, s1, c1, pl1, e.first_gid + g + 1}};
+    const u64 fgid = e.first_gid;
+    GameStat gs[2] = {{f0, e0, s0, c0, pl0, fgid + g}, {f1, e1, s1, c1, pl1, fgid + g + 1}};
     accumulate_stats<2>(e.stats, gs);
 }
 

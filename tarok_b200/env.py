@@ -176,6 +176,10 @@ class TarokEnv:
         leaves behind instead of recomputed: 0 off, 2, 3; -1 = the default for this batch size.  Results are identical."""
         self._check(self._lib.tarok_set_option(self._h, 7, int(rows)))
 
+    def set_graph(self, on: bool):
+        """``rollout(fused=False)`` replays a CUDA graph of its 50 launches (default on; same results, ~4 us of host time)."""
+        self._check(self._lib.tarok_set_option(self._h, 8, 1 if on else 0))
+
     def set_lockstep(self, on: bool):
         """Trick-position-specialised play_step for lock-step batches (default on; the kernel verifies the hint)."""
         self._check(self._lib.tarok_set_option(self._h, 3, 1 if on else 0))

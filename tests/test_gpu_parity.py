@@ -506,7 +506,11 @@ def test_no_cpu_fallback_symbols_loaded():
     env = _env(1000)
     before = env.launches
     env.rollout(0)
-    assert env.launches - before == 50          # setup + 48 x play_step + score
+    assert env.launches - before == 51          # one graph replay: the hand-over kernel + setup + 48 x play_step + score
+    env.set_graph(False)
+    before = env.launches
+    env.rollout(0)
+    assert env.launches - before == 50          # plain launches: setup + 48 x play_step + score
     with open("/proc/self/maps") as f:
         assert "libtarok_b200.so" in f.read()
     env.close()
@@ -640,6 +644,56 @@ def test_hand_slots_follow_the_trick_leader(lock):
         del meta, slots, mask
         env.step_random(1)
     env.close()
+
+
+def test_graph_backed_rollout_equals_plain_launches():
+    """tarok_rollout_stepwise replays a captured CUDA graph whose kernels read first_gid and the draw-cache epoch from device
+    memory (TAROK_OPT_GRAPH, default on).  Replays under different game ids (odd and even: the draw cache is bypassed for
+    odd ids), modes and after option changes must equal the plain 50-launch path bit for bit, on any stream."""
+    import torch
+    n, seed = 30011, 77
+    a, b = _env(n, seed=seed, history=True), _env(n, seed=seed, history=True)
+    b.set_graph(False)
+    side = torch.cuda.Stream()
+    for it, (mode, gid0) in enumerate([(16, 0), (16, 4 * n), (17, 4 * n + 1), (16, 2 ** 40 + 6), (0, 7), (16, 0), (18, 12)]):
+        a.reset_stats(); b.reset_stats()
+        if it == 3:
+            a.set_lazy_mask(False); b.set_lazy_mask(False)       # an option change drops the captured graphs
+        if it == 4:
+            a.set_lazy_mask(True); b.set_lazy_mask(True)
+        if it % 2:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                a.rollout(mode, first_game_id=gid0, fused=False)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            a.rollout(mode, first_game_id=gid0, fused=False)
+        b.rollout(mode, first_game_id=gid0, fused=False)
+        for f in ("hand_slots", "meta", "mask", "talon", "talon_order", "scores"):
+            assert (u64(getattr(a, f)) == u64(getattr(b, f))).all(), (it, f)
+        assert (a.hist[:, :n] == b.hist[:, :n]).all(), it
+        assert (a.stats()[:21] == b.stats()[:21]).all(), it
+        assert a.launches - b.launches == it + 1, it             # the 50 kernels of the graph are counted, + the one-thread hand-over kernel
+    # two graph-backed handles in flight at once on different streams: each reads its own slot of run parameters
+    c = _env(n, seed=seed, history=True)
+    a.reset_stats(); b.reset_stats(); c.reset_stats()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        c.rollout(16, first_game_id=10 * n, fused=False)
+    a.rollout(16, first_game_id=20 * n, fused=False)
+    torch.cuda.current_stream().wait_stream(side)
+    b.rollout(16, first_game_id=10 * n, fused=False)
+    assert (c.hist[:, :n] == b.hist[:, :n]).all() and (u64(c.scores) == u64(b.scores)).all()
+    b.rollout(16, first_game_id=20 * n, fused=False)
+    assert (a.hist[:, :n] == b.hist[:, :n]).all() and (u64(a.scores) == u64(b.scores)).all()
+    c.close()
+    # stepping by hand after a graph-backed rollout starts from a known state
+    a.deal(5); b.deal(5)
+    a.force_contract_synth(16); b.force_contract_synth(16)
+    a.exchange_synth(False); b.exchange_synth(False)
+    a.step_random(48); b.step_random(48)
+    assert (a.score().cpu().numpy() == b.score().cpu().numpy()).all()
+    a.close(); b.close()
 
 
 def test_pipeline_is_cuda_graph_capturable():
