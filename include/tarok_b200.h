@@ -93,8 +93,10 @@ const char* tarok_last_error(const tarok_t* h);/* h may be NULL: last error of a
 #define TAROK_OPT_LAZY_MASK 6   /* 1 (default): a chain of in-kernel random steps (tarok_steps_random, the stepwise rollouts) writes
                                    TAROK_F_MASK in its LAST launch only -- the interior masks cannot be observed; 0: every launch */
 #define TAROK_OPT_GRAPH 8       /* 1 (default): tarok_rollout_stepwise replays a CUDA graph of its 50 launches (captured on first use per
-                                   mode; first_gid is handed over through device memory): ~4 us of host time per rollout instead of
-                                   ~150, and no launch gaps on the GPU; 0: plain launches.  Same results either way. */
+                                   mode; first_gid is handed over through device memory): ~13 us of host time per rollout instead
+                                   of ~150 and no launch gaps on the GPU -- for batches up to 3 M deals (beyond that the kernels are
+                                   long and HBM-bound and the plain launches are as fast); 2: at every size; 0: plain launches.
+                                   Same results either way. */
 #define TAROK_OPT_LOCKSTEP 3   /* 1 (default): play_step variants specialised per trick position for lock-step batches */
 int tarok_set_option(tarok_t* h, int option, int64_t value);
 uint64_t tarok_n_games(const tarok_t* h);

@@ -104,9 +104,9 @@ static inline void set_first_gid(tarok_env* h, u64 first_gid) {
 }
 
 // Draw cache policy: all three positions while the state a chain of steps touches stays inside the 126 MB L2 (the cache
-// adds 12 B per game to it); beyond that the trick-closing launch is HBM-bound and computes its own block, positions 1-2
-// (ALU-bound) keep reading theirs.
-static inline u32 default_draw_cache_rows(u64 n_alloc) { return n_alloc <= (3ull << 20) ? 3u : 2u; }
+// adds 12 B per game to it); beyond that the step kernels are HBM-bound, the extra 4-8 B per game and step cost more than
+// the ten Philox rounds they save (8 M deals, uniform bids: 72.5 us per launch without, 74.9 us with rows 1-2), so it is off.
+static inline u32 default_draw_cache_rows(u64 n_alloc) { return n_alloc <= (3ull << 20) ? 3u : 0u; }
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline unsigned grid1(u64 n_alloc) { return (unsigned)(n_alloc / tk::CTA); }        // one game per lane
@@ -182,7 +182,7 @@ static void drop_graphs(tarok_env* h) {
 int tarok_set_option(tarok_t* h, int option, int64_t value) {
     TK_CHECK_HANDLE(h);
     drop_graphs(h);
-    if (option == TAROK_OPT_GRAPH && (value == 0 || value == 1)) { h->use_graph = (int)value; return 0; }
+    if (option == TAROK_OPT_GRAPH && value >= 0 && value <= 2) { h->use_graph = (int)value; return 0; }
     if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 2) { h->step_impl = (int)value; return 0; }
     if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
     if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
@@ -570,7 +570,7 @@ int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game
     // launch (+ a one-thread kernel that hands over this call's first_gid and draw-cache epoch).  Not while the caller is
     // capturing `stream` itself (the launches below are then captured as they are), nor with the TMA-staged variant.
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (h->use_graph && h->step_impl != 2 && mode < TK_GRAPH_MODES
+    if (h->use_graph && (h->use_graph == 2 || h->e.n_alloc <= (3ull << 20)) && h->step_impl != 2 && mode < TK_GRAPH_MODES
         && cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
         if (!h->graphs[mode])
             if (int rc = capture_rollout_graph(h, mode)) return rc;

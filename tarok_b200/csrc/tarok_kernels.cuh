@@ -793,7 +793,7 @@ __device__ __forceinline__ void step_pair_general(const Env& e, u32 g, ulonglong
 // Cold paths of the lock-step kernels, kept out of line so that their registers and code do not weigh on the hot path:
 // the warp whose vote failed, and the draw-cache miss at trick positions 1-3.
 #ifndef TK_SEL8_LATE
-#define TK_SEL8_LATE 0
+#define TK_SEL8_LATE 1    // table stored + barrier behind the state loads (A/B, profiles/r02/step_ab_run7.txt: 8.03 vs 8.14 us at 1 M, 71.9 vs 72.5 at 8 M)
 #endif
 #ifndef TK_COLD_NOINLINE
 #define TK_COLD_NOINLINE 0   // out of line measured slower (profiles/r02/step_ab_run6.txt): 8.78 vs 7.98 us per launch at 1 M deals
