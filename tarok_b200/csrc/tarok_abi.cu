@@ -631,14 +631,13 @@ static int rollout_host_fused(tarok_t* h, const uint8_t* deals_host, size_t row,
                               const uint8_t* declarer_host, const uint8_t* king_host, int16_t* scores_host,
                               int64_t* stats_host, cudaStream_t s) {
     const u64 n = h->e.n;
-    const u64 want = (u64)h->chunks;
-    const u64 chunk = (n >= (1ull << 18)) ? (((n + want - 1) / want + tk::CTA - 1) / tk::CTA * tk::CTA) : h->e.n_alloc;
-    const int nchunks = (int)((n + chunk - 1) / chunk);
+    uint64_t bounds[TK_MAX_CHUNKS + 1];
+    const int nchunks = tarok_chunk_bounds(n, h->chunks, tarok_pack_block_rows(), bounds);   // tapered: short fill and drain
     TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
     TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));
     TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_fork, 0));
-    for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
-        const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
+    for (int c = 0; c < nchunks; c++) {
+        const u64 b = bounds[c], e_ = bounds[c + 1], len = e_ - b;
         TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * row, deals_host + b * row, len * row, cudaMemcpyHostToDevice, h->s_up));
         if (c == 0 && contract_host) {   // the three 1-byte-per-game inputs go up whole, right behind the first chunk of deals
             TK_CUDA(h, cudaMemcpyAsync(h->st_contract, contract_host, n, cudaMemcpyHostToDevice, h->s_up));
@@ -713,12 +712,12 @@ int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t fir
 }
 
 // Upload / play / download of the chunks of tarok_rollout_host_packed, each as soon as the pool has packed it.
-static int packed_pipeline(tarok_t* h, u64 n, u64 chunk, int nchunks, int16_t* scores_host, int64_t* stats_host, cudaStream_t s) {
+static int packed_pipeline(tarok_t* h, const uint64_t* bounds, int nchunks, int16_t* scores_host, int64_t* stats_host, cudaStream_t s) {
     TK_CUDA(h, cudaEventRecord(h->ev_fork, s));
     TK_CUDA(h, cudaStreamWaitEvent(h->s_up, h->ev_fork, 0));
     TK_CUDA(h, cudaStreamWaitEvent(h->s_down, h->ev_fork, 0));
-    for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) {
-        const u64 b = (u64)c * chunk, e_ = (b + chunk < n) ? b + chunk : n, len = e_ - b;
+    for (int c = 0; c < nchunks; c++) {
+        const u64 b = bounds[c], e_ = bounds[c + 1], len = e_ - b;
         tarok_pack_pool_wait_chunk(h->pool, c);
         TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * TAROK_RECORD_BYTES, (const uint8_t*)h->pin_rec + b * TAROK_RECORD_BYTES,
                                    len * TAROK_RECORD_BYTES, cudaMemcpyHostToDevice, h->s_up));
@@ -761,18 +760,17 @@ int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_
     TK_CUDA(h, cudaMemsetAsync(h->e.stats, 0, TAROK_STATS_LEN * 8, s));
     h->lock_plays = 0;
     set_first_gid(h, first_global_game_id);
-    const u64 n = h->e.n, want = (u64)h->chunks;
+    const u64 n = h->e.n;
     // the previous call's uploads must have left the pinned scratch before it is overwritten
     for (int c = 0; c < TK_MAX_CHUNKS; c++)
         if (h->pack_used[c]) { TK_CUDA(h, cudaEventSynchronize(h->ev_up[c])); h->pack_used[c] = 0; }
     // the pool packs the whole batch block by block in the background; chunk c is uploaded as soon as its blocks are done
-    tarok_pack_pool_begin(h->pool, perm_host, contract_host, declarer_host, king_host, n,
-                          (n >= (1ull << 18)) ? (n + want - 1) / want : h->e.n_alloc, h->pin_rec);
-    const u64 chunk = tarok_pack_pool_chunk_rows(h->pool);                   // whole pack blocks (a multiple of the CTA tile)
-    const int nchunks = (int)((n + chunk - 1) / chunk);
-    const int rc = packed_pipeline(h, n, chunk, nchunks, scores_host, stats_host, s);
+    uint64_t bounds[TK_MAX_CHUNKS + 1];
+    const int nchunks = tarok_chunk_bounds(n, h->chunks, tarok_pack_block_rows(), bounds);
+    tarok_pack_pool_begin(h->pool, perm_host, contract_host, declarer_host, king_host, n, bounds, nchunks, h->pin_rec);
+    const int rc = packed_pipeline(h, bounds, nchunks, scores_host, stats_host, s);
     if (rc)                                                 // the workers still read the caller's rows: let them finish
-        for (int c = 0; c < nchunks && c < TK_MAX_CHUNKS; c++) tarok_pack_pool_wait_chunk(h->pool, c);
+        for (int c = 0; c < nchunks; c++) tarok_pack_pool_wait_chunk(h->pool, c);
     return rc;
 }
 

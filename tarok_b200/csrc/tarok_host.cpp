@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -183,7 +184,9 @@ struct tarok_pack_pool {
     // the current job
     const uint8_t *perm = nullptr, *contract = nullptr, *declarer = nullptr, *king = nullptr;
     uint64_t* records = nullptr;
-    uint64_t n = 0, chunk = 0, nblocks = 0;
+    uint64_t n = 0, nblocks = 0;
+    int nchunks = 0;
+    uint64_t bounds[PACK_MAX_CHUNKS + 1] = {};              // upload chunk c = rows [bounds[c], bounds[c + 1]); whole blocks except the last
     std::atomic<uint64_t> next{0};
     std::atomic<uint64_t> done[PACK_MAX_CHUNKS];            // blocks finished per upload chunk
     std::atomic<int64_t> bad{0};
@@ -195,7 +198,9 @@ struct tarok_pack_pool {
         const uint64_t lo = i * PACK_BLOCK, hi = lo + PACK_BLOCK < n ? lo + PACK_BLOCK : n;
         const int64_t nb = pack_range(perm, contract, declarer, king, lo, hi, records);
         if (nb) bad.fetch_add(nb, std::memory_order_relaxed);
-        done[lo / chunk].fetch_add(1, std::memory_order_release);
+        int c = 0;
+        while (c + 1 < nchunks && lo >= bounds[c + 1]) c++;
+        done[c].fetch_add(1, std::memory_order_release);
         return true;
     }
     void loop() {
@@ -243,15 +248,42 @@ void tarok_pack_pool_destroy(tarok_pack_pool* p) {
 
 int tarok_pack_pool_threads(const tarok_pack_pool* p) { return p ? p->parts : 0; }
 
-// Starts packing rows [0, n) into `records`; `chunk` (rows, rounded up to whole blocks) is the upload granularity
-// that tarok_pack_pool_wait_chunk reports on.  Returns at once; the workers run in the background.
+// The upload chunks of the host pipelines: `want` chunks over n rows, TAPERED -- the first and the last chunk get one unit,
+// their neighbours two, the rest four -- because the pipeline's fill is the first chunk's upload and its drain the last
+// chunk's play + download: small ends, large middle.  Boundaries are multiples of `quantum` rows (the pack block, itself a
+// multiple of the CTA tile); bounds[0] = 0, bounds[returned count] = n.  A small batch is one chunk.
+int tarok_chunk_bounds(uint64_t n, int want, uint64_t quantum, uint64_t* bounds) {
+    if (want > PACK_MAX_CHUNKS) want = PACK_MAX_CHUNKS;
+    bounds[0] = 0;
+    if (want < 2 || n < (1ull << 18)) { bounds[1] = n; return 1; }
+    uint64_t units[PACK_MAX_CHUNKS], total = 0;
+    for (int c = 0; c < want; c++) {
+        const int edge = c < want - 1 - c ? c : want - 1 - c;           // distance from the nearer end
+        units[c] = want < 4 ? 1 : edge == 0 ? 1 : edge == 1 ? 2 : 4;    // steeper tapers (up to 16) measure the same
+        total += units[c];
+    }
+    int count = 0;
+    uint64_t acc = 0;
+    for (int c = 0; c < want; c++) {
+        acc += units[c];
+        uint64_t b = (n * acc / total + quantum - 1) / quantum * quantum;
+        if (b > n || c == want - 1) b = n;
+        if (b > bounds[count]) bounds[++count] = b;
+        if (b == n) break;
+    }
+    return count;
+}
+
+// Starts packing rows [0, n) into `records`; bounds[0..nchunks] (tarok_chunk_bounds with quantum = tarok_pack_block_rows())
+// are the upload chunks that tarok_pack_pool_wait_chunk reports on.  Returns at once; the workers run in the background.
 void tarok_pack_pool_begin(tarok_pack_pool* p, const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer,
-                           const uint8_t* king, uint64_t n, uint64_t chunk, uint64_t* records) {
+                           const uint8_t* king, uint64_t n, const uint64_t* bounds, int nchunks, uint64_t* records) {
     p->next.store(PACK_CLOSED, std::memory_order_release);                  // nobody can take a block while the job changes
     while (p->active.load(std::memory_order_acquire) != 0) _mm_pause();      // stragglers of the previous job
     p->perm = perm; p->contract = contract; p->declarer = declarer; p->king = king; p->records = records;
     p->n = n;
-    p->chunk = (chunk + PACK_BLOCK - 1) / PACK_BLOCK * PACK_BLOCK;           // chunk boundaries on block boundaries
+    p->nchunks = nchunks;
+    for (int c = 0; c <= nchunks; c++) p->bounds[c] = bounds[c];
     p->nblocks = (n + PACK_BLOCK - 1) / PACK_BLOCK;
     for (auto& d : p->done) d.store(0, std::memory_order_relaxed);
     p->bad.store(0, std::memory_order_relaxed);
@@ -263,11 +295,11 @@ void tarok_pack_pool_begin(tarok_pack_pool* p, const uint8_t* perm, const uint8_
     p->cv_job.notify_all();
 }
 
-uint64_t tarok_pack_pool_chunk_rows(const tarok_pack_pool* p) { return p->chunk; }
+uint64_t tarok_pack_block_rows(void) { return PACK_BLOCK; }
 
 // Blocks (packing blocks itself meanwhile) until every row of upload chunk c is in `records`.
 void tarok_pack_pool_wait_chunk(tarok_pack_pool* p, int c) {
-    const uint64_t lo = (uint64_t)c * p->chunk, hi = lo + p->chunk < p->n ? lo + p->chunk : p->n;
+    const uint64_t lo = p->bounds[c], hi = p->bounds[c + 1];
     const uint64_t want = lo < hi ? (hi - lo + PACK_BLOCK - 1) / PACK_BLOCK : 0;
     while (p->done[c].load(std::memory_order_acquire) < want)
         if (!p->take_block()) _mm_pause();
