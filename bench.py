@@ -11,7 +11,7 @@ One "step" = one pass of the hot path over one batch: deal -> contract -> talon 
                is bracketed by its own CUDA-event pair, a 160 MiB L2-flush write runs between the pairs
 * e2e          same metric through the host-buffer C-ABI entry: pinned host permutation rows + contracts uploaded, scores +
                stats downloaded, inside the timed region; the fastest COMPLETE pipeline from rows is the headline
-               (raw 57-byte rows, or rows serialised into 24-byte records by host threads inside the call)
+               (raw 57-byte rows, or rows serialised into 20-byte records by host threads inside the call)
 * roofline     the dominant kernel k_step<random>: 64 B/env-step x live games per launch / its CUDA-event
                duration over the timed region, against MEASURED_PEAKS.json; `traffic` = ncu dram bytes per launch
 * step_forced  the same 48 steps driven by a device-resident action buffer (k_step<false>: what an external policy uses)
@@ -259,7 +259,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
     from tarok_b200.dist import NcclComm, shard
-    from tarok_b200.env import TarokEnv, pack_records, MODE_AUCTION_UNIFORM, S_STEPS, S_FINISHED, S_ERRORS
+    from tarok_b200.env import TarokEnv, pack_records, RECORD_BYTES, MODE_AUCTION_UNIFORM, S_STEPS, S_FINISHED, S_ERRORS
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -460,7 +460,7 @@ def run_ours(args, rank, world, local_rank):
     st_h = torch.zeros(32, dtype=torch.int64).pin_memory()
     host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     pack_threads = max(1, min(64, (os.cpu_count() or host_cores) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
-    rec_h, _ = pack_records(perm_h, c_h, d_h, k_h, threads=pack_threads)   # the same deals + contracts as 24-byte records (pinned)
+    rec_h, _ = pack_records(perm_h, c_h, d_h, k_h, threads=pack_threads)   # the same deals + contracts as 20-byte records (pinned)
 
     def e2e_run(kind):
         def once(i):
@@ -493,7 +493,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_sw = e2e_run("stepwise")        # stepwise kernels, serial upload -> 52 launches -> download
     e2e_rec = e2e_run("records")        # records packed BEFORE the timed region (not end to end for a caller holding rows)
     e2e_packed = e2e_run("packed")      # rows in, packed into records by host threads inside the call, chunk by chunk
-    pipes = {"rows": (e2e_rows, world * n * 57), "packed": (e2e_packed, world * n * 24)}
+    pipes = {"rows": (e2e_rows, world * n * 57), "packed": (e2e_packed, world * n * RECORD_BYTES)}
     best = max(pipes, key=lambda k: pipes[k][0][0])
     clocks = sampler.stop() if sampler else None
 
@@ -608,14 +608,14 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": world * (n * 8 + 256), "ms_per_step": bms, "pipeline": best,
                     "api": {"rows": "tarok_rollout_host (TarokEnv.rollout_host): pinned host permutation rows + contracts in, scores + "
                                     "stats out; fused kernel behind an 8-chunk upload/compute/download pipeline",
-                            "packed": "tarok_rollout_host_packed: the same rows in; every chunk serialised into 24-byte deal records by "
+                            "packed": "tarok_rollout_host_packed: the same rows in; every chunk serialised into 20-byte deal records by "
                                       "%d host threads inside the call, right before its upload" % pack_threads}[best],
                     "rows_57B": {"value": e2e_rows[0], "ms_per_step": e2e_rows[1], "h2d_bytes_per_step": world * n * 57},
-                    "rows_packed_in_call_24B": {"value": e2e_packed[0], "ms_per_step": e2e_packed[1], "h2d_bytes_per_step": world * n * 24,
+                    "rows_packed_in_call_20B": {"value": e2e_packed[0], "ms_per_step": e2e_packed[1], "h2d_bytes_per_step": world * n * RECORD_BYTES,
                                                 "pack_threads_per_rank": pack_threads, "host_cores": os.cpu_count(),
                                                 "timing": "max(CUDA events, host wall clock) per step: the pack runs on host threads"},
                     "stepwise_kernels": {"value": e2e_sw[0], "ms_per_step": e2e_sw[1]},
-                    "records_prepacked": {"value": e2e_rec[0], "ms_per_step": e2e_rec[1], "h2d_bytes_per_step": world * n * 24,
+                    "records_prepacked": {"value": e2e_rec[0], "ms_per_step": e2e_rec[1], "h2d_bytes_per_step": world * n * RECORD_BYTES,
                                           "note": "tarok_rollout_records with the records packed BEFORE the timed region: an upper bound "
                                                   "for the packed pipeline, NOT an end-to-end number for a caller that holds rows"}},
             "gpu_launches": launches * world,

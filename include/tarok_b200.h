@@ -178,37 +178,39 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
                        uint64_t first_global_game_id, int fused,
                        int16_t* scores_host, int64_t* stats_host, void* stream);
 
-/* Deal records: the same inputs as tarok_rollout_host in 24 instead of 57 bytes per deal (the host-buffer path is
-   PCIe-bound, so the bytes are the cost).  One record = three little-endian uint64 words w0,w1,w2:
+/* Deal records: the same inputs as tarok_rollout_host in 20 instead of 57 bytes per deal (the host-buffer path is
+   PCIe-bound, so the bytes are the cost).  One record = 20 bytes, little endian: uint64 w0, uint64 w1, uint32 w2 (records are
+   packed back to back, so only every other one is 8-byte aligned):
      bits 0..53 of w0/w1     = bit planes 0/1 of the seat (0-3) whose twelve cards of Igra.razdeli (Igra.py:65-73) hold
                                card id i (bit i = card id i); the six talon cards carry 0 in both planes;
-     w2 bits 0..35           = the six talon ids in talon order (karte[48:54]), 6 bits each, first card lowest;
-     w2 bits 36..39 contract code, 40..41 declarer seat, 42..44 king suit (7 = none): the arguments of tarok_force_contract;
+     a 45-bit word m         = bits 54..63 of w0 (m bits 0..9), bits 54..63 of w1 (m bits 10..19) and w2 (m bits 20..44):
+       m bits 0..35          = the six talon ids in talon order (karte[48:54]), 6 bits each, first card lowest;
+       m bits 36..39 contract code, 40..41 declarer seat, 42..44 king suit (7 = none): the arguments of tarok_force_contract;
      every other bit is 0.
    tarok_pack_records is the host-side serialiser (plain CPU code; returns the number of rows that are not permutations
    or carry an out-of-range contract/declarer -- those become records that decode to error games -- or -1 on NULL). */
-#define TAROK_RECORD_BYTES 24
+#define TAROK_RECORD_BYTES 20
 int64_t tarok_pack_records(const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
-                           const uint8_t* king_host /* or NULL */, uint64_t n, uint64_t* records_host /* [n,3] */);
+                           const uint8_t* king_host /* or NULL */, uint64_t n, void* records_host /* n x 20 bytes */);
 /* The same serialiser spread over `threads` host threads (std::thread; callers launched by torchrun run with
    OMP_NUM_THREADS=1, so the count is explicit). */
 int64_t tarok_pack_records_mt(const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
-                              const uint8_t* king_host /* or NULL */, uint64_t n, uint64_t* records_host, int threads);
-/* The serialiser picks an AVX-512 implementation at run time where the CPU has it (eight rows at a time, one per 64-bit
-   lane), else scalar code (BMI2 clone where available); both produce identical records.  tarok_pack_uses_avx512 tells which one runs,
+                              const uint8_t* king_host /* or NULL */, uint64_t n, void* records_host, int threads);
+/* The serialiser picks an AVX-512 (VBMI) implementation at run time where the CPU has it (one row per 64-bit lane, sixteen
+   rows = five cache lines of records per iteration), else scalar code (BMI2 clone where available); both produce identical records.  tarok_pack_uses_avx512 tells which one runs,
    tarok_pack_force_scalar(1) pins the scalar one (returns the previous setting; a testing aid). */
 int tarok_pack_uses_avx512(void);
 int tarok_pack_force_scalar(int on);
 /* tarok_rollout_host(fused = 1) that serialises the rows itself: each chunk of the upload/compute/download pipeline is
    packed into records by `threads` host threads (a pool kept in the handle, pinned scratch owned by the handle) right
    before its upload, so the caller keeps handing over what Igra.shuffle produces (Igra.py:65-73) and PCIe carries
-   24 B/deal.  Same outputs as tarok_rollout_host, bit-identical scores.  The pack runs on the calling thread + the pool:
+   20 B/deal.  Same outputs as tarok_rollout_host, bit-identical scores.  The pack runs on the calling thread + the pool:
    the call returns when the last chunk is enqueued (device work still asynchronous on `stream`). */
 int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host,
                               const uint8_t* declarer_host, const uint8_t* king_host, uint64_t first_global_game_id,
                               int threads, int16_t* scores_host, int64_t* stats_host, void* stream);
 /* tarok_rollout_host(fused = 1) fed with deal records; same outputs, bit-identical scores. */
-int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t first_global_game_id,
+int tarok_rollout_records(tarok_t* h, const void* records_host, uint64_t first_global_game_id,
                           int16_t* scores_host, int64_t* stats_host, void* stream);
 
 /* ---- observations: Nevronski_igralec.stanje_v_vektor_rek_navadna (Igralec.py:453-533) --------- */

@@ -43,7 +43,7 @@ struct tarok_env {
     int staging_ready;                         // set only after every stream / event / buffer below exists
     tk::u32* cta_hist;                         // scratch of tarok_obs_buckets: [n_alloc / 256][128]
     tarok_pack_pool* pool;                     // host threads of tarok_rollout_host_packed (lazily created)
-    uint64_t* pin_rec;                         // pinned scratch: the records of the chunk being uploaded [n_alloc, 3]
+    uint8_t* pin_rec;                          // pinned scratch: the records being uploaded [n_alloc x TAROK_RECORD_BYTES]
     int pack_used[TK_MAX_CHUNKS];              // chunk c of the pinned scratch has an upload recorded on ev_up[c]
     cudaStream_t s_up, s_down;                 // internal copy streams of the chunked host pipeline
     cudaEvent_t ev_fork, ev_join, ev_up[TK_MAX_CHUNKS], ev_done[TK_MAX_CHUNKS];
@@ -626,7 +626,7 @@ static int ensure_staging(tarok_t* h) {
 
 // Chunked pipeline shared by the two host-buffer entries: upload chunk c+1 (copy stream) while chunk c plays (caller's
 // stream) and chunk c-1's scores go back (download stream).  `row` = bytes per deal of the input format (54: permutation
-// rows + three 1-byte arrays; 24: deal records, which carry the contract themselves).
+// rows + three 1-byte arrays; 20: deal records, which carry the contract themselves).
 static int rollout_host_fused(tarok_t* h, const uint8_t* deals_host, size_t row, const uint8_t* contract_host,
                               const uint8_t* declarer_host, const uint8_t* king_host, int16_t* scores_host,
                               int64_t* stats_host, cudaStream_t s) {
@@ -653,7 +653,7 @@ static int rollout_host_fused(tarok_t* h, const uint8_t* deals_host, size_t row,
             tk::k_rollout_fused<tk::DEALS_PERM><<<grid, tk::CTA, tk::CTA * 54, s>>>(
                 ev, 0u, h->st_perm, h->st_contract, h->st_declarer, king_host ? h->st_king : nullptr, h->e.scores, 0, b);
         else
-            tk::k_rollout_fused<tk::DEALS_RECORD><<<grid, tk::CTA, 0, s>>>(ev, 0u, h->st_perm, nullptr, nullptr, nullptr,
+            tk::k_rollout_fused<tk::DEALS_RECORD><<<grid, tk::CTA, tk::CTA * TAROK_RECORD_BYTES, s>>>(ev, 0u, h->st_perm, nullptr, nullptr, nullptr,
                                                                           h->e.scores, 0, b);
         TK_LAUNCH_OK(h);
         if (scores_host) {
@@ -697,7 +697,7 @@ int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* cont
     return 0;
 }
 
-int tarok_rollout_records(tarok_t* h, const uint64_t* records_host, uint64_t first_global_game_id, int16_t* scores_host,
+int tarok_rollout_records(tarok_t* h, const void* records_host, uint64_t first_global_game_id, int16_t* scores_host,
                           int64_t* stats_host, void* stream) {
     TK_CHECK_HANDLE(h);
     if (!records_host) return fail(h, -1, "records_host is null");
@@ -719,14 +719,14 @@ static int packed_pipeline(tarok_t* h, const uint64_t* bounds, int nchunks, int1
     for (int c = 0; c < nchunks; c++) {
         const u64 b = bounds[c], e_ = bounds[c + 1], len = e_ - b;
         tarok_pack_pool_wait_chunk(h->pool, c);
-        TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * TAROK_RECORD_BYTES, (const uint8_t*)h->pin_rec + b * TAROK_RECORD_BYTES,
+        TK_CUDA(h, cudaMemcpyAsync(h->st_perm + b * TAROK_RECORD_BYTES, h->pin_rec + b * TAROK_RECORD_BYTES,
                                    len * TAROK_RECORD_BYTES, cudaMemcpyHostToDevice, h->s_up));
         TK_CUDA(h, cudaEventRecord(h->ev_up[c], h->s_up));
         h->pack_used[c] = 1;
         TK_CUDA(h, cudaStreamWaitEvent(s, h->ev_up[c], 0));
         tk::Env ev = h->e;
         ev.n = e_;
-        tk::k_rollout_fused<tk::DEALS_RECORD><<<(unsigned)((len + tk::CTA - 1) / tk::CTA), tk::CTA, 0, s>>>(
+        tk::k_rollout_fused<tk::DEALS_RECORD><<<(unsigned)((len + tk::CTA - 1) / tk::CTA), tk::CTA, tk::CTA * TAROK_RECORD_BYTES, s>>>(
             ev, 0u, h->st_perm, nullptr, nullptr, nullptr, h->e.scores, 0, b);
         TK_LAUNCH_OK(h);
         if (scores_host) {
@@ -742,8 +742,8 @@ static int packed_pipeline(tarok_t* h, const uint64_t* bounds, int nchunks, int1
 }
 
 // Third form of the host-buffer entry: the caller hands over permutation ROWS (what Igra.shuffle produces), the library
-// serialises each chunk into 24-byte deal records with `threads` host threads right before that chunk's upload, so PCIe
-// carries 24 instead of 57 bytes per deal and the packing of chunk c+1 overlaps the upload / play / download of chunk c.
+// serialises each chunk into 20-byte deal records with `threads` host threads right before that chunk's upload, so PCIe
+// carries 20 instead of 57 bytes per deal and the packing of chunk c+1 overlaps the upload / play / download of chunk c.
 int tarok_rollout_host_packed(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host, const uint8_t* declarer_host,
                               const uint8_t* king_host, uint64_t first_global_game_id, int threads, int16_t* scores_host,
                               int64_t* stats_host, void* stream) {

@@ -1,6 +1,6 @@
 // Host-side half of libtarok_b200.so (plain C++, compiled by g++): the serialiser that turns the permutation rows a
-// patched Igra.shuffle produces (Igra.py:65-73: uint8 [n,54]) + forced contracts into 24-byte deal records
-// (layout in include/tarok_b200.h), so the host-buffer entry moves 24 instead of 57 bytes per deal over PCIe.
+// patched Igra.shuffle produces (Igra.py:65-73: uint8 [n,54]) + forced contracts into 20-byte deal records
+// (layout in include/tarok_b200.h), so the host-buffer entry moves 20 instead of 57 bytes per deal over PCIe.
 // No device work here.  tarok_pack_records_mt splits the rows over `threads` std::threads (the callers of the
 // host-buffer entries are launched by torchrun with OMP_NUM_THREADS=1, so the thread count is an explicit argument).
 #include "../../include/tarok_b200.h"
@@ -21,11 +21,19 @@ namespace {
 
 constexpr uint64_t ALL54 = (1ull << 54) - 1;
 
-// One row -> three words (layout "deal records" in include/tarok_b200.h): the owner sets are built with independent
-// accumulators (a load, a shift and an OR per card); plane 0 = seats 1|3, plane 1 = seats 2|3; the six talon ids go into
-// w2 as they stand (6 bits each, talon order), followed by the forced contract.
+constexpr int REC = TAROK_RECORD_BYTES;                    // 20
+
+// One row -> one record (layout "deal records" in include/tarok_b200.h): the owner sets are built with independent
+// accumulators (a load, a shift and an OR per card); plane 0 = seats 1|3, plane 1 = seats 2|3; the six talon ids as they
+// stand (6 bits each, talon order) and the forced contract make up the 45-bit word m, which fills the ten spare bits of
+// each plane word and a third, 32-bit word.
 constexpr uint64_t ERR_PLANE = ALL54;                      // both planes full: every card "belongs to seat 3" -> decodes to an error game
-__attribute__((always_inline)) inline bool pack_row(const uint8_t* row, unsigned contract, unsigned declarer, unsigned king, uint64_t* w) {
+inline void store_record(uint8_t* out, uint64_t p0, uint64_t p1, uint64_t m) {
+    const uint64_t w0 = p0 | (m & 0x3FF) << 54, w1 = p1 | ((m >> 10) & 0x3FF) << 54;
+    const uint32_t w2 = (uint32_t)(m >> 20);
+    memcpy(out, &w0, 8); memcpy(out + 8, &w1, 8); memcpy(out + 16, &w2, 4);
+}
+__attribute__((always_inline)) inline bool pack_row(const uint8_t* row, unsigned contract, unsigned declarer, unsigned king, uint8_t* out) {
     uint64_t h[4] = {0, 0, 0, 0}, talon = 0, order = 0;
     unsigned over = 0;
     for (int s = 0; s < 4; s++) {
@@ -48,9 +56,8 @@ __attribute__((always_inline)) inline bool pack_row(const uint8_t* row, unsigned
     // or 7 of `over`)
     const bool ok = over < 64 && (h[0] | h[1] | h[2] | h[3] | talon) == ALL54 && contract <= 15u && declarer <= 3u;
     const unsigned k = king < 7u ? king : 7u;
-    w[0] = ok ? (h[1] | h[3]) : ERR_PLANE;
-    w[1] = ok ? (h[2] | h[3]) : ERR_PLANE;
-    w[2] = ok ? (order | (uint64_t)contract << 36 | (uint64_t)declarer << 40 | (uint64_t)k << 42) : 0ull;
+    if (ok) store_record(out, h[1] | h[3], h[2] | h[3], order | (uint64_t)contract << 36 | (uint64_t)declarer << 40 | (uint64_t)k << 42);
+    else store_record(out, ERR_PLANE, ERR_PLANE, 0);
     return ok;
 }
 
@@ -58,23 +65,24 @@ __attribute__((always_inline)) inline bool pack_row(const uint8_t* row, unsigned
 // micro-ops instead of the three-uop SHL-by-CL.
 __attribute__((target_clones("default", "arch=x86-64-v3")))
 int64_t pack_range_scalar(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king, uint64_t a,
-                          uint64_t b, uint64_t* records) {
+                          uint64_t b, uint8_t* records) {
     int64_t bad = 0;
     for (uint64_t g = a; g < b; g++)
-        bad += pack_row(perm + g * 54, contract[g], declarer[g], king ? king[g] : 7u, records + g * 3) ? 0 : 1;
+        bad += pack_row(perm + g * 54, contract[g], declarer[g], king ? king[g] : 7u, records + g * REC) ? 0 : 1;
     return bad;
 }
 
-// AVX-512 version, EIGHT ROWS AT A TIME, one row per 64-bit lane, so nothing is ever reduced across lanes: seven gathers
-// fetch bytes 8j..8j+7 of each of the eight rows; position 8j+k of every row is then one shift (byte k to the bottom), one
-// variable rotate of the constant 1 (VPROLVQ takes its count modulo 64 from the low six bits, so the other bytes of the
-// lane need no masking) and one OR into the accumulator of the position's owner.  ids >= 64 are caught by OR-ing the raw
-// bytes, ids 54..63 and duplicates by the cover test.  The last gather of a row reads two bytes of the next row, so the
-// caller keeps at least one row behind every group (the tail goes through the scalar code).
-#define TK_AVX512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,bmi2,popcnt")))
+// AVX-512 version, one row per 64-bit lane, so nothing is ever reduced across lanes: seven gathers fetch bytes 8j..8j+7 of
+// each of eight rows; position 8j+k of every row is then one byte move to the bottom of the lane (a byte shuffle on port
+// 5, for two positions in eight a shift on port 0), one variable rotate of the constant 1 (VPROLVQ takes its count modulo
+// 64 from the low six bits, so the other bytes of the lane need no masking) and one OR into the accumulator of the
+// position's owner.  ids >= 64 are caught by OR-ing the raw bytes, ids 54..63 and duplicates by the cover test.  Sixteen
+// rows (two such groups) make 320 bytes of records = five whole cache lines, assembled with two-source byte permutes
+// (AVX512-VBMI) and written with non-temporal stores when the buffer is 64-byte aligned (no read-for-ownership of lines the
+// CPU never reads back; the DMA engine does).  The last gather of a row reads two bytes of the next row, so the caller
+// keeps at least one row behind every group (the tail goes through the scalar code).
+#define TK_AVX512 __attribute__((target("avx512f,avx512bw,avx512vl,avx512dq,avx512vbmi,bmi2,popcnt")))
 template <int K> TK_AVX512 static inline __m512i one_hot_at(__m512i v) {        // 1 << (byte K of each lane & 63)
-    // the rotate runs on port 0 only (512-bit), so the byte is brought down by a byte shuffle (port 5) rather than a shift
-    // (port 0) for all but two of the eight positions: the two ports end up evenly loaded
     if (K == 0) return _mm512_rolv_epi64(_mm512_set1_epi64(1), v);
     if (K == 7 || K == 4) return _mm512_rolv_epi64(_mm512_set1_epi64(1), _mm512_srli_epi64(v, 8 * K));
     return _mm512_rolv_epi64(_mm512_set1_epi64(1), _mm512_shuffle_epi8(v, _mm512_broadcast_i32x4(_mm_set_epi64x(0x8080808080808008ll | K, 0x8080808080808000ll | K))));
@@ -90,63 +98,98 @@ TK_AVX512 static inline __m512i or4lo_into(__m512i acc, __m512i v) {
 TK_AVX512 static inline __m512i or4hi_into(__m512i acc, __m512i v) {
     return TK_OR3(TK_OR3(acc, one_hot_at<4>(v), one_hot_at<5>(v)), one_hot_at<6>(v), one_hot_at<7>(v));
 }
+// Eight rows -> the three record words per lane (w2 in the low 32 bits of its lane); returns the mask of valid rows.
+TK_AVX512 static inline __mmask8 pack8(const uint8_t* base, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king,
+                                       __m512i& w0, __m512i& w1, __m512i& w2) {
+    const __m512i row_off = _mm512_setr_epi64(0, 54, 108, 162, 216, 270, 324, 378);
+    const __m512i all54 = _mm512_set1_epi64((long long)ALL54);
+    const __m512i v0 = _mm512_i64gather_epi64(row_off, base, 1), v1 = _mm512_i64gather_epi64(row_off, base + 8, 1),
+                  v2 = _mm512_i64gather_epi64(row_off, base + 16, 1), v3 = _mm512_i64gather_epi64(row_off, base + 24, 1),
+                  v4 = _mm512_i64gather_epi64(row_off, base + 32, 1), v5 = _mm512_i64gather_epi64(row_off, base + 40, 1);
+    const __m512i v6 = _mm512_and_si512(_mm512_i64gather_epi64(row_off, base + 48, 1), _mm512_set1_epi64(0x0000FFFFFFFFFFFFll));
+    const __m512i s0 = or4lo_into(or8(v0), v1);                             // positions 0..11
+    const __m512i s1 = or4hi_into(or8(v2), v1);                             // 12..23
+    const __m512i s2 = or4lo_into(or8(v3), v4);                             // 24..35
+    const __m512i s3 = or4hi_into(or8(v5), v4);                             // 36..47
+    const __m512i tal = _mm512_or_si512(TK_OR3(one_hot_at<0>(v6), one_hot_at<1>(v6), one_hot_at<2>(v6)),
+                                        TK_OR3(one_hot_at<3>(v6), one_hot_at<4>(v6), one_hot_at<5>(v6)));
+    const __m512i cover = _mm512_or_si512(TK_OR3(s0, s1, s2), _mm512_or_si512(s3, tal));
+    const __m512i raw = _mm512_or_si512(TK_OR3(v0, v1, v2), _mm512_or_si512(TK_OR3(v3, v4, v5), v6));
+    const __m512i c8 = _mm512_cvtepu8_epi64(_mm_loadl_epi64((const __m128i*)contract));
+    const __m512i d8 = _mm512_cvtepu8_epi64(_mm_loadl_epi64((const __m128i*)declarer));
+    const __m512i k8 = king ? _mm512_min_epu64(_mm512_cvtepu8_epi64(_mm_loadl_epi64((const __m128i*)king)), _mm512_set1_epi64(7))
+                            : _mm512_set1_epi64(7);
+    const __mmask8 ok = _mm512_cmpeq_epi64_mask(cover, all54)
+                      & _mm512_testn_epi64_mask(raw, _mm512_set1_epi64((long long)0xC0C0C0C0C0C0C0C0ull))
+                      & _mm512_cmple_epu64_mask(c8, _mm512_set1_epi64(15)) & _mm512_cmple_epu64_mask(d8, _mm512_set1_epi64(3));
+    // the six talon ids -> 36 contiguous bits: byte pairs (x1, x64) -> 12-bit fields, field pairs (x1, x4096) -> 24 bits
+    const __m512i t12 = _mm512_maddubs_epi16(v6, _mm512_set1_epi16(0x4001));
+    const __m512i t24 = _mm512_madd_epi16(t12, _mm512_set1_epi32(0x10000001));
+    const __m512i order = _mm512_or_si512(_mm512_and_si512(t24, _mm512_set1_epi64(0xFFFFFF)),
+                                          _mm512_slli_epi64(_mm512_srli_epi64(t24, 32), 24));
+    const __m512i m = _mm512_maskz_or_epi64(ok, order, TK_OR3(_mm512_slli_epi64(c8, 36), _mm512_slli_epi64(d8, 40), _mm512_slli_epi64(k8, 42)));
+    const __m512i top = _mm512_set1_epi64((long long)(0x3FFull << 54));
+    w0 = _mm512_or_si512(_mm512_mask_blend_epi64(ok, all54, _mm512_or_si512(s1, s3)), _mm512_and_si512(_mm512_slli_epi64(m, 54), top));
+    w1 = _mm512_or_si512(_mm512_mask_blend_epi64(ok, all54, _mm512_or_si512(s2, s3)), _mm512_and_si512(_mm512_slli_epi64(m, 44), top));
+    w2 = _mm512_srli_epi64(m, 20);
+    return ok;
+}
+
+// Byte-permute tables that lay sixteen rows' (w0, w1, w2) out as 16 x 20 bytes = five 64-byte vectors: output byte k of
+// the block belongs to row k / 20 (half = row / 8, lane = row % 8) at offset k % 20 -- 0..7 from w0, 8..15 from w1, 16..19
+// from w2.  Per output vector and half: ab = index into the concatenation (w0, w1) for VPERMI2B, c = index into w2, cm =
+// bytes taken from w2, hm = bytes that belong to the second half.
+struct RecTables { alignas(64) uint8_t ab[5][2][64]; alignas(64) uint8_t c[5][2][64]; uint64_t cm[5][2]; uint64_t hm[5]; };
+constexpr RecTables make_rec_tables() {
+    RecTables t{};
+    for (int j = 0; j < 5; j++)
+        for (int i = 0; i < 64; i++) {
+            const int k = 64 * j + i, row = k / REC, off = k % REC, half = row / 8, lane = row % 8;
+            if (half) t.hm[j] |= 1ull << i;
+            if (off < 8) t.ab[j][half][i] = (uint8_t)(lane * 8 + off);
+            else if (off < 16) t.ab[j][half][i] = (uint8_t)(64 + lane * 8 + off - 8);
+            else { t.c[j][half][i] = (uint8_t)(lane * 8 + off - 16); t.cm[j][half] |= 1ull << i; }
+        }
+    return t;
+}
+alignas(64) static const RecTables REC_TABLES = make_rec_tables();
+
+template <int J, int HALF> TK_AVX512 static inline __m512i rec_bytes(__m512i w0, __m512i w1, __m512i w2) {
+    const __m512i t = _mm512_permutex2var_epi8(w0, _mm512_load_si512(REC_TABLES.ab[J][HALF]), w1);
+    return _mm512_mask_permutexvar_epi8(t, (__mmask64)REC_TABLES.cm[J][HALF], _mm512_load_si512(REC_TABLES.c[J][HALF]), w2);
+}
+
 TK_AVX512 static int64_t pack_range_avx512(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer,
-                                           const uint8_t* king, uint64_t a, uint64_t b, uint64_t* records) {
+                                           const uint8_t* king, uint64_t a, uint64_t b, uint8_t* records) {
     int64_t bad = 0;
     uint64_t g = a;
-    // a group's three stores are 64-byte aligned when the buffer is and the group starts at a multiple of eight rows: the
-    // records then leave with non-temporal stores (no read-for-ownership of lines the CPU never reads back; the DMA engine does)
+    // a block of sixteen records is five whole cache lines when the buffer is 64-byte aligned and the block starts at a
+    // multiple of sixteen rows
     const bool aligned = ((uintptr_t)records & 63) == 0;
-    if (aligned && (g & 7)) {
-        const uint64_t peel = (g + 7) & ~7ull;
+    if (aligned && (g & 15)) {
+        const uint64_t peel = (g + 15) & ~15ull;
         const uint64_t upto = peel < b ? peel : b;
         bad += pack_range_scalar(perm, contract, declarer, king, g, upto, records);
         g = upto;
     }
-    const __m512i row_off = _mm512_setr_epi64(0, 54, 108, 162, 216, 270, 324, 378);
-    const __m512i all54 = _mm512_set1_epi64((long long)ALL54);
-    // records of eight rows interleaved: [w0 w1 w2] x 8 = three stores
-    const __m512i ia0 = _mm512_setr_epi64(0, 8, 0, 1, 9, 0, 2, 10), ib0 = _mm512_setr_epi64(0, 0, 0, 0, 0, 1, 0, 0);
-    const __m512i ia1 = _mm512_setr_epi64(0, 3, 11, 0, 4, 12, 0, 5), ib1 = _mm512_setr_epi64(2, 0, 0, 3, 0, 0, 4, 0);
-    const __m512i ia2 = _mm512_setr_epi64(13, 0, 6, 14, 0, 7, 15, 0), ib2 = _mm512_setr_epi64(0, 5, 0, 0, 6, 0, 0, 7);
-    for (; g + 8 < b; g += 8) {
+    for (; g + 16 < b; g += 16) {
         const uint8_t* base = perm + g * 54;
-        for (int i = 0; i < 7; i++) _mm_prefetch((const char*)(base + 432 * 12 + 64 * i), _MM_HINT_T0);   // the gathers' lines, 12 groups ahead
-        const __m512i v0 = _mm512_i64gather_epi64(row_off, base, 1), v1 = _mm512_i64gather_epi64(row_off, base + 8, 1),
-                      v2 = _mm512_i64gather_epi64(row_off, base + 16, 1), v3 = _mm512_i64gather_epi64(row_off, base + 24, 1),
-                      v4 = _mm512_i64gather_epi64(row_off, base + 32, 1), v5 = _mm512_i64gather_epi64(row_off, base + 40, 1);
-        const __m512i v6 = _mm512_and_si512(_mm512_i64gather_epi64(row_off, base + 48, 1), _mm512_set1_epi64(0x0000FFFFFFFFFFFFll));
-        const __m512i s0 = or4lo_into(or8(v0), v1);                             // positions 0..11
-        const __m512i s1 = or4hi_into(or8(v2), v1);                             // 12..23
-        const __m512i s2 = or4lo_into(or8(v3), v4);                             // 24..35
-        const __m512i s3 = or4hi_into(or8(v5), v4);                             // 36..47
-        const __m512i tal = _mm512_or_si512(TK_OR3(one_hot_at<0>(v6), one_hot_at<1>(v6), one_hot_at<2>(v6)),
-                                            TK_OR3(one_hot_at<3>(v6), one_hot_at<4>(v6), one_hot_at<5>(v6)));
-        const __m512i cover = _mm512_or_si512(TK_OR3(s0, s1, s2), _mm512_or_si512(s3, tal));
-        const __m512i raw = _mm512_or_si512(TK_OR3(v0, v1, v2), _mm512_or_si512(TK_OR3(v3, v4, v5), v6));
-        const __m512i c8 = _mm512_cvtepu8_epi64(_mm_loadl_epi64((const __m128i*)(contract + g)));
-        const __m512i d8 = _mm512_cvtepu8_epi64(_mm_loadl_epi64((const __m128i*)(declarer + g)));
-        const __m512i k8 = king ? _mm512_min_epu64(_mm512_cvtepu8_epi64(_mm_loadl_epi64((const __m128i*)(king + g))), _mm512_set1_epi64(7))
-                                : _mm512_set1_epi64(7);
-        const __mmask8 ok = _mm512_cmpeq_epi64_mask(cover, all54)
-                          & _mm512_testn_epi64_mask(raw, _mm512_set1_epi64((long long)0xC0C0C0C0C0C0C0C0ull))
-                          & _mm512_cmple_epu64_mask(c8, _mm512_set1_epi64(15)) & _mm512_cmple_epu64_mask(d8, _mm512_set1_epi64(3));
-        // the six talon ids -> 36 contiguous bits: byte pairs (x1, x64) -> 12-bit fields, field pairs (x1, x4096) -> 24 bits
-        const __m512i t12 = _mm512_maddubs_epi16(v6, _mm512_set1_epi16(0x4001));
-        const __m512i t24 = _mm512_madd_epi16(t12, _mm512_set1_epi32(0x10000001));
-        const __m512i order = _mm512_or_si512(_mm512_and_si512(t24, _mm512_set1_epi64(0xFFFFFF)),
-                                              _mm512_slli_epi64(_mm512_srli_epi64(t24, 32), 24));
-        const __m512i meta = TK_OR3(_mm512_slli_epi64(c8, 36), _mm512_slli_epi64(d8, 40), _mm512_slli_epi64(k8, 42));
-        const __m512i w0 = _mm512_mask_blend_epi64(ok, all54, _mm512_or_si512(s1, s3));
-        const __m512i w1 = _mm512_mask_blend_epi64(ok, all54, _mm512_or_si512(s2, s3));
-        const __m512i w2 = _mm512_maskz_or_epi64(ok, order, meta);
-        uint64_t* out = records + g * 3;
-        const __m512i o0 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(w0, ia0, w1), (__mmask8)0x24, ib0, w2);
-        const __m512i o1 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(w0, ia1, w1), (__mmask8)0x49, ib1, w2);
-        const __m512i o2 = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(w0, ia2, w1), (__mmask8)0x92, ib2, w2);
-        if (aligned) { _mm512_stream_si512((__m512i*)out, o0); _mm512_stream_si512((__m512i*)(out + 8), o1); _mm512_stream_si512((__m512i*)(out + 16), o2); }
-        else { _mm512_storeu_si512(out, o0); _mm512_storeu_si512(out + 8, o1); _mm512_storeu_si512(out + 16, o2); }
-        bad += 8 - __builtin_popcount((unsigned)ok);
+        for (int i = 0; i < 14; i++) _mm_prefetch((const char*)(base + 864 * 6 + 64 * i), _MM_HINT_T0);   // the gathers' lines, 6 blocks ahead
+        __m512i a0, b0, c0, a1, b1, c1;
+        const __mmask8 ok0 = pack8(base, contract + g, declarer + g, king ? king + g : nullptr, a0, b0, c0);
+        const __mmask8 ok1 = pack8(base + 432, contract + g + 8, declarer + g + 8, king ? king + g + 8 : nullptr, a1, b1, c1);
+        const __m512i o0 = rec_bytes<0, 0>(a0, b0, c0), o1 = rec_bytes<1, 0>(a0, b0, c0);
+        const __m512i o2 = _mm512_mask_blend_epi8((__mmask64)REC_TABLES.hm[2], rec_bytes<2, 0>(a0, b0, c0), rec_bytes<2, 1>(a1, b1, c1));
+        const __m512i o3 = rec_bytes<3, 1>(a1, b1, c1), o4 = rec_bytes<4, 1>(a1, b1, c1);
+        uint8_t* out = records + g * REC;
+        if (aligned) {
+            _mm512_stream_si512((__m512i*)out, o0); _mm512_stream_si512((__m512i*)(out + 64), o1); _mm512_stream_si512((__m512i*)(out + 128), o2);
+            _mm512_stream_si512((__m512i*)(out + 192), o3); _mm512_stream_si512((__m512i*)(out + 256), o4);
+        } else {
+            _mm512_storeu_si512(out, o0); _mm512_storeu_si512(out + 64, o1); _mm512_storeu_si512(out + 128, o2);
+            _mm512_storeu_si512(out + 192, o3); _mm512_storeu_si512(out + 256, o4);
+        }
+        bad += 16 - __builtin_popcount((unsigned)ok0) - __builtin_popcount((unsigned)ok1);
     }
     if (aligned) _mm_sfence();
     return bad + pack_range_scalar(perm, contract, declarer, king, g, b, records);
@@ -154,10 +197,14 @@ TK_AVX512 static int64_t pack_range_avx512(const uint8_t* perm, const uint8_t* c
 
 std::atomic<int> g_force_scalar{0};
 
+bool cpu_is_wide() {
+    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl")
+        && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("bmi2");
+}
+
 int64_t pack_range(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king, uint64_t a,
-                   uint64_t b, uint64_t* records) {
-    static const bool wide = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")
-                          && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("bmi2");
+                   uint64_t b, uint8_t* records) {
+    static const bool wide = cpu_is_wide();
     return (wide && !g_force_scalar.load(std::memory_order_relaxed)) ? pack_range_avx512(perm, contract, declarer, king, a, b, records)
                 : pack_range_scalar(perm, contract, declarer, king, a, b, records);
 }
@@ -183,7 +230,7 @@ struct tarok_pack_pool {
     int parts = 1;
     // the current job
     const uint8_t *perm = nullptr, *contract = nullptr, *declarer = nullptr, *king = nullptr;
-    uint64_t* records = nullptr;
+    uint8_t* records = nullptr;
     uint64_t n = 0, nblocks = 0;
     int nchunks = 0;
     uint64_t bounds[PACK_MAX_CHUNKS + 1] = {};              // upload chunk c = rows [bounds[c], bounds[c + 1]); whole blocks except the last
@@ -277,10 +324,10 @@ int tarok_chunk_bounds(uint64_t n, int want, uint64_t quantum, uint64_t* bounds)
 // Starts packing rows [0, n) into `records`; bounds[0..nchunks] (tarok_chunk_bounds with quantum = tarok_pack_block_rows())
 // are the upload chunks that tarok_pack_pool_wait_chunk reports on.  Returns at once; the workers run in the background.
 void tarok_pack_pool_begin(tarok_pack_pool* p, const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer,
-                           const uint8_t* king, uint64_t n, const uint64_t* bounds, int nchunks, uint64_t* records) {
+                           const uint8_t* king, uint64_t n, const uint64_t* bounds, int nchunks, void* records) {
     p->next.store(PACK_CLOSED, std::memory_order_release);                  // nobody can take a block while the job changes
     while (p->active.load(std::memory_order_acquire) != 0) _mm_pause();      // stragglers of the previous job
-    p->perm = perm; p->contract = contract; p->declarer = declarer; p->king = king; p->records = records;
+    p->perm = perm; p->contract = contract; p->declarer = declarer; p->king = king; p->records = (uint8_t*)records;
     p->n = n;
     p->nchunks = nchunks;
     for (int c = 0; c <= nchunks; c++) p->bounds[c] = bounds[c];
@@ -310,15 +357,16 @@ int64_t tarok_pack_pool_bad(const tarok_pack_pool* p) { return p->bad.load(); }
 extern "C" {
 
 int64_t tarok_pack_records_mt(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king,
-                              uint64_t n, uint64_t* records, int threads) {
-    if (!perm || !contract || !declarer || !records) return -1;
+                              uint64_t n, void* records_out, int threads) {
+    if (!perm || !contract || !declarer || !records_out) return -1;
+    uint8_t* records = (uint8_t*)records_out;
     if (threads < 1) threads = 1;
     if ((uint64_t)threads > n / 4096 + 1) threads = (int)(n / 4096 + 1);      // not worth a thread below 4096 rows
     if (threads == 1) return pack_range(perm, contract, declarer, king, 0, n, records);
     std::vector<int64_t> bad((size_t)threads, 0);
     std::vector<std::thread> pool;
     pool.reserve((size_t)threads - 1);
-    const uint64_t per = (n + (uint64_t)threads - 1) / (uint64_t)threads;
+    const uint64_t per = ((n + (uint64_t)threads - 1) / (uint64_t)threads + 15) & ~15ull;   // slices start on 16-row blocks
     for (int t = 1; t < threads; t++) {
         const uint64_t a = per * (uint64_t)t, b = a + per < n ? a + per : n;
         if (a >= n) break;
@@ -333,14 +381,10 @@ int64_t tarok_pack_records_mt(const uint8_t* perm, const uint8_t* contract, cons
 
 int tarok_pack_force_scalar(int on) { return g_force_scalar.exchange(on ? 1 : 0); }
 
-int tarok_pack_uses_avx512(void) {
-    if (g_force_scalar.load()) return 0;
-    return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl")
-        && __builtin_cpu_supports("avx512dq") && __builtin_cpu_supports("bmi2");
-}
+int tarok_pack_uses_avx512(void) { return g_force_scalar.load() ? 0 : (cpu_is_wide() ? 1 : 0); }
 
 int64_t tarok_pack_records(const uint8_t* perm, const uint8_t* contract, const uint8_t* declarer, const uint8_t* king,
-                           uint64_t n, uint64_t* records) {
+                           uint64_t n, void* records) {
     return tarok_pack_records_mt(perm, contract, declarer, king, n, records, 1);
 }
 

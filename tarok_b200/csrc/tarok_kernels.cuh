@@ -354,14 +354,18 @@ __global__ void __launch_bounds__(CTA) k_set_deals(Env e, const uint8_t* __restr
     e.dpts[g] = 0;
 }
 
-// Compact deal record (24 B = three u64 words; include/tarok_b200.h "deal records"): two bit planes over the 54 card
-// ids give the seat of every hand card, w2 carries the six talon ids in talon order (= `torder` as it stands) and the
-// forced contract.  Decoding is a handful of bitwise ops plus six shifts for the talon set.
+// Compact deal record (20 B = five u32 words; include/tarok_b200.h "deal records"): two bit planes over the 54 card ids
+// give the seat of every hand card; the 45-bit word m -- the six talon ids in talon order (= `torder` as it stands) and the
+// forced contract -- sits in the ten spare bits of each plane word and the fifth u32.  Decoding is a handful of bitwise
+// ops plus six shifts for the talon set.
 struct DealRecord { u32 contract, declarer, king; };
-__device__ __forceinline__ Dealt deal_from_record(u64 w0, u64 w1, u64 w2, DealRecord& r, bool& ok) {
+constexpr int RECORD_BYTES = 20;
+__device__ __forceinline__ Dealt deal_from_record(const u32* a, DealRecord& r, bool& ok) {
+    const u64 w0 = (u64)a[0] | ((u64)a[1] << 32), w1 = (u64)a[2] | ((u64)a[3] << 32);
+    const u64 m = (w0 >> 54) | ((w1 >> 54) << 10) | ((u64)a[4] << 20);
     const u64 p0 = w0 & ALL54, p1 = w1 & ALL54;
     Dealt d;
-    d.order = w2 & ((1ull << 36) - 1ull);
+    d.order = m & ((1ull << 36) - 1ull);
     u64 t = 0;
     u32 top = 0;
 #pragma unroll
@@ -374,8 +378,8 @@ __device__ __forceinline__ Dealt deal_from_record(u64 w0, u64 w1, u64 w2, DealRe
     d.h0 = ALL54 & ~(p0 | p1 | t); d.h1 = p0 & ~p1; d.h2 = p1 & ~p0; d.h3 = p0 & p1;
     // two planes partition the ids into four classes; (12,12,12,12) + six distinct talon ids outside classes 1-3 <=> a deal
     ok = top < 54u && !(t & (p0 | p1)) && __popcll(t) == 6 && __popcll(d.h0) == 12 && __popcll(d.h1) == 12
-         && __popcll(d.h2) == 12 && __popcll(d.h3) == 12;
-    r.contract = (u32)(w2 >> 36) & 15u; r.declarer = (u32)(w2 >> 40) & 3u; r.king = (u32)(w2 >> 42) & 7u;
+         && __popcll(d.h2) == 12 && __popcll(d.h3) == 12 && (m >> 45) == 0ull;
+    r.contract = (u32)(m >> 36) & 15u; r.declarer = (u32)(m >> 40) & 3u; r.king = (u32)(m >> 42) & 7u;
     return d;
 }
 
@@ -1231,6 +1235,13 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
     u64 g = base + threadIdx.x;
     const u64 na = e.n_alloc;
     const u64 gid = e.first_gid + g;
+    if (DEALS == DEALS_RECORD) {
+        // the CTA's 256 records (5120 B, 16-byte aligned: the tile starts at a multiple of 4 records) go through shared memory
+        // with coalesced 16-byte loads; a lane then reads its five words at a stride of 5 banks (conflict-free).  The staging
+        // buffer is n_alloc x 54 bytes, so the last tile may read past the records: those lanes are not live.
+        const uint4* src = reinterpret_cast<const uint4*>(perm + base * RECORD_BYTES);
+        for (u32 v = threadIdx.x; v < CTA * RECORD_BYTES / 16; v += CTA) reinterpret_cast<uint4*>(shp)[v] = src[v];
+    }
     if (DEALS == DEALS_PERM) {
         const u64 total = e.n * 54ull, off = base * 54ull;
         const bool vec_ok = (((uintptr_t)perm) & 15u) == 0;
@@ -1249,10 +1260,8 @@ __global__ void __launch_bounds__(CTA) k_rollout_fused(Env e, u32 mode, const ui
         bool ok = true;
         DealRecord rec = {0u, 0u, NO_KING};
         if (DEALS == DEALS_PERM) d = deal_from_perm(shp + threadIdx.x * 54, ok);
-        else if (DEALS == DEALS_RECORD) {
-            const u64* w = reinterpret_cast<const u64*>(perm) + g * 3;
-            d = deal_from_record(w[0], w[1], w[2], rec, ok);
-        } else d = deal_philox(e.rng, gid);
+        else if (DEALS == DEALS_RECORD) d = deal_from_record(reinterpret_cast<const u32*>(shp) + threadIdx.x * (RECORD_BYTES / 4), rec, ok);
+        else d = deal_philox(e.rng, gid);
         h0 = d.h0; h1 = d.h1; h2 = d.h2; h3 = d.h3; talon = d.talon; order = d.order;
         meta = meta_fresh();
         const Words4 sb = setup_block(e.rng, gid);       // the device-side pre-play decisions (contract unless forced, exchange)

@@ -85,19 +85,24 @@ def test_pack_records_is_the_documented_layout():
     king = rng.integers(0, 4, n).astype(np.uint8)
     rec, bad = pack_records(perm, contract, declarer, king)
     assert bad == 0
-    w = rec.numpy().view(np.uint64)
+    raw = rec.numpy()
+    assert raw.shape == (n, 20) and raw.dtype == np.uint8
     for g in range(n):
-        w0, w1, w2 = (int(x) for x in w[g])
-        assert w0 >> 54 == 0 and w1 >> 54 == 0 and w2 >> 45 == 0
-        talon = [(w2 >> (6 * i)) & 63 for i in range(6)]
+        w0 = int.from_bytes(raw[g, 0:8].tobytes(), "little")
+        w1 = int.from_bytes(raw[g, 8:16].tobytes(), "little")
+        w2 = int.from_bytes(raw[g, 16:20].tobytes(), "little")
+        m = (w0 >> 54) | (w1 >> 54) << 10 | w2 << 20
+        w0 &= (1 << 54) - 1; w1 &= (1 << 54) - 1
+        assert m >> 45 == 0
+        talon = [(m >> (6 * i)) & 63 for i in range(6)]
         assert talon == perm[g, 48:].tolist()
         code = [((w0 >> c) & 1) | ((w1 >> c) & 1) << 1 for c in range(54)]
         assert all(code[c] == 0 for c in talon)
         for s in range(4):
             assert sorted(c for c in range(54) if code[c] == s and c not in talon) == sorted(perm[g, 12 * s:12 * s + 12].tolist())
-        assert (w2 >> 36) & 15 == contract[g]
-        assert (w2 >> 40) & 3 == declarer[g]
-        assert (w2 >> 42) & 7 == king[g]
+        assert (m >> 36) & 15 == contract[g]
+        assert (m >> 40) & 3 == declarer[g]
+        assert (m >> 42) & 7 == king[g]
     perm[0, 0] = perm[0, 1]
     assert pack_records(perm, contract, declarer, None)[1] == 1
 
@@ -134,10 +139,10 @@ def test_pack_records_vector_and_scalar_serialisers_agree():
                 out[(scalar, threads)] = (rec.numpy().copy(), bad)
         lib.tarok_pack_force_scalar(0)
         import torch
-        for shift in (0, 1, 5):                  # 64-byte aligned output (non-temporal stores) and two unaligned ones
-            buf = torch.zeros(n * 3 + 16, dtype=torch.int64)
-            off = (-buf.data_ptr() % 64) // 8 + shift
-            view = buf[off:off + n * 3].view(n, 3)
+        for shift in (0, 4, 20, 33):             # 64-byte aligned output (non-temporal stores) and three unaligned ones
+            buf = torch.zeros(n * 20 + 128, dtype=torch.uint8)
+            off = (-buf.data_ptr() % 64) + shift
+            view = buf[off:off + n * 20].view(n, 20)
             rec, bad = pack_records(perm, contract, declarer, king, out=view, threads=2)
             out[("vector, output shifted", shift)] = (rec.numpy().copy(), bad)
     finally:

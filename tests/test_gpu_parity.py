@@ -440,14 +440,14 @@ def test_host_buffer_entry_matches_device_path(oracle):
 
 @pytest.mark.parametrize("mode", [0, 16, 17])
 def test_deal_records_match_permutation_rows(oracle, mode):
-    """24-byte deal records carry the same deal (incl. the ORDER of the talon, which Klop consumes card by card) and the same
+    """20-byte deal records carry the same deal (incl. the ORDER of the talon, which Klop consumes card by card) and the same
     forced contract as the 57-byte row format: identical scores, and both agree with the oracle."""
     import torch
     from tarok_b200.env import pack_records
     n = 300001                                                       # ragged: not a multiple of the chunk or the CTA
     ref = oracle.rollout(77, 0, n, mode)
     rec, bad = pack_records(ref["perm"], ref["contract"], ref["declarer"], ref["king"])
-    assert bad == 0 and rec.shape == (n, 3)
+    assert bad == 0 and rec.shape == (n, 20)
     out = []
     for records in (False, True):
         env = _env(n, seed=77)

@@ -1,4 +1,4 @@
-"""Host-buffer entries: wall time per rollout vs pipeline depth (rows = 57 B/deal, records = 24 B/deal, rows packed in the call).
+"""Host-buffer entries: wall time per rollout vs pipeline depth (rows = 57 B/deal, records = 20 B/deal, rows packed in the call).
    python tools/e2e_chunks.py [games] [pack threads]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
