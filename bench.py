@@ -313,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
         else:
             env.rollout(mode, first_game_id=gid0, fused=False)
         stats_ring[i % len(stats_ring)].copy_(env.stats_dev)
-        if world > 1 and not probe:
+        if world > 1 and not probe and not os.environ.get("TAROK_BENCH_NO_ALLREDUCE"):   # (diagnostic switch; never set by default)
             # the one collective: returns/statistics, 256 B over NCCL/NVLink; asynchronous so that the next
             # rollout's deal overlaps it (waited for before the timed region closes)
             pending.append(dist.all_reduce(stats_ring[i % len(stats_ring)], async_op=True))
@@ -342,6 +342,12 @@ def run_ours(args, rank, world, local_rank):
     launches0 = env.launches
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if world > 1:
+        # device-side start gate: the host barrier lets the ranks go up to a millisecond or two apart (scheduler jitter), and a
+        # rank that starts late makes every other rank wait that long for its all-reduces inside their last timed interval.
+        # A collective enqueued on the launching stream holds every GPU until all have arrived, so the K steps start together.
+        gate = torch.zeros(1, device=dev)
+        dist.all_reduce(gate)
     t0.record()
     for i in range(args.steps):
         rollout(args.warmup + i, True, last=(i == args.steps - 1))
