@@ -232,6 +232,11 @@ int tarok_obs_shape(tarok_t* h, uint8_t* type_dev, uint8_t* rows_dev, void* stre
    offsets into sel_dev (entry 255 = number of listed games), 128 bucket offsets in observation ROWS (sum of size * T over
    the earlier buckets).  The caller reads counts once per step. */
 int tarok_obs_buckets(tarok_t* h, int players, int32_t* sel_dev, uint32_t* counts_dev, uint8_t* selkey_dev, void* stream);
+/* The same, and the 384 counts copied to counts_host (pinned host memory, may be NULL) behind them; the three kernels and the
+   copy go out as one CUDA-graph launch (TAROK_OPT_GRAPH): this call runs once per self-play step on an empty stream, where
+   every launch costs its full latency.  The caller synchronises the stream before reading counts_host. */
+int tarok_obs_buckets_host(tarok_t* h, int players, int32_t* sel_dev, uint32_t* counts_dev, uint8_t* selkey_dev,
+                           uint32_t* counts_host, void* stream);
 /* All buckets of a step in ONE launch each: tarok_obs_expand_buckets writes the inputs of every listed game into arenas
    laid out so that each bucket's arrays are contiguous -- opp [rows,3,54] / hand [rows,54] at row counts[256 + key] +
    (i - counts[128 + key]) * T for position i of sel_dev, the per-game vectors (talon [.,6,55], talon_klop [.,54], king [.,4],
@@ -246,6 +251,11 @@ int tarok_obs_expand_buckets(tarok_t* h, const int32_t* sel_dev, const uint8_t* 
 int tarok_select_action_buckets(tarok_t* h, const float* const* q_ptrs_dev, const int32_t* sel_dev, const uint8_t* selkey_dev,
                                 const uint32_t* counts_dev, uint64_t n_total, const float* random_card4, uint8_t* card_dev,
                                 float* qmax_dev, void* stream);
+/* tarok_select_action_buckets with the table of 128 device pointers given in HOST memory (it travels as kernel parameters:
+   nothing to fill or copy on the device). */
+int tarok_select_action_buckets_tab(tarok_t* h, const float* const* q_ptrs_host, const int32_t* sel_dev, const uint8_t* selkey_dev,
+                                    const uint32_t* counts_dev, uint64_t n_total, const float* random_card4, uint8_t* card_dev,
+                                    float* qmax_dev, void* stream);
 int tarok_obs_expand(tarok_t* h, int net_type, uint32_t rows, const int32_t* sel_dev, uint64_t n_sel, float* opp_dev,
                      float* hand_dev, float* talon_dev, float* king_dev, float* decl_dev, float* discard_dev,
                      float* mozne_dev, uint8_t* ok_dev, void* stream);

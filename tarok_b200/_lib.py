@@ -52,8 +52,10 @@ SIGNATURES = {
     "tarok_rollout_host_packed": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _I, _VP, _VP, _VP]),
     "tarok_obs_shape": (_I, [_VP, _VP, _VP, _VP]),
     "tarok_obs_buckets": (_I, [_VP, _I, _VP, _VP, _VP, _VP]),
+    "tarok_obs_buckets_host": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _VP]),
     "tarok_obs_expand_buckets": (_I, [_VP, _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tarok_select_action_buckets": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP]),
+    "tarok_select_action_buckets_tab": (_I, [_VP, _VP, _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP]),
     "tarok_obs_expand": (_I, [_VP, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tarok_obs_expand_at": (_I, [_VP, _I, _I, _U32, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tarok_targets": (_I, [_VP, _VP, _U64, C.c_float, _VP, _VP, _VP, _VP]),

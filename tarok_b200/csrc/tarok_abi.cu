@@ -33,6 +33,8 @@ struct tarok_env {
     cudaStream_t s_cap;                        // private stream the graphs are captured on
     tk::RunParams* run_dev;                    // {first_gid, rc_epoch} the GRAPH kernel variants read (rewritten before every replay)
     int capturing;                             // launch the GRAPH variants (set while a rollout graph is being captured)
+    cudaGraphExec_t bucket_graph;              // tarok_obs_buckets_host: hist + scan + scatter + counts copy as one launch
+    const void* bucket_key[5];                 // the arguments that graph was captured with
     int lazy_mask;                             // chains of random steps write legal masks in their last launch only (default on)
     int materialise;                           // tarok_score writes the materialised piles / talon back (default on)
     int chunks;                                // upload/compute/download pipeline depth of the host-buffer entries
@@ -175,6 +177,7 @@ extern "C" {
 
 // The captured graphs freeze every option (kernel variant, launch attributes, parameters): any change drops them.
 static void drop_graphs(tarok_env* h) {
+    if (h->bucket_graph) { cudaGraphExecDestroy(h->bucket_graph); h->bucket_graph = nullptr; }
     for (int m = 0; m < TK_GRAPH_MODES; m++)
         if (h->graphs[m]) { cudaGraphExecDestroy(h->graphs[m]); h->graphs[m] = nullptr; }
 }
@@ -217,7 +220,7 @@ int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, ta
     h->st_perm = h->st_contract = h->st_declarer = h->st_king = nullptr;
     h->s_up = h->s_down = nullptr; h->ev_fork = h->ev_join = nullptr; h->staging_ready = 0;
     memset(h->ev_up, 0, sizeof(h->ev_up)); memset(h->ev_done, 0, sizeof(h->ev_done));
-    h->use_graph = 1; memset(h->graphs, 0, sizeof(h->graphs)); h->s_cap = nullptr; h->run_dev = nullptr; h->capturing = 0; h->e.run_ptr = nullptr;
+    h->use_graph = 1; memset(h->graphs, 0, sizeof(h->graphs)); h->s_cap = nullptr; h->run_dev = nullptr; h->capturing = 0; h->e.run_ptr = nullptr; h->bucket_graph = nullptr;
     h->cta_hist = nullptr; h->pool = nullptr; h->pin_rec = nullptr; memset(h->pack_used, 0, sizeof(h->pack_used));
     const u64 na = (n_games + tk::TILE - 1) / tk::TILE * tk::TILE;
     h->e.n = n_games; h->e.n_alloc = na; h->epoch = 0; set_first_gid(h, 0);
@@ -785,20 +788,60 @@ int tarok_obs_shape(tarok_t* h, uint8_t* type_dev, uint8_t* rows_dev, void* stre
     return 0;
 }
 
+static int enqueue_obs_buckets(tarok_t* h, int players, int32_t* sel_dev, uint32_t* counts_dev, uint8_t* selkey_dev,
+                               uint32_t* counts_host, cudaStream_t s) {
+    const unsigned n_cta = grid1(h->e.n_alloc);
+    tk::k_bucket_hist<<<n_cta, tk::CTA, 0, s>>>(h->e, (u32)players, h->cta_hist);
+    TK_LAUNCH_OK(h);
+    tk::k_bucket_scan<<<1, tk::BUCKETS, 0, s>>>(h->cta_hist, n_cta, counts_dev);
+    TK_LAUNCH_OK(h);
+    tk::k_bucket_scatter<<<n_cta, tk::CTA, 0, s>>>(h->e, (u32)players, h->cta_hist, counts_dev, (int*)sel_dev, selkey_dev);
+    TK_LAUNCH_OK(h);
+    if (counts_host) TK_CUDA(h, cudaMemcpyAsync(counts_host, counts_dev, 3 * tk::BUCKETS * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
 int tarok_obs_buckets(tarok_t* h, int players, int32_t* sel_dev, uint32_t* counts_dev, uint8_t* selkey_dev, void* stream) {
+    return tarok_obs_buckets_host(h, players, sel_dev, counts_dev, selkey_dev, nullptr, stream);
+}
+
+// The same + the 1.5 KB of counts copied to (pinned) host memory.  This runs once per self-play step right after a
+// synchronisation, i.e. on an empty stream, where every launch costs its full latency: the three kernels and the copy are
+// replayed as ONE graph launch (captured per argument set on first use; dropped when an option changes).
+int tarok_obs_buckets_host(tarok_t* h, int players, int32_t* sel_dev, uint32_t* counts_dev, uint8_t* selkey_dev,
+                           uint32_t* counts_host, void* stream) {
     TK_CHECK_HANDLE(h);
     if (!sel_dev || !counts_dev) return fail(h, -1, "sel_dev/counts_dev is null");
     if (players != 1 && players != 4) return fail(h, -1, "players must be 1 or 4");
     DeviceGuard dg(h->device);
+    cudaStream_t s = S(stream);
     const unsigned n_cta = grid1(h->e.n_alloc);
     if (!h->cta_hist) TK_CUDA(h, cudaMalloc((void**)&h->cta_hist, (size_t)n_cta * tk::BUCKETS * sizeof(u32)));
-    tk::k_bucket_hist<<<n_cta, tk::CTA, 0, S(stream)>>>(h->e, (u32)players, h->cta_hist);
-    TK_LAUNCH_OK(h);
-    tk::k_bucket_scan<<<1, tk::BUCKETS, 0, S(stream)>>>(h->cta_hist, n_cta, counts_dev);
-    TK_LAUNCH_OK(h);
-    tk::k_bucket_scatter<<<n_cta, tk::CTA, 0, S(stream)>>>(h->e, (u32)players, h->cta_hist, counts_dev, (int*)sel_dev, selkey_dev);
-    TK_LAUNCH_OK(h);
-    return 0;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (h->use_graph && cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+        const void* key[5] = {sel_dev, counts_dev, selkey_dev, counts_host, (const void*)(intptr_t)players};
+        if (!h->bucket_graph || memcmp(key, h->bucket_key, sizeof(key)) != 0) {
+            if (h->bucket_graph) { cudaGraphExecDestroy(h->bucket_graph); h->bucket_graph = nullptr; }
+            if (!h->s_cap) TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            const uint64_t launches0 = h->launches;
+            TK_CUDA(h, cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_obs_buckets(h, players, sel_dev, counts_dev, selkey_dev, counts_host, h->s_cap);
+            const cudaError_t ce = cudaStreamEndCapture(h->s_cap, &g);
+            h->launches = launches0;
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(h, -2, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&h->bucket_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { h->bucket_graph = nullptr; return fail(h, -2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+            memcpy(h->bucket_key, key, sizeof(key));
+        }
+        TK_CUDA(h, cudaGraphLaunch(h->bucket_graph, s));
+        h->launches += 3;
+        return 0;
+    }
+    cudaGetLastError();
+    return enqueue_obs_buckets(h, players, sel_dev, counts_dev, selkey_dev, counts_host, s);
 }
 
 int tarok_obs_expand_buckets(tarok_t* h, const int32_t* sel_dev, const uint8_t* selkey_dev, const uint32_t* counts_dev,
@@ -845,6 +888,29 @@ int tarok_select_action_buckets(tarok_t* h, const float* const* q_ptrs_dev, cons
     const u64 warps_per_cta = tk::CTA / 32;
     tk::k_select_action_all<<<(unsigned)((n_total + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
         h->e, q_ptrs_dev, (const int*)sel_dev, selkey_dev, counts_dev, n_total, t4, card_dev, qmax_dev);
+    TK_LAUNCH_OK(h);
+    return 0;
+}
+
+int tarok_select_action_buckets_tab(tarok_t* h, const float* const* q_ptrs_host, const int32_t* sel_dev, const uint8_t* selkey_dev,
+                                    const uint32_t* counts_dev, uint64_t n_total, const float* random_card4, uint8_t* card_dev,
+                                    float* qmax_dev, void* stream) {
+    TK_CHECK_HANDLE(h);
+    if (!q_ptrs_host || !sel_dev || !selkey_dev || !counts_dev || !card_dev || !random_card4)
+        return fail(h, -1, "q_ptrs_host/sel_dev/selkey_dev/counts_dev/card_dev/random_card4 is null");
+    tk::Thresholds4 t4;
+    for (int p = 0; p < 4; p++) {
+        if (!(random_card4[p] >= 0.f && random_card4[p] <= 1.f)) return fail(h, -1, "random_card must be in [0,1]");
+        t4.t[p] = explore_threshold(random_card4[p]);
+    }
+    if (n_total == 0) return 0;
+    if (n_total > h->e.n) return fail(h, -1, "n_total exceeds the number of games");
+    DeviceGuard dg(h->device);
+    tk::QTable qt;
+    memcpy(qt.p, q_ptrs_host, sizeof(qt.p));
+    const u64 warps_per_cta = tk::CTA / 32;
+    tk::k_select_action_all_tab<<<(unsigned)((n_total + warps_per_cta - 1) / warps_per_cta), tk::CTA, 0, S(stream)>>>(
+        h->e, qt, (const int*)sel_dev, selkey_dev, counts_dev, n_total, t4, card_dev, qmax_dev);
     TK_LAUNCH_OK(h);
     return 0;
 }

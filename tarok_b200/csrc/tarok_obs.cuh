@@ -343,6 +343,23 @@ __global__ void __launch_bounds__(CTA) k_select_action(Env e, const float* __res
 // The action selection of EVERY bucket of a step in one launch: qptr[key] = the [bucket size, 54] output of that bucket's
 // forward pass (a table of device pointers the host fills), thr4[player] = the player's epsilon as a 32-bit threshold.
 struct Thresholds4 { u32 t[4]; };
+// The same with the table of bucket outputs passed BY VALUE (1 KB of kernel parameters): no device table to fill and copy.
+struct QTable { const float* p[BUCKETS]; };
+__global__ void __launch_bounds__(CTA) k_select_action_all_tab(Env e, QTable qt, const int* __restrict__ sel,
+                                                               const uint8_t* __restrict__ selkey, const u32* __restrict__ counts,
+                                                               u64 n_total, Thresholds4 thr4, uint8_t* __restrict__ card_out,
+                                                               float* __restrict__ qmax_out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 i = ((u64)blockIdx.x * CTA + threadIdx.x) >> 5;
+    if (i >= n_total) return;
+    const u32 key = selkey[i];
+    const float* q = qt.p[key & (BUCKETS - 1)];
+    if (!q) return;                                               // no forward was supplied for this bucket
+    const u32 p = key / 28u;
+    const u32 thr = p == 0 ? thr4.t[0] : p == 1 ? thr4.t[1] : p == 2 ? thr4.t[2] : thr4.t[3];
+    select_game(e, (u64)sel[i], q + (i - counts[BUCKETS + key]) * 54u, thr, card_out, qmax_out, lane);
+}
+
 __global__ void __launch_bounds__(CTA) k_select_action_all(Env e, const float* const* __restrict__ qptr,
                                                            const int* __restrict__ sel, const uint8_t* __restrict__ selkey,
                                                            const u32* __restrict__ counts, u64 n_total, Thresholds4 thr4,

@@ -342,9 +342,8 @@ class TarokEnv:
                         torch.zeros(128, dtype=torch.int64).pin_memory(),
                         torch.zeros(128, dtype=torch.int64, device=self.torch_device))
         sel, cnt, host, selkey = self._bk[:4]
-        self._check(self._lib.tarok_obs_buckets(self._h, int(players), C.c_void_p(sel.data_ptr()), C.c_void_p(cnt.data_ptr()),
-                                                C.c_void_p(selkey.data_ptr()), self._stream()))
-        host.copy_(cnt, non_blocking=True)
+        self._check(self._lib.tarok_obs_buckets_host(self._h, int(players), C.c_void_p(sel.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                                     C.c_void_p(selkey.data_ptr()), C.c_void_p(host.data_ptr()), self._stream()))
         torch.cuda.current_stream(self.torch_device).synchronize()
         return sel, host.numpy().view(np.uint32)
 
@@ -359,15 +358,14 @@ class TarokEnv:
     def select_action_buckets(self, n_total: int, q_by_key: dict, random_card4, cards, qmax=None):
         """ONE launch of ``select_action`` for every bucket: ``q_by_key[key]`` = that bucket's [size, 54] fp32 network output
         (contiguous CUDA tensors, kept alive by the caller until the stream has run the launch)."""
-        sel, cnt, _, selkey, ptr_h, ptr_d = self._bk
-        ptr_h.zero_()
+        sel, cnt, _, selkey = self._bk[:4]
+        tab = (C.c_void_p * 128)()                                   # travels as kernel parameters
         for k, q in q_by_key.items():
-            ptr_h[k] = q.data_ptr()
-        ptr_d.copy_(ptr_h, non_blocking=True)
+            tab[k] = q.data_ptr()
         eps = (C.c_float * 4)(*[float(x) for x in random_card4])
         p = lambda t: C.c_void_p(t.data_ptr())
-        self._check(self._lib.tarok_select_action_buckets(self._h, p(ptr_d), p(sel), p(selkey), p(cnt), int(n_total), eps, p(cards),
-                                                          p(qmax) if qmax is not None else None, self._stream()))
+        self._check(self._lib.tarok_select_action_buckets_tab(self._h, tab, p(sel), p(selkey), p(cnt), int(n_total), eps, p(cards),
+                                                              p(qmax) if qmax is not None else None, self._stream()))
 
     def obs_expand(self, net_type: int, rows: int, sel=None, play=None):
         """The network inputs of ``Nevronski_igralec.stanje_v_vektor_rek_navadna`` for the seat to move of the
