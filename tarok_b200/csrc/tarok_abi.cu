@@ -575,8 +575,11 @@ int tarok_rollout_stepwise(tarok_t* h, uint32_t mode, uint64_t first_global_game
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (h->use_graph && (h->use_graph == 2 || h->e.n_alloc <= (3ull << 20)) && h->step_impl != 2 && mode < TK_GRAPH_MODES
         && cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
-        if (!h->graphs[mode])
-            if (int rc = capture_rollout_graph(h, mode)) return rc;
+        if (!h->graphs[mode] && capture_rollout_graph(h, mode) != 0) {
+            h->use_graph = 0;                              // e.g. another capture is open in this thread: plain launches from now on
+            cudaGetLastError();
+            return enqueue_rollout_stepwise(h, mode, s);
+        }
         tk::k_set_run<<<1, 1, 0, s>>>(h->run_dev, h->e.first_gid, h->e.rc_epoch);
         TK_LAUNCH_OK(h);
         TK_CUDA(h, cudaGraphLaunch(h->graphs[mode], s));
@@ -825,20 +828,23 @@ int tarok_obs_buckets_host(tarok_t* h, int players, int32_t* sel_dev, uint32_t* 
             if (!h->s_cap) TK_CUDA(h, cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking));
             cudaGraph_t g = nullptr;
             const uint64_t launches0 = h->launches;
-            TK_CUDA(h, cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_obs_buckets(h, players, sel_dev, counts_dev, selkey_dev, counts_host, h->s_cap);
-            const cudaError_t ce = cudaStreamEndCapture(h->s_cap, &g);
+            cudaError_t ie = cudaErrorUnknown;
+            if (cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = enqueue_obs_buckets(h, players, sel_dev, counts_dev, selkey_dev, counts_host, h->s_cap);
+                const cudaError_t ce = cudaStreamEndCapture(h->s_cap, &g);
+                if (!rc && ce == cudaSuccess) ie = cudaGraphInstantiate(&h->bucket_graph, g, 0);
+            }
             h->launches = launches0;
-            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-            if (ce != cudaSuccess) return fail(h, -2, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
-            const cudaError_t ie = cudaGraphInstantiate(&h->bucket_graph, g, 0);
-            cudaGraphDestroy(g);
-            if (ie != cudaSuccess) { h->bucket_graph = nullptr; return fail(h, -2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
-            memcpy(h->bucket_key, key, sizeof(key));
+            if (g) cudaGraphDestroy(g);
+            if (ie != cudaSuccess) h->bucket_graph = nullptr;
+            else memcpy(h->bucket_key, key, sizeof(key));
         }
-        TK_CUDA(h, cudaGraphLaunch(h->bucket_graph, s));
-        h->launches += 3;
-        return 0;
+        if (h->bucket_graph) {
+            TK_CUDA(h, cudaGraphLaunch(h->bucket_graph, s));
+            h->launches += 3;
+            return 0;
+        }
+        cudaGetLastError();                                // capture failed: plain launches below
     }
     cudaGetLastError();
     return enqueue_obs_buckets(h, players, sel_dev, counts_dev, selkey_dev, counts_host, s);

@@ -1,6 +1,7 @@
 """CPU: the C-ABI library loads (no GPU needed) and exports every symbol include/tarok_b200.h declares."""
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -151,3 +152,17 @@ def test_pack_records_vector_and_scalar_serialisers_agree():
     assert bad == 8
     for k, (rec, b) in out.items():
         assert b == bad and np.array_equal(rec, ref), k
+
+
+def test_pack_pool_and_tapered_chunks_without_a_gpu(tmp_path):
+    """The host half of tarok_rollout_host_packed -- tapered upload chunks, the block-scheduled pack pool whose chunks complete
+    in order while later ones are still being packed -- compiled from the library's own source into a plain C++ harness
+    and compared with the single-threaded serialiser (ragged sizes, 1..4 threads, 1..29 chunks, one invalid row)."""
+    exe = str(tmp_path / "harness")
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", os.path.join(ROOT, "tests", "host_pool_harness.cpp"),
+           os.path.join(ROOT, "tarok_b200", "csrc", "tarok_host.cpp"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for rows, threads in ((300007, 4), (1 << 18, 3), (5000, 2), (1, 1), (2049, 4), (700001, 1)):
+        out = subprocess.run([exe, str(rows), str(threads)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and out.stdout.startswith("ok"), (rows, threads, out.stdout, out.stderr)
