@@ -83,7 +83,8 @@ enum { TAROK_F_HANDS = 0,   /* uint64 [4, n_alloc]  hand bitboards (Roka, Roka.p
 int tarok_create(int device, uint64_t n_games, uint64_t seed, uint32_t flags, tarok_t** out);
 int tarok_destroy(tarok_t* h);                 /* error if exported tensors are still alive */
 const char* tarok_last_error(const tarok_t* h);/* h may be NULL: last error of a failed tarok_create */
-/* Tuning knobs.  TAROK_OPT_STEP_IMPL: 0 auto (default), 1 plain play_step kernel, 2 persistent TMA-staged kernel. */
+/* Tuning knobs.  TAROK_OPT_STEP_IMPL: 0 auto (default), 1 plain play_step kernel, 2 persistent TMA-staged kernel (general path),
+   3 persistent prefetching lock-step kernel for the interior launches of random chains (both persistent ones measure slower). */
 #define TAROK_OPT_STEP_IMPL 1
 #define TAROK_OPT_PDL 2        /* 1 (default): chain play_step launches with programmatic dependent launch */
 #define TAROK_OPT_MATERIALISE 4 /* 1 (default): tarok_score writes the full piles / Klop talon back; 0: scores + stats only */

@@ -140,7 +140,22 @@ static void launch_step(tarok_env* h, const uint8_t* action, cudaStream_t s) {
     at[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (tma) cudaLaunchKernelEx(&cfg, tk::k_step_tma<RANDOM>, h->e, action);
+    // TAROK_OPT_STEP_IMPL = 3: the persistent prefetching kernel for what it covers -- interior launches (no masks) of a
+    // lock-step chain of random steps with the draw cache on for all three positions; everything else takes the plain kernel
+    const bool pp = h->step_impl == 3 && RANDOM && !MASK && h->lockstep && h->lock_plays >= 0 && h->e.rc_rows == 3u;
+    if (pp) {
+        const int hint = h->lock_plays;
+        const int pos = hint & 3;
+        const unsigned per_sm = pos == 3 ? TK_PP_BLOCKS_3 : TK_PP_BLOCKS_012;
+        const unsigned slots = (unsigned)h->sm_count * per_sm;
+        cfg.gridDim = dim3(tiles < slots ? tiles : slots);
+        switch (pos) {
+            case 0: cfg.dynamicSmemBytes = 2 * sizeof(tk::LockStage<0>); cudaLaunchKernelEx(&cfg, tk::k_step_pp<0, GRAPH>, h->e, hint); break;
+            case 1: cfg.dynamicSmemBytes = 2 * sizeof(tk::LockStage<1>); cudaLaunchKernelEx(&cfg, tk::k_step_pp<1, GRAPH>, h->e, hint); break;
+            case 2: cfg.dynamicSmemBytes = 2 * sizeof(tk::LockStage<2>); cudaLaunchKernelEx(&cfg, tk::k_step_pp<2, GRAPH>, h->e, hint); break;
+            default: cfg.dynamicSmemBytes = 2 * sizeof(tk::LockStage<3>); cudaLaunchKernelEx(&cfg, tk::k_step_pp<3, GRAPH>, h->e, hint); break;
+        }
+    } else if (tma) cudaLaunchKernelEx(&cfg, tk::k_step_tma<RANDOM>, h->e, action);
     else {
         const int hint = h->lockstep ? h->lock_plays : -1;
         switch (hint >= 0 ? (hint & 3) : 4) {
@@ -186,7 +201,7 @@ int tarok_set_option(tarok_t* h, int option, int64_t value) {
     TK_CHECK_HANDLE(h);
     drop_graphs(h);
     if (option == TAROK_OPT_GRAPH && value >= 0 && value <= 2) { h->use_graph = (int)value; return 0; }
-    if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 2) { h->step_impl = (int)value; return 0; }
+    if (option == TAROK_OPT_STEP_IMPL && value >= 0 && value <= 3) { h->step_impl = (int)value; return 0; }
     if (option == TAROK_OPT_PDL && (value == 0 || value == 1)) { h->pdl = (int)value; return 0; }
     if (option == TAROK_OPT_LOCKSTEP && (value == 0 || value == 1)) { h->lockstep = (int)value; return 0; }
     if (option == TAROK_OPT_MATERIALISE && (value == 0 || value == 1)) { h->materialise = (int)value; return 0; }

@@ -853,44 +853,13 @@ __device__ __forceinline__ void step_game_lock(const Env& e, u32 g, u64& meta, u
     }
 }
 
+// The work of a lock-step launch on one lane's game pair once its state is in registers: m = meta, hm = slot POS (the
+// mover's hand), n0 = slot POS + 1 (MASK or POS == 3), n1 / n2 = slots 1 / 2 (POS == 3), rc = the draw-cache entry.
 template <bool RANDOM, int POS, bool MASK>
-__device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restrict__ action, int hint) {
-    const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
-    const u32 na = (u32)e.n_alloc;                 // the grid covers n_alloc exactly: no partial warps
-    __shared__ __align__(16) uint8_t sel8[RANDOM ? SELECT8_SMEM : 16];
-    uint2 sel8_mine = {0u, 0u};                    // this thread's 8 bytes of the byte-select table (tarok_rules.cuh): independent of
-    if (RANDOM) sel8_mine = select8_fetch();       // the previous launch, so the load is issued before the dependency wait
-    // the run parameters (constant memory slot inside a replayed graph, else launch parameters)
-    const u64 fgid = RANDOM ? e.first_gid : 0ull;
-    const u32 tag = (RANDOM ? e.rc_epoch : 0u) | ((u32)hint >> 2);
-#if !TK_SEL8_LATE
-    if (RANDOM) { select8_store(sel8, sel8_mine); __syncthreads(); }
-#endif
-    pdl_wait();                                    // the previous step's writes are visible from here on
-    // every load is issued before the first use: one memory round trip per step
-    ulonglong2 m = ld2(e.meta + g);
-    ulonglong2 hm = ld2(e.hands + (POS * na + g));
-    ulonglong2 n0 = {0, 0}, n1 = {0, 0}, n2 = {0, 0};
-    if (MASK || POS == 3) n0 = ld2(e.hands + (((POS + 1) & 3) * na + g));     // the next seat's slot is only read for its mask
-    if (POS == 3) { n1 = ld2(e.hands + (na + g)); n2 = ld2(e.hands + (2 * na + g)); }
-    u32 act = 0;
-    if (!RANDOM) act = load_actions(action, g, e.n);
-    // draw cache: the pair's Philox block is computed by the position-0 launch of a trick, which leaves the lanes of
-    // positions 1-3 behind ({tag, lanes}, 8 B per pair and position); the three launches that follow read 8 B instead of
-    // running the ten rounds again.  The tag (epoch of first_gid | trick) makes a stale or never-written entry harmless:
-    // the block is then computed here as before.  Lanes straddle two pairs when first_gid is odd: no cache then.
-    constexpr u32 UPOS = POS > 0 ? (u32)POS : 0u;
-    bool in_rows = RANDOM && e.rc_rows != 0u;      // a launch parameter: the entry is fetched whatever first_gid turns out to be
-    if constexpr (POS > 0) in_rows = in_rows && UPOS <= e.rc_rows;
-    const bool cached = in_rows && !((u32)fgid & 1u);
-    uint2 rc = {0u, 0u};
-    if (in_rows && POS > 0) rc = e.rcache[(UPOS > 0u ? UPOS - 1u : 0u) * (na >> 1) + (g >> 1)];
-#if TK_SEL8_LATE
-    if (RANDOM) {                                  // behind the state loads in program order: all of them are in flight together
-        select8_store(sel8, sel8_mine);
-        __syncthreads();
-    }
-#endif
+__device__ __forceinline__ void step_lock_body(const Env& e, u32 g, int hint, u64 fgid, u32 tag, bool cached, ulonglong2 m,
+                                               ulonglong2 hm, ulonglong2 n0, ulonglong2 n1, ulonglong2 n2, uint2 rc, u32 act,
+                                               const uint8_t* __restrict__ sel8) {
+    const u32 na = (u32)e.n_alloc;
     const bool a0 = (((u32)m.x >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act & 0xFFu) != CARD_SKIP),
                a1 = (((u32)m.y >> M_PHASE) & 3u) == PH_PLAY && (RANDOM || (act >> 8) != CARD_SKIP);
     // plays sit in the top byte of the high word and the bits above them are clear for every live game
@@ -937,6 +906,47 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     st2(e.meta + g, m.x, m.y);
     // an in-kernel pick is always legal and only the trick-closing play can end a game: nothing to clear at positions 0-2
     if (MASK || !RANDOM || POS == 3) store_masks<RANDOM, MASK>(e, g, m, a0, a1, k0, k1);
+}
+
+template <bool RANDOM, int POS, bool MASK>
+__device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restrict__ action, int hint) {
+    const u32 g = (blockIdx.x * CTA + threadIdx.x) * 2;
+    const u32 na = (u32)e.n_alloc;                 // the grid covers n_alloc exactly: no partial warps
+    __shared__ __align__(16) uint8_t sel8[RANDOM ? SELECT8_SMEM : 16];
+    uint2 sel8_mine = {0u, 0u};                    // this thread's 8 bytes of the byte-select table (tarok_rules.cuh): independent of
+    if (RANDOM) sel8_mine = select8_fetch();       // the previous launch, so the load is issued before the dependency wait
+    // the run parameters (constant memory slot inside a replayed graph, else launch parameters)
+    const u64 fgid = RANDOM ? e.first_gid : 0ull;
+    const u32 tag = (RANDOM ? e.rc_epoch : 0u) | ((u32)hint >> 2);
+#if !TK_SEL8_LATE
+    if (RANDOM) { select8_store(sel8, sel8_mine); __syncthreads(); }
+#endif
+    pdl_wait();                                    // the previous step's writes are visible from here on
+    // every load is issued before the first use: one memory round trip per step
+    ulonglong2 m = ld2(e.meta + g);
+    ulonglong2 hm = ld2(e.hands + (POS * na + g));
+    ulonglong2 n0 = {0, 0}, n1 = {0, 0}, n2 = {0, 0};
+    if (MASK || POS == 3) n0 = ld2(e.hands + (((POS + 1) & 3) * na + g));     // the next seat's slot is only read for its mask
+    if (POS == 3) { n1 = ld2(e.hands + (na + g)); n2 = ld2(e.hands + (2 * na + g)); }
+    u32 act = 0;
+    if (!RANDOM) act = load_actions(action, g, e.n);
+    // draw cache: the pair's Philox block is computed by the position-0 launch of a trick, which leaves the lanes of
+    // positions 1-3 behind ({tag, lanes}, 8 B per pair and position); the three launches that follow read 8 B instead of
+    // running the ten rounds again.  The tag (epoch of first_gid | trick) makes a stale or never-written entry harmless:
+    // the block is then computed here as before.  Lanes straddle two pairs when first_gid is odd: no cache then.
+    constexpr u32 UPOS = POS > 0 ? (u32)POS : 0u;
+    bool in_rows = RANDOM && e.rc_rows != 0u;      // a launch parameter: the entry is fetched whatever first_gid turns out to be
+    if constexpr (POS > 0) in_rows = in_rows && UPOS <= e.rc_rows;
+    const bool cached = in_rows && !((u32)fgid & 1u);
+    uint2 rc = {0u, 0u};
+    if (in_rows && POS > 0) rc = e.rcache[(UPOS > 0u ? UPOS - 1u : 0u) * (na >> 1) + (g >> 1)];
+#if TK_SEL8_LATE
+    if (RANDOM) {                                  // behind the state loads in program order: all of them are in flight together
+        select8_store(sel8, sel8_mine);
+        __syncthreads();
+    }
+#endif
+    step_lock_body<RANDOM, POS, MASK>(e, g, hint, fgid, tag, cached, m, hm, n0, n1, n2, rc, act, sel8);
 }
 
 // `hint` = the number of plays every live game has made so far (lock-step pipelines know it on the host); POS = hint & 3
@@ -1041,6 +1051,88 @@ __global__ void __launch_bounds__(CTA, 4) k_step_tma(Env e, const uint8_t* __res
             step_pair_any<RANDOM>(e, g, m, a0, a1, s0, s1, s2, s3, act);
         }
         __syncthreads();                              // stage s may be refilled from the next iteration on
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// play_step, persistent + prefetching, position-specialised (TAROK_OPT_STEP_IMPL = 3): the interior launches of a chain of
+// in-kernel random steps (lock-step hint, lazy masks, draw cache on).  After the instruction cuts of round 2 the plain kernel
+// stalls on its initial loads (long scoreboard) -- every CTA waits a full L2 round trip before it has anything to do.  Here
+// one CTA per resident slot loops over 512-game tiles; ONE elected lane fetches the next tile's streams -- meta, the mover's
+// slot (all four at the trick-closing position) and the draw-cache row -- with 1-D bulk async copies
+// (cp.async.bulk -> UBLKCP) that complete on an mbarrier while the CTA works on the current tile, which it reads from shared
+// memory with conflict-free 128-bit LDS.  Same step_lock_body as the plain kernel, same results.
+// ------------------------------------------------------------------------------------------------
+template <int POS> struct __align__(128) LockStage {
+    u64 meta[TILE];
+    u64 slot[POS == 3 ? 4 : 1][TILE];
+    uint2 rc[POS > 0 ? TILE / 2 : 2];
+};
+template <int POS> __host__ __device__ constexpr u32 lock_stage_bytes() {
+    return TILE * 8u * (POS == 3 ? 5u : 2u) + (POS > 0 ? TILE * 4u : 0u);
+}
+#ifndef TK_PP_BLOCKS_012
+#define TK_PP_BLOCKS_012 5
+#endif
+#ifndef TK_PP_BLOCKS_3
+#define TK_PP_BLOCKS_3 4
+#endif
+
+template <int POS, bool GRAPH = false>
+__global__ void __launch_bounds__(CTA, POS == 3 ? TK_PP_BLOCKS_3 : TK_PP_BLOCKS_012) k_step_pp(Env e, int hint) {
+    extern __shared__ __align__(128) uint8_t pp_smem[];
+    LockStage<POS>* stage = reinterpret_cast<LockStage<POS>*>(pp_smem);
+    __shared__ __align__(8) u64 full[2];
+    __shared__ __align__(16) uint8_t sel8[SELECT8_SMEM];
+    pdl_launch_dependents();
+    if constexpr (GRAPH) load_run_params(e);
+    select8_to_shared(sel8);
+    const u32 na = (u32)e.n_alloc;
+    const u32 tiles = na / TILE;
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const u64 fgid = e.first_gid;
+    const u32 tag = e.rc_epoch | ((u32)hint >> 2);
+    const bool cached = !((u32)fgid & 1u);             // the host launches this variant with the draw cache on (rows 1-3)
+    pdl_wait();                                        // the previous step's writes are visible from here on
+    auto fetch = [&](u32 tile, u32 s) {                // elected lane: arm the barrier, issue the bulk copies of one tile
+        const u32 g0 = tile * TILE;
+        mbar_arrive_expect_tx(&full[s], lock_stage_bytes<POS>());
+        bulk_load(stage[s].meta, e.meta + g0, TILE * 8, &full[s]);
+        if (POS == 3) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) bulk_load(stage[s].slot[k], e.hands + (u64)k * na + g0, TILE * 8, &full[s]);
+        } else {
+            bulk_load(stage[s].slot[0], e.hands + (u64)POS * na + g0, TILE * 8, &full[s]);
+        }
+        if (POS > 0) bulk_load(stage[s].rc, e.rcache + (u64)(POS > 0 ? POS - 1 : 0) * (na >> 1) + (g0 >> 1), TILE * 4, &full[s]);
+    };
+    u32 tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < tiles) fetch(tile, 0);
+    const u32 l = threadIdx.x * 2;
+    for (u32 it = 0; tile < tiles; it++, tile += gridDim.x) {
+        const u32 s = it & 1u;
+        if (threadIdx.x == 0 && tile + gridDim.x < tiles) fetch(tile + gridDim.x, s ^ 1u);
+        const u32 g = tile * TILE + l;
+        mbar_wait(&full[s], (it >> 1) & 1u);
+        const ulonglong2 m = *reinterpret_cast<const ulonglong2*>(&stage[s].meta[l]);
+        ulonglong2 hm, n0 = {0, 0}, n1 = {0, 0}, n2 = {0, 0};
+        if (POS == 3) {
+            hm = *reinterpret_cast<const ulonglong2*>(&stage[s].slot[POS == 3 ? 3 : 0][l]);
+            n0 = *reinterpret_cast<const ulonglong2*>(&stage[s].slot[0][l]);
+            n1 = *reinterpret_cast<const ulonglong2*>(&stage[s].slot[POS == 3 ? 1 : 0][l]);
+            n2 = *reinterpret_cast<const ulonglong2*>(&stage[s].slot[POS == 3 ? 2 : 0][l]);
+        } else {
+            hm = *reinterpret_cast<const ulonglong2*>(&stage[s].slot[0][l]);
+        }
+        uint2 rc = {0u, 0u};
+        if (POS > 0) rc = stage[s].rc[threadIdx.x];
+        step_lock_body<true, POS, false>(e, g, hint, fgid, tag, cached, m, hm, n0, n1, n2, rc, 0u, sel8);
+        __syncthreads();                               // stage s may be refilled from the next iteration on
     }
 }
 

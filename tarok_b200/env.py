@@ -162,7 +162,8 @@ class TarokEnv:
     qmax_hist = property(lambda self: self.view(F_QMAX_HIST))    # float32 [48, n_alloc]
 
     def set_step_impl(self, impl: int):
-        """0 auto, 1 plain play_step kernel, 2 persistent TMA-staged kernel (A/B measurements)."""
+        """0 auto, 1 plain play_step kernel, 2 persistent TMA-staged kernel (general path), 3 persistent prefetching lock-step
+        kernel for the interior launches of random chains (A/B measurements)."""
         self._check(self._lib.tarok_set_option(self._h, 1, int(impl)))
 
     def set_chunks(self, chunks: int):

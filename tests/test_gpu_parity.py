@@ -595,10 +595,11 @@ def test_scores_only_path_matches_oracle(oracle, mode):
     env.close()
 
 
-@pytest.mark.parametrize("impl,pdl,lock", [(1, False, False), (1, True, False), (1, False, True), (2, True, False), (2, False, False)])
+@pytest.mark.parametrize("impl,pdl,lock", [(1, False, False), (1, True, False), (1, False, True), (2, True, False), (2, False, False),
+                                           (3, True, True), (3, False, True)])
 def test_every_play_step_variant_matches_oracle(oracle, impl, pdl, lock):
-    """The selectable play_step implementations (plain / TMA-staged, PDL on/off, lock-step specialisation on/off)
-    all produce the oracle's games; the default (plain + PDL + lock-step) is what the other tests run."""
+    """The selectable play_step implementations (plain / TMA-staged general path / persistent prefetching lock-step kernel, PDL
+    on/off, lock-step specialisation on/off) all produce the oracle's games, graph-backed or not."""
     n, seed = 70001, 31
     for mode in (17, 0):
         ref = oracle.rollout(seed, 10, n, mode)
