@@ -173,7 +173,9 @@ int tarok_rollout_fused(tarok_t* h, uint32_t mode, uint64_t first_global_game_id
 /* Host-buffer entry (the end-to-end path): uploads injected deals (uint8 [n,54]) and forced
    contracts (uint8 [n] each; king may be NULL for non-king games), plays them with uniform-random
    players, downloads scores (int16 [n,4]) and the stats vector (int64 [32]).  Asynchronous on
-   `stream` when the host buffers are pinned; the caller synchronises. */
+   `stream` when the host buffers are pinned; the caller synchronises.  The host-buffer entries (this one, _host_packed,
+   _records) START FROM A CLEARED statistics vector: stats_host holds the statistics of this call's deals only, and whatever
+   the handle had accumulated before is gone (read it with tarok_read_stats first if it matters). */
 int tarok_rollout_host(tarok_t* h, const uint8_t* perm_host, const uint8_t* contract_host,
                        const uint8_t* declarer_host, const uint8_t* king_host,
                        uint64_t first_global_game_id, int fused,
