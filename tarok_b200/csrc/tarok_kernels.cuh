@@ -1199,15 +1199,27 @@ __device__ __forceinline__ u64 score_from_log(u64 meta, const uint2* log12, int 
     if (is_navadna(contract)) {
         const u32 team = (lo >> M_TEAM) & 15u, king = (lo >> M_KING) & 7u;
         const u32 valid = (1u << tricks) - 1u;            // entries past the tricks played are stale
-        u32 pts = dpts, won = 0, kings = 0;
+        // Four tricks at a time, one per byte: the top byte of an entry is points (5 bits) | called-king flag | winner (2 bits).
+        // "won by the declarer's team" = bit `winner` of the 4-bit team mask, picked per byte with two select stages on
+        // byte-replicated team bits; everything else is byte-parallel adds (no byte can overflow: <= 3 x 20 points).
+        const u32 ONES = 0x01010101u;
+        const u32 t0 = (team & 1u) * ONES, t1 = ((team >> 1) & 1u) * ONES, t2 = ((team >> 2) & 1u) * ONES, t3 = (team >> 3) * ONES;
+        u32 accp = 0, accw = 0, acck = 0;
 #pragma unroll
-        for (u32 k = 0; k < 12; k++) {
-            const u32 entry = which ? log12[k].y : log12[k].x;
-            const u32 mine = (valid >> k) & (team >> (entry >> 30)) & 1u;            // a trick of the declarer's team
-            pts += mine * ((entry >> 24) & 31u);
-            won += mine;
-            kings |= mine & (entry >> 29);                                           // bit 0: the called king was in it
+        for (u32 j = 0; j < 3; j++) {
+            const u32 e0 = which ? log12[4 * j].y : log12[4 * j].x, e1 = which ? log12[4 * j + 1].y : log12[4 * j + 1].x,
+                      e2 = which ? log12[4 * j + 2].y : log12[4 * j + 2].x, e3 = which ? log12[4 * j + 3].y : log12[4 * j + 3].x;
+            const u32 top = __byte_perm(__byte_perm(e0, e1, 0x0073), __byte_perm(e2, e3, 0x0073), 0x5410);
+            const u32 w0 = (top >> 6) & ONES, w1 = (top >> 7) & ONES;
+            const u32 lo2 = (t0 & ~w0) | (t1 & w0), hi2 = (t2 & ~w0) | (t3 & w0);
+            const u32 vj = (((valid >> (4 * j)) & 15u) * 0x00204081u) & ONES;        // the four valid bits, one per byte
+            const u32 mine = ((lo2 & ~w1) | (hi2 & w1)) & vj;                         // 0 / 1 per byte
+            accp += top & (mine * 0x1Fu);
+            accw += mine;
+            acck |= (top >> 5) & mine;
         }
+        const u32 pts_won = (accp * ONES) >> 24, won = (accw * ONES) >> 24, kings = acck != 0u ? 1u : 0u;
+        u32 pts = dpts + pts_won;
         u32 n = 4u * won + (((lo >> M_GROUP) & 7u) != NO_GROUP ? talon_k(contract) : 0u);
         // leftover talon to a lone declarer of a king game who took the called king (Q7); a lone declarer is the whole team
         if (contract != C_SOLO_BREZ && __popc(team) == 1 && king != NO_KING && (kings & 1u)) {
