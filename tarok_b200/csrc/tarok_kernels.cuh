@@ -915,7 +915,7 @@ __device__ __forceinline__ void step_lock(const Env& e, const uint8_t* __restric
     __shared__ __align__(16) uint8_t sel8[RANDOM ? SELECT8_SMEM : 16];
     uint2 sel8_mine = {0u, 0u};                    // this thread's 8 bytes of the byte-select table (tarok_rules.cuh): independent of
     if (RANDOM) sel8_mine = select8_fetch();       // the previous launch, so the load is issued before the dependency wait
-    // the run parameters (constant memory slot inside a replayed graph, else launch parameters)
+    // the run parameters: launch parameters, overwritten from the device record first thing in the GRAPH kernel variants
     const u64 fgid = RANDOM ? e.first_gid : 0ull;
     const u32 tag = (RANDOM ? e.rc_epoch : 0u) | ((u32)hint >> 2);
 #if !TK_SEL8_LATE
