@@ -811,7 +811,7 @@ static int enqueue_obs_buckets(tarok_t* h, int players, int32_t* sel_dev, uint32
     const unsigned n_cta = grid1(h->e.n_alloc);
     tk::k_bucket_hist<<<n_cta, tk::CTA, 0, s>>>(h->e, (u32)players, h->cta_hist);
     TK_LAUNCH_OK(h);
-    tk::k_bucket_scan<<<1, tk::BUCKETS, 0, s>>>(h->cta_hist, n_cta, counts_dev);
+    tk::k_bucket_scan<<<1, tk::BUCKETS * tk::SCAN_PARTS, 0, s>>>(h->cta_hist, n_cta, counts_dev);
     TK_LAUNCH_OK(h);
     tk::k_bucket_scatter<<<n_cta, tk::CTA, 0, s>>>(h->e, (u32)players, h->cta_hist, counts_dev, (int*)sel_dev, selkey_dev);
     TK_LAUNCH_OK(h);

@@ -73,22 +73,32 @@ __global__ void __launch_bounds__(CTA) k_bucket_hist(Env e, u32 players, u32* __
     if (threadIdx.x < BUCKETS) cta_hist[(u64)blockIdx.x * BUCKETS + threadIdx.x] = sh[threadIdx.x];
 }
 
-// One CTA of 128 threads: thread k turns column k of cta_hist into exclusive offsets (in CTA order) and its total into
-// counts[k]; then an exclusive scan over the keys gives the bucket bases, counts[128 + k] (counts[255] = all listed games),
-// and the bases in observation ROWS, counts[256 + k] = sum over earlier buckets of size * T (where a bucket's block of the
-// [rows, 3, 54] / [rows, 54] arenas starts).
-__global__ void __launch_bounds__(BUCKETS) k_bucket_scan(u32* __restrict__ cta_hist, u32 n_cta, u32* __restrict__ counts) {
+// One CTA of 128 x SCAN_PARTS threads: column k of cta_hist (one entry per CTA of the histogram kernel) becomes exclusive
+// offsets in CTA order and its total counts[k] -- SCAN_PARTS threads per column, each over a contiguous range of CTAs (load
+// all, local exclusive scan, add the sum of the ranges before it), instead of one thread walking the whole column; then an
+// exclusive scan over the keys gives the bucket bases, counts[128 + k] (counts[255] = all listed games), and the bases in
+// observation ROWS, counts[256 + k] = sum over earlier buckets of size * T (where a bucket's block of the [rows, 3, 54] /
+// [rows, 54] arenas starts).
+constexpr u32 SCAN_PARTS = 8;
+__global__ void __launch_bounds__(BUCKETS * SCAN_PARTS) k_bucket_scan(u32* __restrict__ cta_hist, u32 n_cta, u32* __restrict__ counts) {
+    __shared__ u32 part[SCAN_PARTS][BUCKETS];
     __shared__ u32 tot[BUCKETS];
-    const u32 k = threadIdx.x;
+    const u32 k = threadIdx.x % BUCKETS, p = threadIdx.x / BUCKETS;
+    const u32 per = (n_cta + SCAN_PARTS - 1) / SCAN_PARTS, lo = p * per, hi = min(lo + per, n_cta);
+    u32 sum = 0;
+    for (u32 c = lo; c < hi; c++) sum += cta_hist[(u64)c * BUCKETS + k];
+    part[p][k] = sum;
+    __syncthreads();
     u32 run = 0;
-    for (u32 c = 0; c < n_cta; c++) {
+    for (u32 q = 0; q < p; q++) run += part[q][k];
+    for (u32 c = lo; c < hi; c++) {
         const u32 v = cta_hist[(u64)c * BUCKETS + k];
         cta_hist[(u64)c * BUCKETS + k] = run;
         run += v;
     }
-    tot[k] = k == BUCKET_DEAD ? 0u : run;              // games not waiting for a card are not listed
+    if (p == SCAN_PARTS - 1) tot[k] = k == BUCKET_DEAD ? 0u : run;      // games not waiting for a card are not listed
     __syncthreads();
-    if (k == 0) {
+    if (threadIdx.x == 0) {
         u32 base = 0, rows = 0;
         for (u32 j = 0; j < BUCKETS; j++) {
             const u32 v = tot[j];
