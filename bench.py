@@ -189,12 +189,14 @@ def cpu_port_rate(mode, target_seconds):
 
 
 def python_reference_same_box(budget_seconds):
-    """The unmodified Python reference timed on THIS box's host cores in THIS run -- possible only where its tree exists
-    (baseline/_ref or /root/reference; never on the GPU box: the reference is not pip-installable and may not be copied)."""
+    """The unmodified Python reference timed on THIS box's host cores in THIS run, from baseline/_ref (installed by
+    oracle/install_reference.sh in the build container; git-ignored, it travels to the GPU box with the snapshot) or
+    /root/reference."""
     try:
         from oracle import ref_harness as H
         if not H.reference_available():
             return {"status": "absent on this box", "looked_in": ["baseline/_ref", "/root/reference"],
+                    "how": "bash oracle/install_reference.sh in the build container puts the unmodified reference into baseline/_ref",
                     "container_measurement": "profiles/r02/reference_cpu_container.json (same script, build container)"}
         from oracle import time_reference as TR
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -207,42 +209,98 @@ def python_reference_same_box(budget_seconds):
         return {"status": "failed: %s" % str(ex)[:200]}
 
 
-def run_reference(args, rank):
-    """Reference arm: the reference's CPU rule engine (C port, all host threads) on the same workload; the Python engine
-    itself beside it where its tree exists on the box."""
-    if rank != 0:
-        return
+PY_WORKLOAD_OF_MODE = {16: "navadna_mix", 17: "paralel_start", 18: "paralel_start", 0: "klop", 1: "tri", 2: "dve", 3: "ena",
+                       7: "berac", 9: "berac"}
+
+
+def port_arm(args, seconds_per_step, steps, warmup):
+    """The C port of the reference rule engine (oracle/tarok_oracle.c + synth.c, OpenMP, all host threads) on bounded samples."""
     from oracle import oracle as O
     O.build()
     cores = O.use_all_threads()          # torchrun exports OMP_NUM_THREADS=1; the arm uses every host core
     t = time.perf_counter()
     O.rollout_stats_only(SEED, 0, 20000, args.mode)
     rate = 20000 / max(time.perf_counter() - t, 1e-4)
-    per_step = int(min(max(rate * 1.0, 20000), args.games))          # ~1 s of CPU work per step
-    for i in range(args.warmup):
+    per_step = int(min(max(rate * seconds_per_step, 20000), args.games))
+    for i in range(warmup):
         O.rollout_stats_only(SEED, i * per_step, per_step, args.mode)
     t0 = time.perf_counter()
-    steps = 0
-    for i in range(args.steps):
-        st = O.rollout_stats_only(SEED, (args.warmup + i) * per_step, per_step, args.mode)
-        steps += int(st[8])
+    env_steps = 0
+    for i in range(steps):
+        st = O.rollout_stats_only(SEED, (warmup + i) * per_step, per_step, args.mode)
+        env_steps += int(st[8])
     dt = time.perf_counter() - t0
-    v = steps / dt
-    sample = "%d deals per step (of the %d-deal workload), %d steps" % (per_step, args.games, args.steps)
-    pyref = python_reference_same_box(30.0) if not args.no_pyref else {"status": "skipped (--no-pyref)"}
-    print(json.dumps({
-        "impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": config_of(args),
-        "deals_per_sec": per_step * args.steps / dt,
-        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
-                         "python_reference_same_box": pyref},
-        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "C port of the reference rule engine (oracle/tarok_oracle.c + synth.c, OpenMP); the Python reference cannot "
-                "travel to the GPU box -- where its tree exists (build container) it is timed in this same run "
-                "(cpu_baseline.python_reference_same_box)",
-    }))
+    return {"value": env_steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port", "deals_per_sec": per_step * steps / dt,
+            "ms_per_step": dt / steps * 1e3,
+            "sample": "%d deals per step (of the %d-deal workload), %d steps" % (per_step, args.games, steps)}
+
+
+def run_reference(args, rank):
+    """Reference arm.  Where the unmodified Python reference is on the box (baseline/_ref, installed by
+    oracle/install_reference.sh; or /root/reference) THAT is what is timed -- the same workload through its own classes
+    (Igra.razdeli, Navadna_igra / Klop / Berac / Tarok.paralel_start with four Bot_igralec), one process per host core, each
+    step a bounded sample -- and the C port of the engine is reported beside it; otherwise the C port is the arm."""
+    if rank != 0:
+        return
+    from oracle import ref_harness as H
+    use_py = H.reference_available() and not args.no_pyref and args.mode in PY_WORKLOAD_OF_MODE
+    if use_py:
+        try:
+            line = python_arm(args, H)
+        except Exception as ex:                                              # anything wrong with the tree or the pool: the port
+            print("bench.py: Python reference arm failed (%s); timing the C port instead" % str(ex)[:200], file=sys.stderr)
+            line = None
+        if line is not None:
+            print(json.dumps(line))
+            return
+    base = port_arm(args, 1.0, args.steps, args.warmup)
+    base["python_reference_same_box"] = python_reference_same_box(30.0) if not args.no_pyref else {"status": "skipped (--no-pyref)"}
+    v, ms, dps = base["value"], base.pop("ms_per_step"), base["deals_per_sec"]
+    note = ("C port of the reference rule engine (oracle/tarok_oracle.c + synth.c, OpenMP): the Python reference is not on this "
+            "box (bash oracle/install_reference.sh in the build container installs it into baseline/_ref)")
+    print(json.dumps(reference_line(args, v, ms, dps, base, note)))
+
+
+def reference_line(args, v, ms, dps, base, note):
+    return {"impl": "reference", "metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": config_of(args),
+            "deals_per_sec": dps,
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": note}
+
+
+def python_arm(args, H):
+    if True:
+        from oracle import time_reference as TR
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        fn = PY_WORKLOAD_OF_MODE[args.mode]
+        H.load_reference()                                                   # once, before the pools fork
+        TR.run_workload(fn, 10 * cores, cores)                               # imports, page faults
+        probe = TR.run_workload(fn, 60 * cores, cores)
+        # a step = about one second of the box's cores (the whole run must end within minutes whatever --steps is)
+        budget = min(1.0, 150.0 / max(1, args.steps + args.warmup))
+        per_step = max(cores * 8, int(probe["deals_per_sec"] * budget))
+        for i in range(args.warmup):
+            TR.run_workload(fn, per_step, cores, seed0=1000 + 64 * i)
+        env_steps, deals, busy = 0, 0, 0.0
+        for i in range(args.steps):
+            r = TR.run_workload(fn, per_step, cores, seed0=100000 + 64 * i)
+            env_steps += r["env_steps"]; deals += r["deals"]; busy += r["seconds"]
+        v = env_steps / busy
+        port = port_arm(args, 0.5, 3, 1)
+        one = TR.run_workload(fn, max(40, int(probe["deals_per_sec"] / cores * 1.0)), 1)
+        base = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "reference",
+                "sample": "%d deals per step through the unmodified Python engine (%s, 4 x Bot_igralec), %d processes, %d steps; a "
+                          "step's time = its slowest process (process-pool start-up excluded)" % (per_step, fn, cores, args.steps),
+                "tree": H.REFERENCE_DIR, "python": sys.version.split()[0], "single_core_value": one["env_steps_per_sec"],
+                "c_port": port}
+        ms = busy / args.steps * 1e3
+        note = ("the UNMODIFIED Python reference (baseline/_ref) on every host core; cpu_baseline.c_port = the C restatement of its "
+                "engine (OpenMP) on the same cores, the conservative comparison")
+        return reference_line(args, v, ms, deals / busy, base, note)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

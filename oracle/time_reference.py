@@ -156,15 +156,15 @@ def _run(args):
             sys.stdout = old
 
 
-def run_workload(fn, total_deals, workers):
-    """`total_deals` of workload `fn` spread over `workers` processes; returns the result row."""
+def run_workload(fn, total_deals, workers, seed0=100):
+    """`total_deals` of workload `fn` spread over `workers` processes (seeds seed0 + i); returns the result row."""
     per = max(1, total_deals // workers)
     t0 = time.perf_counter()
     if workers == 1:
-        res = [_run((fn, per, 1))]
+        res = [_run((fn, per, seed0 - 99))]
     else:
         with mp.get_context("fork").Pool(workers) as pool:
-            res = pool.map(_run, [(fn, per, 100 + i) for i in range(workers)])
+            res = pool.map(_run, [(fn, per, seed0 + i) for i in range(workers)])
     wall = time.perf_counter() - t0
     deals, steps = sum(r[0] for r in res), sum(r[1] for r in res)
     busy = max(r[2] for r in res)
