@@ -66,3 +66,27 @@ def test_two_rank_allreduce_equals_single_process(tmp_path, oracle):
     assert (got[0:4] == r["stats"][0:4]).all() and (got[4:8] == r["stats"][4:8]).all()
     assert got[19] == r["stats"][8] and got[18] == ok.sum()
     assert (got[8:18] == np.bincount(r["contract"][ok], minlength=10)).all()
+
+
+def test_reference_arm_prints_the_contract_line(tmp_path):
+    """`bench.py --impl reference` needs no GPU: it must print exactly one JSON line with the contract's keys -- the C port arm
+    (`--no-pyref`) and, where the reference tree is installed, the arm that times the unmodified Python engine."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in (["--no-pyref"], []):
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                              "--games", "65536"] + extra, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-500:]
+        lines = [l for l in out.stdout.splitlines() if l.strip()]
+        assert len(lines) == 1, out.stdout[-500:]
+        d = json.loads(lines[0])
+        for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config",
+                  "cpu_baseline", "e2e"):
+            assert k in d, k
+        assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["value"] > 0
+        assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+        assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        if extra:
+            assert d["cpu_baseline"]["kind"] == "port"
