@@ -189,14 +189,13 @@ def cpu_port_rate(mode, target_seconds):
 
 
 def python_reference_same_box(budget_seconds):
-    """The unmodified Python reference timed on THIS box's host cores in THIS run, from baseline/_ref (installed by
-    oracle/install_reference.sh in the build container; git-ignored, it travels to the GPU box with the snapshot) or
-    /root/reference."""
+    """The unmodified Python reference timed on THIS box's host cores in THIS run -- possible only where its tree exists
+    (/root/reference in the build container, or a tree named by TAROK_REFERENCE_DIR; a Python reference does not travel to the
+    GPU box and its sources are not copied into this repository)."""
     try:
         from oracle import ref_harness as H
         if not H.reference_available():
             return {"status": "absent on this box", "looked_in": ["baseline/_ref", "/root/reference"],
-                    "how": "bash oracle/install_reference.sh in the build container puts the unmodified reference into baseline/_ref",
                     "container_measurement": "profiles/r02/reference_cpu_container.json (same script, build container)"}
         from oracle import time_reference as TR
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -236,10 +235,10 @@ def port_arm(args, seconds_per_step, steps, warmup):
 
 
 def run_reference(args, rank):
-    """Reference arm.  Where the unmodified Python reference is on the box (baseline/_ref, installed by
-    oracle/install_reference.sh; or /root/reference) THAT is what is timed -- the same workload through its own classes
-    (Igra.razdeli, Navadna_igra / Klop / Berac / Tarok.paralel_start with four Bot_igralec), one process per host core, each
-    step a bounded sample -- and the C port of the engine is reported beside it; otherwise the C port is the arm."""
+    """Reference arm.  Where the unmodified Python reference is on the box (/root/reference in the build container, or
+    TAROK_REFERENCE_DIR) THAT is what is timed -- the same workload through its own classes (Igra.razdeli, Navadna_igra / Klop /
+    Berac / Tarok.paralel_start with four Bot_igralec), one process per host core, each step a bounded sample -- and the C port
+    of the engine is reported beside it; on the GPU box, where the Python tree cannot be, the C port is the arm."""
     if rank != 0:
         return
     from oracle import ref_harness as H
@@ -257,7 +256,7 @@ def run_reference(args, rank):
     base["python_reference_same_box"] = python_reference_same_box(30.0) if not args.no_pyref else {"status": "skipped (--no-pyref)"}
     v, ms, dps = base["value"], base.pop("ms_per_step"), base["deals_per_sec"]
     note = ("C port of the reference rule engine (oracle/tarok_oracle.c + synth.c, OpenMP): the Python reference is not on this "
-            "box (bash oracle/install_reference.sh in the build container installs it into baseline/_ref)")
+            "box; where its tree exists (build container) the same command times the Python engine itself")
     print(json.dumps(reference_line(args, v, ms, dps, base, note)))
 
 
@@ -298,7 +297,7 @@ def python_arm(args, H):
                 "tree": H.REFERENCE_DIR, "python": sys.version.split()[0], "single_core_value": one["env_steps_per_sec"],
                 "c_port": port}
         ms = busy / args.steps * 1e3
-        note = ("the UNMODIFIED Python reference (baseline/_ref) on every host core; cpu_baseline.c_port = the C restatement of its "
+        note = ("the UNMODIFIED Python reference (%s) on every host core; cpu_baseline.c_port = the C restatement of its " % H.REFERENCE_DIR +
                 "engine (OpenMP) on the same cores, the conservative comparison")
         return reference_line(args, v, ms, deals / busy, base, note)
 
