@@ -153,6 +153,9 @@ int tarok_steps_random(tarok_t* h, uint32_t count, void* stream);    /* `count` 
         Berac.py:33-44; Tarok.rezultati accumulation (Tarok.py:59-61) --------------------------- */
 int tarok_score(tarok_t* h, int16_t* out_dev /* [n_games,4] or NULL */, void* stream);
 int tarok_reset_stats(tarok_t* h, void* stream);
+/* A new run seed for an existing handle (what tarok_create's `seed` sets: the key of every synthetic Philox draw) without
+   releasing the device buffers; work already enqueued keeps the old seed. */
+int tarok_reseed(tarok_t* h, uint64_t seed);
 int tarok_read_stats(tarok_t* h, int64_t* out_host /* [32] */, void* stream); /* synchronises stream */
 
 /* ---- multi-GPU: the only exchange on the path ------------------------------------ */

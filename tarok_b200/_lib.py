@@ -38,6 +38,7 @@ SIGNATURES = {
     "tarok_steps_random": (_I, [_VP, _U32, _VP]),
     "tarok_score": (_I, [_VP, _VP, _VP]),
     "tarok_reset_stats": (_I, [_VP, _VP]),
+    "tarok_reseed": (_I, [_VP, _U64]),
     "tarok_read_stats": (_I, [_VP, _VP, _VP]),
     "tarok_allreduce_stats": (_I, [_VP, _VP, _VP, _VP]),
     "tarok_setup_synth": (_I, [_VP, _U32, _U64, _VP]),

@@ -472,6 +472,17 @@ int tarok_score(tarok_t* h, int16_t* out_dev, void* stream) {
     return 0;
 }
 
+// A new run seed for an existing handle (the Philox key of every synthetic draw): what tarok_create(seed) sets, without
+// giving the device buffers back -- a caller that plays batch after batch under fresh seeds (Tarok.start / paralel_start with no
+// seed given) keeps one handle.  Work already enqueued keeps the old key (kernel parameters are copied at launch).
+int tarok_reseed(tarok_t* h, uint64_t seed) {
+    TK_CHECK_HANDLE(h);
+    drop_graphs(h);                                        // the captured kernels carry the old round keys
+    tk::philox_keys_init(h->e.rng, seed);
+    set_first_gid(h, h->e.first_gid);                      // a new draw-cache epoch: cached lanes belong to the old key
+    return 0;
+}
+
 int tarok_reset_stats(tarok_t* h, void* stream) {
     TK_CHECK_HANDLE(h);
     DeviceGuard dg(h->device);

@@ -275,6 +275,11 @@ class TarokEnv:
         self._check(self._lib.tarok_score(self._h, None, self._stream()))
         return self.scores[: self.n]
 
+    def reseed(self, seed: int):
+        """A new run seed (the Philox key of every synthetic draw) for this environment, keeping its device buffers."""
+        self._check(self._lib.tarok_reseed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+        self.seed = int(seed)
+
     def reset_stats(self):
         self._check(self._lib.tarok_reset_stats(self._h, self._stream()))
 

@@ -469,12 +469,11 @@ class Tarok:
         on the device (the fused rollout kernel: bit-identical to the 50-launch stepwise pipeline, one launch); only the
         32-entry statistics vector comes back."""
         seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(8), "little")
-        env = E.TarokEnv(st_iger, seed=seed, device=self.device)
-        env.set_materialise(False)                       # only the result sums are needed (Tarok.py:59-61)
+        env = _okolje_na_napravi(st_iger, seed, self.device)
+        env.reset_stats()
         env.rollout(E.MODE_AUCTION_BOT, first_game_id=0, fused=True)
         st = env.stats()
         self.statistika = st
-        env.close()
         if int(st[E.S_ERRORS]):
             # the reference raises out of random.sample when fewer than k cards can be laid down (Igralec.py:166, Q19)
             raise ValueError("Sample larger than population or is negative (%d of %d deals: a Bot_igralec declarer "
@@ -482,6 +481,33 @@ class Tarok:
         vsote = st[E.S_PLAYER:E.S_PLAYER + 4] if rotacija else st[E.S_SEAT:E.S_SEAT + 4]
         for p, igralec in enumerate(self.igralci):
             self.rezultati[igralec] += int(vsote[p])
+
+
+# The device environment of the Bot fast path is kept between calls (one per device, the last batch size): main.py's loop
+# builds a new Tarok(igralci, num_games) for every iteration (main.py:111-116), and allocating + clearing ~170 MB of state per
+# million games each time costs far more than playing them (20 ms against 0.3 ms).  ``sprosti_okolja()`` gives the memory back.
+_OKOLJA = {}
+
+
+def _okolje_na_napravi(st_iger, seed, device):
+    env = _OKOLJA.get(device)
+    if env is not None and (env.n != st_iger or not env._h):
+        env.close()
+        env = None
+    if env is None:
+        env = E.TarokEnv(st_iger, seed=seed, device=device)
+        env.set_materialise(False)                       # only the result sums are needed (Tarok.py:59-61)
+        _OKOLJA[device] = env
+    else:
+        env.reseed(seed)
+    return env
+
+
+def sprosti_okolja():
+    """Releases the device environments kept by the Bot fast path of ``Tarok.start`` / ``paralel_start``."""
+    for env in _OKOLJA.values():
+        env.close()
+    _OKOLJA.clear()
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -238,3 +238,28 @@ def test_reference_exceptions_are_reproduced():
     t.izpis = False
     t.paralel_start()
     assert all(v <= 0 for v in t.rezultati.values())                 # Klop scores are never positive (Klop.py:36-42)
+
+
+def test_bot_fast_path_keeps_its_environment_between_calls():
+    """main.py builds a new Tarok(igralci, num_games) every iteration (main.py:111-116): the Bot fast path re-uses one device
+    environment (re-seeded) instead of allocating a new one -- same results as before for a given seed, different deals for
+    different seeds, and the memory can be handed back."""
+    from tarok_b200 import Tarok, Bot_igralec
+    from tarok_b200 import igra as I
+    I.sprosti_okolja()
+    res = []
+    for seed in (5, 6, 5):
+        bots = [Bot_igralec() for _ in range(4)]
+        t = Tarok(bots, 4096, seed=seed)
+        t.izpis = False
+        t.paralel_start()
+        res.append([t.rezultati[b] for b in bots])
+    assert res[0] == res[2] and res[0] != res[1]
+    assert len(I._OKOLJA) == 1
+    env = next(iter(I._OKOLJA.values()))
+    t = Tarok([Bot_igralec() for _ in range(4)], 1000, seed=5)        # another batch size: a new environment replaces the old one
+    t.izpis = False
+    t.paralel_start()
+    assert next(iter(I._OKOLJA.values())) is not env and not env._h
+    I.sprosti_okolja()
+    assert not I._OKOLJA

@@ -697,6 +697,24 @@ def test_graph_backed_rollout_equals_plain_launches():
     a.close(); b.close()
 
 
+def test_reseed_equals_a_fresh_environment():
+    """tarok_reseed gives an existing handle a new run seed: every later draw (deal, bids, exchange, plays -- stepwise, graph-backed
+    and fused) is the one a handle created with that seed makes, also right after rollouts under the old seed (stale graphs and
+    draw-cache entries must not leak through)."""
+    n = 20011
+    a = _env(n, seed=111, history=True)
+    for mode in (16, 18):
+        a.rollout(mode, first_game_id=4)                      # old seed: fills the graph cache and the draw cache
+    a.reseed(222)
+    b = _env(n, seed=222, history=True)
+    for mode, fused in ((16, False), (18, False), (16, True)):
+        a.reset_stats(); b.reset_stats()
+        a.rollout(mode, first_game_id=4, fused=fused); b.rollout(mode, first_game_id=4, fused=fused)
+        assert (a.hist[:, :n] == b.hist[:, :n]).all() and (u64(a.scores) == u64(b.scores)).all(), (mode, fused)
+        assert (a.stats()[:21] == b.stats()[:21]).all()
+    a.close(); b.close()
+
+
 def test_pipeline_is_cuda_graph_capturable():
     """Every entry point only enqueues stream-ordered work (incl. the programmatic-dependent-launch chain of play_steps), so a
     caller can capture deal -> 48 steps -> score into a CUDA graph and replay it."""
