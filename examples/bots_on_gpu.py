@@ -12,9 +12,10 @@ from tarok_b200 import Bot_igralec, Tarok
 
 if __name__ == "__main__":
     igralci = [Bot_igralec() for _ in range(4)]
-    for poskus in ("first call (includes CUDA start-up and the buffer allocation)", "second call"):
+    for poskus in ("first call (includes CUDA start-up and the buffer allocation)",
+                   "second call (the device environment is kept between calls)"):
         t = Tarok(igralci, 1_000_000, seed=2026)
         t0 = time.time()
         t.paralel_start()                   # prints t.rezultati like the reference
-        print("Time need for 1000000 game: %.3f s -- %s" % (time.time() - t0, poskus))
+        print("Time need for 1000000 game: %.4f s -- %s" % (time.time() - t0, poskus))
     print("contract histogram (Klop, Tri, Dve, Ena, ...):", t.statistika[8:18].tolist())
